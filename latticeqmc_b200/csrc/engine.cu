@@ -1,0 +1,433 @@
+// C-ABI implementation of the B200 sweep engine (include/lqmc_b200.h).
+//
+// Host side of the drop-in boundary: owns the device state of `n_chains` Markov chains, converts
+// between the reference's host layouts (Configuration.config, (gf_up, gf_dn)) and the kernels'
+// padded device layouts, and launches the sweep kernels.  No CPU fallback exists: every entry
+// point that computes launches a CUDA kernel or fails.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <stdarg.h>
+#include <vector>
+#include <new>
+
+#include "../../include/lqmc_b200.h"
+#include "sweep_reg.cuh"
+#include "sweep_l2.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t err__ = (call);                                                                    \
+    if (err__ != cudaSuccess)                                                                      \
+      return fail(LQMC_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(err__), __FILE__, __LINE__); \
+  } while (0)
+
+}  // namespace
+
+struct lqmc_engine {
+  int device = 0;
+  int N = 0, L = 0, C = 0, NP = 0;
+  uint32_t flags = 0;
+  bool family_reg = true;
+  double lamb = 0;
+  double hs[4] = {1, 1, 0, 0};
+  cudaStream_t stream = nullptr;
+  // device state
+  double *dE = nullptr, *dEt = nullptr, *dEi = nullptr, *dEit = nullptr;
+  int8_t* dField = nullptr;
+  double* dG = nullptr;
+  double* dGsum = nullptr;
+  double* dObs = nullptr;
+  long long* dNmeas = nullptr;
+  long long* dNacc = nullptr;
+  double* dUni = nullptr;   size_t uniCap = 0;     // staged host uniforms
+  double* dTrRatio = nullptr; uint8_t* dTrAcc = nullptr; size_t trCap = 0; size_t trCount = 0;
+  lqmc::L2Workspace l2;
+  long long sweep_counter = 0;
+  long long chain0 = 0;
+  long long launches = 0;
+  std::vector<int8_t> hostField;   // staging for layout conversion
+  std::vector<double> hostG;
+};
+
+namespace {
+
+size_t field_bytes(const lqmc_engine* e) { return (size_t)e->C * e->L * e->NP; }
+size_t g_elems(const lqmc_engine* e) { return (size_t)e->C * 2 * e->NP * e->NP; }
+
+int ensure_trace(lqmc_engine* e, size_t count) {
+  if (!(e->flags & LQMC_TRACE)) { e->trCount = 0; return LQMC_OK; }
+  if (count > e->trCap) {
+    if (e->dTrRatio) cudaFree(e->dTrRatio);
+    if (e->dTrAcc) cudaFree(e->dTrAcc);
+    e->dTrRatio = nullptr; e->dTrAcc = nullptr; e->trCap = 0;
+    CU(cudaMalloc(&e->dTrRatio, count * sizeof(double)));
+    CU(cudaMalloc(&e->dTrAcc, count));
+    e->trCap = count;
+  }
+  e->trCount = count;
+  return LQMC_OK;
+}
+
+int stage_uniforms(lqmc_engine* e, const double* host, size_t count, cudaStream_t s) {
+  if (count > e->uniCap) {
+    if (e->dUni) cudaFree(e->dUni);
+    e->dUni = nullptr; e->uniCap = 0;
+    CU(cudaMalloc(&e->dUni, count * sizeof(double)));
+    e->uniCap = count;
+  }
+  CU(cudaMemcpyAsync(e->dUni, host, count * sizeof(double), cudaMemcpyHostToDevice, s));
+  return LQMC_OK;
+}
+
+template <int NP>
+int launch_reg(lqmc_engine* e, const lqmc::SweepParams& p, cudaStream_t s) {
+  const bool exact = !(e->flags & LQMC_ARITH_FMA);
+  const bool phys = (e->flags & LQMC_MODE_PHYSICS) != 0;
+  const size_t smem = lqmc::RegCfg<NP>::smem_bytes;
+  auto go = [&](auto kernel) -> int {
+    CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kernel<<<e->C, 128, smem, s>>>(p);
+    CU(cudaGetLastError());
+    e->launches += 1;
+    return LQMC_OK;
+  };
+  if (exact && !phys) return go(lqmc::sweep_reg_kernel<NP, true, false>);
+  if (!exact && !phys) return go(lqmc::sweep_reg_kernel<NP, false, false>);
+  if (exact && phys) return go(lqmc::sweep_reg_kernel<NP, true, true>);
+  return go(lqmc::sweep_reg_kernel<NP, false, true>);
+}
+
+// One entry for every phase combination: n_sweeps x [recompute?] + steps [step_lo, step_hi) x [propose?][wrap?]
+int run(lqmc_engine* e, int n_sweeps, int step_lo, int step_hi, bool recompute, bool propose, bool wrap, bool measure,
+        int l0, const double* d_uniforms, uint64_t seed, cudaStream_t s) {
+  CU(cudaSetDevice(e->device));
+  lqmc::SweepParams p;
+  memset(&p, 0, sizeof(p));
+  p.n_sites = e->N; p.n_slices = e->L; p.n_chains = e->C;
+  p.E = e->dE; p.Et = e->dEt; p.Ei = e->dEi; p.Eit = e->dEit;
+  p.field = e->dField; p.G = e->dG;
+  p.uniforms = d_uniforms; p.seed = seed;
+  p.sweep0 = e->sweep_counter; p.chain0 = e->chain0;
+  p.g_sum = e->dGsum; p.obs_sum = e->dObs; p.n_meas = e->dNmeas; p.n_acc = e->dNacc;
+  p.n_sweeps = n_sweeps; p.step_lo = step_lo; p.step_hi = step_hi;
+  p.do_recompute = recompute; p.do_propose = propose; p.do_wrap = wrap; p.measure = measure; p.recompute_l0 = l0;
+  p.exp_pl = e->hs[0]; p.exp_ml = e->hs[1]; p.f_p2 = e->hs[2]; p.f_m2 = e->hs[3];
+  if (propose) {
+    const size_t count = (size_t)e->C * n_sweeps * (step_hi - step_lo) * e->N;
+    int rc = ensure_trace(e, count);
+    if (rc) return rc;
+    if (e->flags & LQMC_TRACE) { p.tr_ratio = e->dTrRatio; p.tr_acc = e->dTrAcc; }
+  }
+  int rc;
+  if (e->family_reg) {
+    switch (e->NP) {
+      case 16: rc = launch_reg<16>(e, p, s); break;
+      case 32: rc = launch_reg<32>(e, p, s); break;
+      case 64: rc = launch_reg<64>(e, p, s); break;
+      default: return fail(LQMC_ERR_UNSUPPORTED, "no register-resident kernel for padded size %d", e->NP);
+    }
+  } else {
+    rc = lqmc::launch_l2(e->l2, p, e->flags, s, &e->launches, g_err, sizeof(g_err));
+    if (rc) return rc;
+  }
+  return rc;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* lqmc_last_error(void) { return g_err; }
+const char* lqmc_version(void) { return "lqmc_b200 0.1 (sm_100a)"; }
+
+int lqmc_create(lqmc_engine** out, int device, int n_sites, int n_slices, int n_chains, const double* exp_k,
+                const double* exp_k_inv, double lamb, const double hs_consts[4], uint32_t flags) {
+  if (!out) return fail(LQMC_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  if (n_sites < 1 || n_slices < 1 || n_chains < 1) return fail(LQMC_ERR_INVALID, "n_sites, n_slices, n_chains must be >= 1");
+  if (!exp_k || !exp_k_inv || !hs_consts) return fail(LQMC_ERR_INVALID, "exp_k / exp_k_inv / hs_consts is NULL");
+  int ndev = 0;
+  CU(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(LQMC_ERR_INVALID, "device %d out of range (%d visible)", device, ndev);
+  CU(cudaSetDevice(device));
+  lqmc_engine* e = new (std::nothrow) lqmc_engine();
+  if (!e) return fail(LQMC_ERR_NOMEM, "out of host memory");
+  e->device = device; e->N = n_sites; e->L = n_slices; e->C = n_chains; e->flags = flags; e->lamb = lamb;
+  memcpy(e->hs, hs_consts, sizeof(e->hs));
+  if (n_sites <= 64) {
+    e->family_reg = true;
+    e->NP = n_sites <= 16 ? 16 : (n_sites <= 32 ? 32 : 64);
+  } else {
+    e->family_reg = false;
+    e->NP = lqmc::l2_padded_size(n_sites);
+    if (e->NP <= 0) { delete e; return fail(LQMC_ERR_UNSUPPORTED, "n_sites = %d exceeds the largest supported lattice", n_sites); }
+  }
+  const int NP = e->NP, N = e->N;
+  auto cleanup = [&](int code) { lqmc_destroy(e); return code; };
+  if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) return cleanup(fail(LQMC_ERR_CUDA, "cudaStreamCreate failed"));
+  // identity-padded operator matrices and their transposes
+  std::vector<double> m((size_t)NP * NP), mt((size_t)NP * NP);
+  double** dst[4] = {&e->dE, &e->dEt, &e->dEi, &e->dEit};
+  for (int which = 0; which < 2; ++which) {
+    const double* src = which ? exp_k_inv : exp_k;
+    for (int i = 0; i < NP; ++i)
+      for (int j = 0; j < NP; ++j) {
+        const double v = (i < N && j < N) ? src[(size_t)i * N + j] : (i == j ? 1.0 : 0.0);
+        m[(size_t)i * NP + j] = v;
+        mt[(size_t)j * NP + i] = v;
+      }
+    for (int tr = 0; tr < 2; ++tr) {
+      double** d = dst[2 * which + tr];
+      if (cudaMalloc(d, sizeof(double) * NP * NP) != cudaSuccess) return cleanup(fail(LQMC_ERR_NOMEM, "cudaMalloc(E) failed"));
+      if (cudaMemcpy(*d, tr ? mt.data() : m.data(), sizeof(double) * NP * NP, cudaMemcpyHostToDevice) != cudaSuccess)
+        return cleanup(fail(LQMC_ERR_CUDA, "upload of exp_k failed"));
+    }
+  }
+  const size_t nG = g_elems(e);
+  if (cudaMalloc(&e->dField, field_bytes(e)) != cudaSuccess || cudaMalloc(&e->dG, nG * sizeof(double)) != cudaSuccess ||
+      cudaMalloc(&e->dGsum, (size_t)e->C * 2 * N * N * sizeof(double)) != cudaSuccess ||
+      cudaMalloc(&e->dObs, (size_t)e->C * 3 * N * sizeof(double)) != cudaSuccess ||
+      cudaMalloc(&e->dNmeas, (size_t)e->C * sizeof(long long)) != cudaSuccess ||
+      cudaMalloc(&e->dNacc, (size_t)e->C * sizeof(long long)) != cudaSuccess)
+    return cleanup(fail(LQMC_ERR_NOMEM, "cudaMalloc of chain state failed (%d chains, N=%d)", e->C, N));
+  cudaMemset(e->dField, 1, field_bytes(e));
+  cudaMemset(e->dG, 0, nG * sizeof(double));
+  if (!e->family_reg) {
+    int rc = lqmc::l2_alloc(e->l2, N, NP, e->L, e->C, g_err, sizeof(g_err));
+    if (rc) return cleanup(rc);
+  }
+  int rc = lqmc_reset_measurements(e);
+  if (rc) return cleanup(rc);
+  *out = e;
+  return LQMC_OK;
+}
+
+void lqmc_destroy(lqmc_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  void* ptrs[] = {e->dE, e->dEt, e->dEi, e->dEit, e->dField, e->dG, e->dGsum, e->dObs, e->dNmeas, e->dNacc, e->dUni, e->dTrRatio, e->dTrAcc};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  lqmc::l2_free(e->l2);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+int lqmc_set_field(lqmc_engine* e, const int8_t* field) {
+  if (!e || !field) return fail(LQMC_ERR_INVALID, "engine or field is NULL");
+  CU(cudaSetDevice(e->device));
+  const int N = e->N, L = e->L, NP = e->NP;
+  e->hostField.assign(field_bytes(e), 1);
+  for (int c = 0; c < e->C; ++c)
+    for (int i = 0; i < N; ++i)
+      for (int l = 0; l < L; ++l) {
+        const int8_t v = field[((size_t)c * N + i) * L + l];
+        if (v != 1 && v != -1) return fail(LQMC_ERR_INVALID, "field[%d][%d][%d] = %d is not +-1", c, i, l, (int)v);
+        e->hostField[((size_t)c * L + l) * NP + i] = v;
+      }
+  CU(cudaMemcpyAsync(e->dField, e->hostField.data(), field_bytes(e), cudaMemcpyHostToDevice, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  return LQMC_OK;
+}
+
+int lqmc_get_field(lqmc_engine* e, int8_t* field) {
+  if (!e || !field) return fail(LQMC_ERR_INVALID, "engine or field is NULL");
+  CU(cudaSetDevice(e->device));
+  const int N = e->N, L = e->L, NP = e->NP;
+  e->hostField.resize(field_bytes(e));
+  CU(cudaMemcpyAsync(e->hostField.data(), e->dField, field_bytes(e), cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  for (int c = 0; c < e->C; ++c)
+    for (int i = 0; i < N; ++i)
+      for (int l = 0; l < L; ++l) field[((size_t)c * N + i) * L + l] = e->hostField[((size_t)c * L + l) * NP + i];
+  return LQMC_OK;
+}
+
+int lqmc_set_g(lqmc_engine* e, const double* g) {
+  if (!e || !g) return fail(LQMC_ERR_INVALID, "engine or g is NULL");
+  CU(cudaSetDevice(e->device));
+  const int N = e->N, NP = e->NP;
+  e->hostG.assign(g_elems(e), 0.0);
+  for (size_t m = 0; m < (size_t)e->C * 2; ++m) {
+    double* dst = e->hostG.data() + m * NP * NP;
+    for (int i = 0; i < NP; ++i) dst[(size_t)i * NP + i] = 1.0;
+    for (int i = 0; i < N; ++i) memcpy(dst + (size_t)i * NP, g + (m * N + i) * N, sizeof(double) * N);
+  }
+  CU(cudaMemcpyAsync(e->dG, e->hostG.data(), g_elems(e) * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  return LQMC_OK;
+}
+
+int lqmc_get_g(lqmc_engine* e, double* g) {
+  if (!e || !g) return fail(LQMC_ERR_INVALID, "engine or g is NULL");
+  CU(cudaSetDevice(e->device));
+  const int N = e->N, NP = e->NP;
+  e->hostG.resize(g_elems(e));
+  CU(cudaMemcpyAsync(e->hostG.data(), e->dG, g_elems(e) * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  for (size_t m = 0; m < (size_t)e->C * 2; ++m)
+    for (int i = 0; i < N; ++i) memcpy(g + (m * N + i) * N, e->hostG.data() + m * NP * NP + (size_t)i * NP, sizeof(double) * N);
+  return LQMC_OK;
+}
+
+int lqmc_recompute(lqmc_engine* e, int l0) {
+  if (!e) return fail(LQMC_ERR_INVALID, "engine is NULL");
+  if (l0 < 0 || l0 >= e->L) return fail(LQMC_ERR_INVALID, "l0 = %d outside [0, %d)", l0, e->L);
+  int rc = run(e, 1, 0, 0, true, false, false, false, l0, nullptr, 0, e->stream);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(e->stream));
+  return LQMC_OK;
+}
+
+int lqmc_slice(lqmc_engine* e, int l, const double* uniforms, uint64_t seed) {
+  if (!e) return fail(LQMC_ERR_INVALID, "engine is NULL");
+  if (l < 0 || l >= e->L) return fail(LQMC_ERR_INVALID, "slice %d outside [0, %d)", l, e->L);
+  const int step = e->L - 1 - l;
+  const double* d_u = nullptr;
+  if (uniforms) {
+    int rc = stage_uniforms(e, uniforms, (size_t)e->C * e->N, e->stream);
+    if (rc) return rc;
+    d_u = e->dUni;
+  }
+  int rc = run(e, 1, step, step + 1, false, true, false, false, 0, d_u, seed, e->stream);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(e->stream));
+  return LQMC_OK;
+}
+
+int lqmc_wrap(lqmc_engine* e, int l) {
+  if (!e) return fail(LQMC_ERR_INVALID, "engine is NULL");
+  if (l < 1 || l >= e->L) return fail(LQMC_ERR_INVALID, "wrap needs 1 <= l < %d, got %d", e->L, l);
+  const int step = e->L - 1 - l;
+  int rc = run(e, 1, step, step + 1, false, false, true, false, 0, nullptr, 0, e->stream);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(e->stream));
+  return LQMC_OK;
+}
+
+int lqmc_sweep_async(lqmc_engine* e, int n_sweeps, const double* d_uniforms, uint64_t seed, int measure, void* stream) {
+  if (!e) return fail(LQMC_ERR_INVALID, "engine is NULL");
+  if (n_sweeps < 0) return fail(LQMC_ERR_INVALID, "n_sweeps = %d is negative", n_sweeps);
+  if (n_sweeps == 0) return LQMC_OK;
+  cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
+  const bool phys = (e->flags & LQMC_MODE_PHYSICS) != 0;
+  int rc = run(e, n_sweeps, 0, e->L, true, true, true, measure != 0, phys ? e->L - 1 : 0, d_uniforms, seed, s);
+  if (rc) return rc;
+  e->sweep_counter += n_sweeps;
+  return LQMC_OK;
+}
+
+int lqmc_sync(lqmc_engine* e) {
+  if (!e) return fail(LQMC_ERR_INVALID, "engine is NULL");
+  CU(cudaSetDevice(e->device));
+  CU(cudaStreamSynchronize(e->stream));
+  CU(cudaDeviceSynchronize());
+  return LQMC_OK;
+}
+
+int lqmc_sweep(lqmc_engine* e, int n_sweeps, const double* uniforms, uint64_t seed, int measure) {
+  if (!e) return fail(LQMC_ERR_INVALID, "engine is NULL");
+  if (n_sweeps < 0) return fail(LQMC_ERR_INVALID, "n_sweeps = %d is negative", n_sweeps);
+  if (n_sweeps == 0) return LQMC_OK;
+  CU(cudaSetDevice(e->device));
+  const double* d_u = nullptr;
+  if (uniforms) {
+    int rc = stage_uniforms(e, uniforms, (size_t)e->C * n_sweeps * e->L * e->N, e->stream);
+    if (rc) return rc;
+    d_u = e->dUni;
+  }
+  int rc = lqmc_sweep_async(e, n_sweeps, d_u, seed, measure, e->stream);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(e->stream));
+  return LQMC_OK;
+}
+
+int lqmc_get_trace(lqmc_engine* e, uint8_t* acc, double* ratio) {
+  if (!e) return fail(LQMC_ERR_INVALID, "engine is NULL");
+  if (!(e->flags & LQMC_TRACE)) return fail(LQMC_ERR_INVALID, "engine was created without LQMC_TRACE");
+  CU(cudaSetDevice(e->device));
+  if (acc) CU(cudaMemcpy(acc, e->dTrAcc, e->trCount, cudaMemcpyDeviceToHost));
+  if (ratio) CU(cudaMemcpy(ratio, e->dTrRatio, e->trCount * sizeof(double), cudaMemcpyDeviceToHost));
+  return LQMC_OK;
+}
+
+int lqmc_get_measurements(lqmc_engine* e, double* g_sum, double* obs_sum, int64_t* n_meas, int64_t* n_accepted) {
+  if (!e) return fail(LQMC_ERR_INVALID, "engine is NULL");
+  CU(cudaSetDevice(e->device));
+  CU(cudaStreamSynchronize(e->stream));
+  const size_t C = e->C, N = e->N;
+  if (g_sum) CU(cudaMemcpy(g_sum, e->dGsum, C * 2 * N * N * sizeof(double), cudaMemcpyDeviceToHost));
+  if (obs_sum) CU(cudaMemcpy(obs_sum, e->dObs, C * 3 * N * sizeof(double), cudaMemcpyDeviceToHost));
+  if (n_meas) CU(cudaMemcpy(n_meas, e->dNmeas, C * sizeof(long long), cudaMemcpyDeviceToHost));
+  if (n_accepted) CU(cudaMemcpy(n_accepted, e->dNacc, C * sizeof(long long), cudaMemcpyDeviceToHost));
+  return LQMC_OK;
+}
+
+int lqmc_reset_measurements(lqmc_engine* e) {
+  if (!e) return fail(LQMC_ERR_INVALID, "engine is NULL");
+  CU(cudaSetDevice(e->device));
+  const size_t C = e->C, N = e->N;
+  CU(cudaMemset(e->dGsum, 0, C * 2 * N * N * sizeof(double)));
+  CU(cudaMemset(e->dObs, 0, C * 3 * N * sizeof(double)));
+  CU(cudaMemset(e->dNmeas, 0, C * sizeof(long long)));
+  CU(cudaMemset(e->dNacc, 0, C * sizeof(long long)));
+  return LQMC_OK;
+}
+
+int lqmc_device_ptr(lqmc_engine* e, int which, void** ptr, uint64_t* n_bytes) {
+  if (!e || !ptr) return fail(LQMC_ERR_INVALID, "engine or ptr is NULL");
+  const size_t C = e->C, N = e->N;
+  size_t bytes = 0;
+  switch (which) {
+    case 0: *ptr = e->dField; bytes = field_bytes(e); break;
+    case 1: *ptr = e->dG; bytes = g_elems(e) * sizeof(double); break;
+    case 2: *ptr = e->dGsum; bytes = C * 2 * N * N * sizeof(double); break;
+    case 3: *ptr = e->dObs; bytes = C * 3 * N * sizeof(double); break;
+    case 4: *ptr = e->dNmeas; bytes = C * sizeof(long long); break;
+    case 5: *ptr = e->dNacc; bytes = C * sizeof(long long); break;
+    default: return fail(LQMC_ERR_INVALID, "unknown buffer id %d", which);
+  }
+  if (n_bytes) *n_bytes = bytes;
+  return LQMC_OK;
+}
+
+int lqmc_info(lqmc_engine* e, int* n_pad, int64_t* sweep_counter, int64_t* launches, char family[8]) {
+  if (!e) return fail(LQMC_ERR_INVALID, "engine is NULL");
+  if (n_pad) *n_pad = e->NP;
+  if (sweep_counter) *sweep_counter = e->sweep_counter;
+  if (launches) *launches = e->launches;
+  if (family) { memset(family, 0, 8); strncpy(family, e->family_reg ? "reg" : "l2", 7); }
+  return LQMC_OK;
+}
+
+int lqmc_set_sweep_counter(lqmc_engine* e, int64_t counter) {
+  if (!e) return fail(LQMC_ERR_INVALID, "engine is NULL");
+  e->sweep_counter = counter;
+  return LQMC_OK;
+}
+
+int lqmc_set_chain_offset(lqmc_engine* e, int64_t chain0) {
+  if (!e) return fail(LQMC_ERR_INVALID, "engine is NULL");
+  e->chain0 = chain0;
+  return LQMC_OK;
+}
+
+void lqmc_philox_uniforms(uint64_t seed, uint64_t chain, uint64_t sweep, int n_proposals, double* out) {
+  for (int p = 0; p < n_proposals; ++p) out[p] = lqmc_philox_uniform(seed, chain, sweep, (uint32_t)p);
+}
+
+}  // extern "C"

@@ -1,0 +1,268 @@
+"""ctypes binding of the C-ABI sweep engine (`include/lqmc_b200.h`) - the only compute path.
+
+There is no CPU fallback: if `liblqmc_b200.so` is missing or no CUDA device is visible, creating a
+`SweepEngine` raises.  (The NumPy restatement under `oracle/` is test infrastructure and is never
+imported from here.)
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liblqmc_b200.so")
+
+MODE_PARITY = 0x0
+MODE_PHYSICS = 0x1
+ARITH_EXACT = 0x0
+ARITH_FMA = 0x2
+TRACE = 0x4
+
+EXPORTS = (
+    "lqmc_create", "lqmc_destroy", "lqmc_set_field", "lqmc_get_field", "lqmc_set_g", "lqmc_get_g",
+    "lqmc_recompute", "lqmc_slice", "lqmc_wrap", "lqmc_sweep", "lqmc_sweep_async", "lqmc_sync",
+    "lqmc_get_trace", "lqmc_get_measurements", "lqmc_reset_measurements", "lqmc_device_ptr", "lqmc_info",
+    "lqmc_set_sweep_counter", "lqmc_set_chain_offset", "lqmc_philox_uniforms", "lqmc_last_error",
+    "lqmc_version",
+)
+
+
+class EngineError(RuntimeError):
+    """A C-ABI call returned a non-zero status.  LQMC_ERR_INVALID maps to ValueError instead,
+    mirroring the plain Python exceptions the reference raises on bad arguments."""
+
+
+_lib = None
+
+
+def load_library(path=None):
+    """dlopen the engine and declare every prototype of include/lqmc_b200.h."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or LIB_PATH
+    if not os.path.isfile(path):
+        raise EngineError(f"{path} not found - build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          f"(nvcc, sm_100a); there is no CPU fallback")
+    lib = ctypes.CDLL(path)
+    c_dp = ctypes.POINTER(ctypes.c_double)
+    vp = ctypes.c_void_p
+    lib.lqmc_create.argtypes = [ctypes.POINTER(vp), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                c_dp, c_dp, ctypes.c_double, c_dp, ctypes.c_uint32]
+    lib.lqmc_destroy.argtypes = [vp]
+    lib.lqmc_destroy.restype = None
+    lib.lqmc_set_field.argtypes = [vp, vp]
+    lib.lqmc_get_field.argtypes = [vp, vp]
+    lib.lqmc_set_g.argtypes = [vp, vp]
+    lib.lqmc_get_g.argtypes = [vp, vp]
+    lib.lqmc_recompute.argtypes = [vp, ctypes.c_int]
+    lib.lqmc_slice.argtypes = [vp, ctypes.c_int, vp, ctypes.c_uint64]
+    lib.lqmc_wrap.argtypes = [vp, ctypes.c_int]
+    lib.lqmc_sweep.argtypes = [vp, ctypes.c_int, vp, ctypes.c_uint64, ctypes.c_int]
+    lib.lqmc_sweep_async.argtypes = [vp, ctypes.c_int, vp, ctypes.c_uint64, ctypes.c_int, vp]
+    lib.lqmc_sync.argtypes = [vp]
+    lib.lqmc_get_trace.argtypes = [vp, vp, vp]
+    lib.lqmc_get_measurements.argtypes = [vp, vp, vp, vp, vp]
+    lib.lqmc_reset_measurements.argtypes = [vp]
+    lib.lqmc_device_ptr.argtypes = [vp, ctypes.c_int, ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_uint64)]
+    lib.lqmc_info.argtypes = [vp, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int64),
+                              ctypes.POINTER(ctypes.c_int64), ctypes.c_char_p]
+    lib.lqmc_set_sweep_counter.argtypes = [vp, ctypes.c_int64]
+    lib.lqmc_set_chain_offset.argtypes = [vp, ctypes.c_int64]
+    lib.lqmc_philox_uniforms.argtypes = [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int, c_dp]
+    lib.lqmc_philox_uniforms.restype = None
+    lib.lqmc_last_error.restype = ctypes.c_char_p
+    lib.lqmc_version.restype = ctypes.c_char_p
+    for name in EXPORTS:
+        fn = getattr(lib, name)
+        if fn.restype is ctypes.c_int and name not in ("lqmc_destroy", "lqmc_philox_uniforms"):
+            fn.restype = ctypes.c_int
+    if path == LIB_PATH:
+        _lib = lib
+    return lib
+
+
+def philox_uniforms(seed, chain, sweep, n_proposals):
+    """Host evaluation of the device RNG stream (visiting order) - lets tests feed the oracle the
+    very numbers a Philox-mode sweep consumed."""
+    out = np.empty(n_proposals, dtype=np.float64)
+    load_library().lqmc_philox_uniforms(seed, chain, sweep, n_proposals, out.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
+    return out
+
+
+def hs_constants(lamb):
+    """The four exponentials the sweep needs, evaluated with the NumPy calls the reference makes:
+    `np.exp(-1 * sigma * lamb * config[:, l])` on an int8 column for exp(-+lamb) (lqmc.py:149,154) and
+    `np.exp(+-arg) - 1` with the scalar `arg = 2 * lamb * config[i, l]` (lqmc.py:313-323)."""
+    col = np.array([-1, 1], dtype=np.int8)
+    ev = np.exp(-1 * 1 * lamb * col)          # [exp(+lamb), exp(-lamb)]
+    arg = 2 * lamb * col[1]
+    return np.array([ev[0], ev[1], np.exp(+arg) - 1, np.exp(-arg) - 1], dtype=np.float64)
+
+
+class SweepEngine:
+    """`n_chains` independent Markov chains of one model on one CUDA device.
+
+    Parameters mirror what `LatticeQMC.set_beta` caches (lqmc.py:93-117): `exp_k = expm(-dtau K)`,
+    `lamb`.  `exp_k_inv` defaults to `np.linalg.inv(exp_k)`.
+    """
+
+    def __init__(self, exp_k, lamb, n_slices, n_chains=1, exp_k_inv=None, device=0, mode="parity",
+                 arith="exact", trace=False, chain_offset=0):
+        self._lib = load_library()
+        self._h = ctypes.c_void_p()
+        exp_k = np.ascontiguousarray(exp_k, dtype=np.float64)
+        if exp_k.ndim != 2 or exp_k.shape[0] != exp_k.shape[1]:
+            raise ValueError("exp_k must be a square matrix")
+        if exp_k_inv is None:
+            exp_k_inv = np.linalg.inv(exp_k)
+        exp_k_inv = np.ascontiguousarray(exp_k_inv, dtype=np.float64)
+        if mode not in ("parity", "physics"):
+            raise ValueError("mode must be 'parity' or 'physics'")
+        if arith not in ("exact", "fma"):
+            raise ValueError("arith must be 'exact' or 'fma'")
+        flags = (MODE_PHYSICS if mode == "physics" else MODE_PARITY) | (ARITH_FMA if arith == "fma" else ARITH_EXACT)
+        if trace:
+            flags |= TRACE
+        self.n_sites = int(exp_k.shape[0])
+        self.n_slices = int(n_slices)
+        self.n_chains = int(n_chains)
+        self.mode, self.arith, self.trace = mode, arith, bool(trace)
+        self.lamb = float(lamb)
+        self.device = int(device)
+        hs = hs_constants(self.lamb)
+        dp = ctypes.POINTER(ctypes.c_double)
+        self._check(self._lib.lqmc_create(ctypes.byref(self._h), self.device, self.n_sites, self.n_slices,
+                                          self.n_chains, exp_k.ctypes.data_as(dp), exp_k_inv.ctypes.data_as(dp),
+                                          self.lamb, hs.ctypes.data_as(dp), flags))
+        if chain_offset:
+            self.set_chain_offset(chain_offset)
+        self._last_trace_shape = None
+
+    # -- plumbing ------------------------------------------------------------------------------
+    def _check(self, rc):
+        if rc == 0:
+            return
+        msg = self._lib.lqmc_last_error().decode()
+        if rc == 1:
+            raise ValueError(msg)
+        raise EngineError(f"lqmc_b200 error {rc}: {msg}")
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.lqmc_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- state ---------------------------------------------------------------------------------
+    def set_field(self, field):
+        """`field`: int8 `(n_chains, N, L)` (or `(N, L)` for one chain) - stacked
+        `Configuration.config` arrays."""
+        f = np.ascontiguousarray(field, dtype=np.int8).reshape(self.n_chains, self.n_sites, self.n_slices)
+        self._check(self._lib.lqmc_set_field(self._h, f.ctypes.data))
+
+    def get_field(self):
+        out = np.empty((self.n_chains, self.n_sites, self.n_slices), dtype=np.int8)
+        self._check(self._lib.lqmc_get_field(self._h, out.ctypes.data))
+        return out
+
+    def set_g(self, g):
+        g = np.ascontiguousarray(g, dtype=np.float64).reshape(self.n_chains, 2, self.n_sites, self.n_sites)
+        self._check(self._lib.lqmc_set_g(self._h, g.ctypes.data))
+
+    def get_g(self):
+        out = np.empty((self.n_chains, 2, self.n_sites, self.n_sites), dtype=np.float64)
+        self._check(self._lib.lqmc_get_g(self._h, out.ctypes.data))
+        return out
+
+    # -- phases --------------------------------------------------------------------------------
+    def recompute(self, l0=0):
+        self._check(self._lib.lqmc_recompute(self._h, int(l0)))
+
+    def slice(self, l, uniforms=None, seed=0):
+        ptr = None
+        if uniforms is not None:
+            u = np.ascontiguousarray(uniforms, dtype=np.float64).reshape(self.n_chains, self.n_sites)
+            ptr = u.ctypes.data
+        self._check(self._lib.lqmc_slice(self._h, int(l), ptr, int(seed)))
+        self._last_trace_shape = (self.n_chains, 1, 1, self.n_sites)
+
+    def wrap(self, l):
+        self._check(self._lib.lqmc_wrap(self._h, int(l)))
+
+    def sweep(self, n_sweeps=1, uniforms=None, seed=0, measure=False):
+        """`n_sweeps` x `LatticeQMC._update_step`.  `uniforms`: `(n_chains, n_sweeps, L, N)` in
+        visiting order, or None for the device Philox stream."""
+        ptr = None
+        if uniforms is not None:
+            u = np.ascontiguousarray(uniforms, dtype=np.float64).reshape(self.n_chains, n_sweeps, self.n_slices, self.n_sites)
+            ptr = u.ctypes.data
+        self._check(self._lib.lqmc_sweep(self._h, int(n_sweeps), ptr, int(seed), int(bool(measure))))
+        self._last_trace_shape = (self.n_chains, int(n_sweeps), self.n_slices, self.n_sites)
+
+    def sweep_async(self, n_sweeps=1, d_uniforms=0, seed=0, measure=False, stream=0):
+        """Device-resident variant: `d_uniforms` is a raw device pointer (0 = Philox), `stream` a raw
+        cudaStream_t (0 = the engine's stream).  Returns immediately; call `sync()`."""
+        self._check(self._lib.lqmc_sweep_async(self._h, int(n_sweeps), ctypes.c_void_p(d_uniforms or None), int(seed),
+                                               int(bool(measure)), ctypes.c_void_p(stream or None)))
+        self._last_trace_shape = (self.n_chains, int(n_sweeps), self.n_slices, self.n_sites)
+
+    def sync(self):
+        self._check(self._lib.lqmc_sync(self._h))
+
+    def get_trace(self):
+        """`(acc bool, ratio float64)` of the last sweep/slice call, shape `(chains, sweeps, steps, N)`."""
+        shape = self._last_trace_shape
+        if shape is None:
+            raise ValueError("no sweep or slice has run yet")
+        acc = np.empty(shape, dtype=np.uint8)
+        ratio = np.empty(shape, dtype=np.float64)
+        self._check(self._lib.lqmc_get_trace(self._h, acc.ctypes.data, ratio.ctypes.data))
+        return acc.astype(bool), ratio
+
+    # -- measurements --------------------------------------------------------------------------
+    def get_measurements(self):
+        """dict with `g_sum (C,2,N,N)`, `obs_sum (C,3,N)`, `n_meas (C,)`, `n_accepted (C,)`."""
+        c, n = self.n_chains, self.n_sites
+        g_sum = np.empty((c, 2, n, n), dtype=np.float64)
+        obs = np.empty((c, 3, n), dtype=np.float64)
+        n_meas = np.empty(c, dtype=np.int64)
+        n_acc = np.empty(c, dtype=np.int64)
+        self._check(self._lib.lqmc_get_measurements(self._h, g_sum.ctypes.data, obs.ctypes.data, n_meas.ctypes.data,
+                                                    n_acc.ctypes.data))
+        return dict(g_sum=g_sum, obs_sum=obs, n_meas=n_meas, n_accepted=n_acc)
+
+    def reset_measurements(self):
+        self._check(self._lib.lqmc_reset_measurements(self._h))
+
+    def device_ptr(self, which):
+        """Raw `(pointer, n_bytes)` of an engine buffer (see lqmc_device_ptr)."""
+        ptr = ctypes.c_void_p()
+        nbytes = ctypes.c_uint64()
+        self._check(self._lib.lqmc_device_ptr(self._h, int(which), ctypes.byref(ptr), ctypes.byref(nbytes)))
+        return ptr.value, nbytes.value
+
+    def info(self):
+        n_pad = ctypes.c_int()
+        counter = ctypes.c_int64()
+        launches = ctypes.c_int64()
+        fam = ctypes.create_string_buffer(8)
+        self._check(self._lib.lqmc_info(self._h, ctypes.byref(n_pad), ctypes.byref(counter), ctypes.byref(launches), fam))
+        return dict(n_pad=n_pad.value, sweep_counter=counter.value, launches=launches.value, family=fam.value.decode())
+
+    def set_sweep_counter(self, counter):
+        self._check(self._lib.lqmc_set_sweep_counter(self._h, int(counter)))
+
+    def set_chain_offset(self, chain0):
+        self._check(self._lib.lqmc_set_chain_offset(self._h, int(chain0)))

@@ -1,0 +1,306 @@
+"""GPU parity: the CUDA sweep (through the C ABI) against the oracle and the golden vectors recorded
+from the reference (`/root/reference/lqmc/lqmc.py:301-347`).
+
+Bar (BASELINE.json north_star): same HS field + same uniforms => identical accept/reject sequence,
+and G within 1e-10 relative (of max|G|) in FP64.  Where that is achievable free-running is bounded
+by the reference recurrence's own roundoff amplification: free-running at cfg1 and
+the other small lattices; teacher-forced (reference's own G as input) at N=64 and above.  Inside a
+slice the EXACT arithmetic mode performs the reference's roundings operation by operation, so
+there the comparison is bit-for-bit.
+"""
+import numpy as np
+import pytest
+
+from oracle import sweep_oracle as so
+
+pytestmark = pytest.mark.gpu
+
+RTOL_G = 1e-10   # relative to max|G|, the north_star tolerance
+
+
+def _engine(exp_k, lamb, lt, **kw):
+    from latticeqmc_b200 import SweepEngine
+    return SweepEngine(exp_k, lamb, lt, **kw)
+
+
+def _close(a, b, rtol=RTOL_G):
+    return np.max(np.abs(a - b)) <= rtol * max(np.max(np.abs(b)), 1e-300)
+
+
+def _field_after(g, l):
+    """Field as it stood after the proposals of slice l in a recorded full sweep."""
+    lt = g["field0"].shape[1]
+    h = g["field0"].copy()
+    for step in range(lt - l):
+        h[g["accs"][step], lt - 1 - step] *= -1
+    return h
+
+
+# ------------------------------------------------------------------------------------------------
+# free-running, well-conditioned: cfg1 (BASELINE configs[0]) and the other small lattices
+# ------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("name", ["cfg1_2x2_free", "small_4x4_free", "small_3x2_free"])
+@pytest.mark.parametrize("arith", ["exact", "fma"])
+def test_free_running_small(golden, name, arith):
+    g = golden(name)
+    n, lt = g["field0"].shape
+    sweeps = g["uniforms"].shape[0]
+    with _engine(g["exp_k"], float(g["lamb"]), lt, trace=True, arith=arith) as eng:
+        eng.set_field(g["field0"][None])
+        # one launch per sweep so that every end-of-sweep G can be compared
+        for s in range(sweeps):
+            eng.sweep(1, g["uniforms"][s][None, None])
+            acc, ratio = eng.get_trace()
+            assert np.array_equal(acc[0, 0], g["accs"][s]), f"accept/reject differs in sweep {s}"
+            assert np.array_equal(eng.get_field()[0], g["fields"][s])
+            big = np.abs(g["ratios"][s]) > 1e-6     # tiny ratios are differences of O(1) numbers
+            assert np.allclose(ratio[0, 0][big], g["ratios"][s][big], rtol=1e-8)
+            gg = eng.get_g()[0]
+            assert _close(gg[0], g["gf_up"][s]) and _close(gg[1], g["gf_dn"][s]), f"G differs in sweep {s}"
+
+
+def test_cfg1_one_launch_many_sweeps(golden):
+    """All ten sweeps in ONE kernel launch (the way warm-up / measurement run) - same trace, and the
+    on-device accumulation equals measure_loop's (lqmc.py:364-375)."""
+    g = golden("cfg1_2x2_free")
+    n, lt = g["field0"].shape
+    with _engine(g["exp_k"], float(g["lamb"]), lt, trace=True) as eng:
+        eng.set_field(g["field0"][None])
+        eng.sweep(10, g["uniforms"][None], measure=True)
+        acc, _ = eng.get_trace()
+        assert np.array_equal(acc[0], g["accs"])
+        m = eng.get_measurements()
+        assert m["n_meas"][0] == 10
+        assert m["n_accepted"][0] == g["accs"].sum()
+        ref = np.stack([g["gf_up"].sum(0), g["gf_dn"].sum(0)])
+        assert _close(m["g_sum"][0], ref)
+        nu, nd = 1 - np.einsum("sii->si", g["gf_up"]), 1 - np.einsum("sii->si", g["gf_dn"])
+        assert np.allclose(m["obs_sum"][0, 0], nu.sum(0), rtol=1e-9, atol=1e-9 * np.abs(nu).max())
+        assert np.allclose(m["obs_sum"][0, 2], (nu * nd).sum(0), rtol=1e-8, atol=1e-8 * np.abs(nu * nd).max())
+
+
+def test_u0_known_answer(golden):
+    """exact.py:27-54: U=0 => lamb=0, every ratio exactly 1, all accepted, G = (I+exp(-beta K))^-1."""
+    g = golden("u0_chain10")
+    n, lt = g["field0"].shape
+    with _engine(g["exp_k"], float(g["lamb"]), lt, trace=True) as eng:
+        eng.set_field(g["field0"][None])
+        eng.sweep(1, g["uniforms"][None, None])
+        acc, ratio = eng.get_trace()
+        assert acc.all() and np.all(ratio == 1.0)
+        assert np.array_equal(eng.get_field()[0], -g["field0"])
+        gg = eng.get_g()[0]
+    assert np.max(np.abs(gg[0] - g["gf_up"])) < 1e-9 and np.max(np.abs(gg[1] - g["gf_dn"])) < 1e-9
+    assert np.max(np.abs(gg[0] + g["pole_gf_tau0"])) < 1e-9
+
+
+# ------------------------------------------------------------------------------------------------
+# phases one at a time (teacher-forced): recompute, slice, wrap
+# ------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("case", [("square", 2, 4.0, 2.0, 20), ("square", 4, 4.0, 2.0, 20), ("square", 6, 4.0, 1.0, 10),
+                                   ("square", 8, 4.0, 1.0, 10), ("ring", 10, 2.0, 1.0, 8), ("ring", 37, 2.0, 0.8, 8)])
+def test_recompute_matches_get_m_inverse(case):
+    """get_m + np.linalg.inv (lqmc.py:156-185,303-307) on well-conditioned products, incl. sizes that
+    need padding (N=36, 10, 37)."""
+    kind, size, u, beta, lt = case
+    ham = so.ideal_square_kinetic(size, 1.0, u / 2) if kind == "square" else so.ideal_ring_kinetic(size, 1.0, u / 2)
+    n = ham.shape[0]
+    dtau, lamb, exp_k = so.set_beta_constants(ham, u, beta, lt)
+    fields = np.stack([so.initial_field(n, lt, seed=100 + c) for c in range(3)])
+    with _engine(exp_k, lamb, lt, n_chains=3) as eng:
+        eng.set_field(fields)
+        eng.recompute(0)
+        gg = eng.get_g()
+        eng.recompute(lt - 1)
+        gl = eng.get_g()
+    for c in range(3):
+        ref = so.sweep_start_g(fields[c], exp_k, lamb)
+        cond = np.linalg.cond(so.get_m(fields[c], exp_k, lamb, 0, +1))
+        tol = max(RTOL_G, 50 * cond * 2.2e-16)
+        assert _close(gg[c, 0], ref[0], tol) and _close(gg[c, 1], ref[1], tol), (case, c, cond)
+        ref_l = np.linalg.inv(so.get_m(fields[c], exp_k, lamb, lt - 1, +1))
+        assert _close(gl[c, 0], ref_l, tol)
+
+
+@pytest.mark.parametrize("name,slices", [("cfg2_8x8_sweep", (39, 20, 1)), ("cfg3_ring64_sweep", (79, 40))])
+def test_n64_wrap_then_slice_teacher_forced(golden, name, slices):
+    """N=64 (BASELINE configs[1] and [2]): start from the REFERENCE's G after the proposals of slice
+    l, wrap to l-1, run the proposals of l-1: accept/reject identical, G within 1e-10 of the
+    reference's own snapshot."""
+    g = golden(name)
+    n, lt = g["field0"].shape
+    lamb = float(g["lamb"])
+    with _engine(g["exp_k"], lamb, lt, trace=True) as eng:
+        for l in slices:
+            h = _field_after(g, l)
+            eng.set_field(h[None])
+            eng.set_g(np.stack([g[f"post{l}_up"], g[f"post{l}_dn"]])[None])
+            eng.wrap(l)
+            w = eng.get_g()[0]
+            wu, wd = so.wrap(g[f"post{l}_up"], g[f"post{l}_dn"], h, l, g["exp_k"], lamb)
+            assert _close(w[0], wu) and _close(w[1], wd), f"wrap {l}"
+            step = lt - l
+            eng.slice(l - 1, g["uniforms"][step][None])
+            acc, ratio = eng.get_trace()
+            assert np.array_equal(acc[0, 0, 0], g["accs"][step]), f"accept/reject differs at slice {l - 1}"
+            out = eng.get_g()[0]
+            # amplification inside one slice is modest; the wrap's 1e-16-level differences grow to <1e-10
+            assert _close(out[0], g[f"post{l - 1}_up"], 1e-9) and _close(out[1], g[f"post{l - 1}_dn"], 1e-9)
+            assert np.array_equal(eng.get_field()[0], _field_after(g, l - 1))
+
+
+@pytest.mark.parametrize("name,l", [("cfg2_8x8_sweep", 38), ("cfg2_8x8_sweep", 19), ("cfg3_ring64_sweep", 39)])
+def test_slice_is_bit_exact_in_exact_mode(golden, name, l):
+    """Proposals only, G given: the EXACT mode performs the reference's roundings one by one
+    (lqmc.py:313-331), so ratios, decisions and the updated G are bit-identical to NumPy's."""
+    g = golden(name)
+    n, lt = g["field0"].shape
+    lamb = float(g["lamb"])
+    h = _field_after(g, l + 1)
+    gu, gd = so.wrap(g[f"post{l + 1}_up"], g[f"post{l + 1}_dn"], h, l + 1, g["exp_k"], lamb)
+    step = lt - 1 - l
+    with _engine(g["exp_k"], lamb, lt, trace=True) as eng:
+        eng.set_field(h[None])
+        eng.set_g(np.stack([gu, gd])[None])
+        eng.slice(l, g["uniforms"][step][None])
+        acc, ratio = eng.get_trace()
+        out = eng.get_g()[0]
+    ratios, accs = so.slice_proposals(gu, gd, h, l, lamb, g["uniforms"][step])
+    assert np.array_equal(acc[0, 0, 0], accs)
+    assert np.array_equal(ratio[0, 0, 0], ratios)
+    assert np.array_equal(out[0], gu) and np.array_equal(out[1], gd)
+
+
+def test_cfg2_full_sweep_teacher_forced_from_reference_g0(golden):
+    """8x8 beta=4: the sweep-start inverse is ill-conditioned (cond ~ 6e18), so the sweep
+    is started from the reference's own G0 and run slice by slice through the C ABI: the whole
+    accept/reject sequence of the sweep (2560 proposals) must match the reference."""
+    g = golden("cfg2_8x8_sweep")
+    n, lt = g["field0"].shape
+    lamb = float(g["lamb"])
+    with _engine(g["exp_k"], lamb, lt, trace=True) as eng:
+        eng.set_field(g["field0"][None])
+        eng.set_g(np.stack([g["g0_up"], g["g0_dn"]])[None])
+        for step in range(lt):
+            l = lt - 1 - step
+            eng.slice(l, g["uniforms"][step][None])
+            acc, _ = eng.get_trace()
+            assert np.array_equal(acc[0, 0, 0], g["accs"][step]), f"accept/reject differs at slice {l}"
+            if l > 0:
+                eng.wrap(l)
+        out = eng.get_g()[0]
+        assert np.array_equal(eng.get_field()[0], g["field1"])
+    # H8: 1e-16 grows to ~5e-7 in a beta=4 sweep; the end-of-sweep G is compared at that scale
+    assert _close(out[0], g["gf_up"], 1e-5) and _close(out[1], g["gf_dn"], 1e-5)
+
+
+# ------------------------------------------------------------------------------------------------
+# batch semantics
+# ------------------------------------------------------------------------------------------------
+
+def test_chains_are_independent(golden):
+    """A batch of chains equals the chains run one at a time (bitwise)."""
+    g = golden("small_4x4_free")
+    n, lt = g["field0"].shape
+    lamb = float(g["lamb"])
+    fields = np.stack([so.initial_field(n, lt, seed=s) for s in (1, 2, 3, 4, 5)])
+    uni = np.random.RandomState(9).rand(5, 2, lt, n)
+    with _engine(g["exp_k"], lamb, lt, n_chains=5, trace=True) as eng:
+        eng.set_field(fields)
+        eng.sweep(2, uni, measure=True)
+        acc_b, ratio_b = eng.get_trace()
+        g_b, f_b, m_b = eng.get_g(), eng.get_field(), eng.get_measurements()
+    for c in range(5):
+        with _engine(g["exp_k"], lamb, lt, n_chains=1, trace=True) as eng:
+            eng.set_field(fields[c][None])
+            eng.sweep(2, uni[c][None], measure=True)
+            acc, ratio = eng.get_trace()
+            assert np.array_equal(acc[0], acc_b[c]) and np.array_equal(ratio[0], ratio_b[c])
+            assert np.array_equal(eng.get_g()[0], g_b[c]) and np.array_equal(eng.get_field()[0], f_b[c])
+            assert np.array_equal(eng.get_measurements()["g_sum"][0], m_b["g_sum"][c])
+
+
+def test_philox_stream_matches_host_evaluation(golden):
+    """Device RNG mode: the uniforms the kernel draws are the ones `lqmc_philox_uniforms` reports;
+    feeding those to the oracle reproduces the device trace; chain_offset shifts the stream."""
+    from latticeqmc_b200 import philox_uniforms
+    g = golden("cfg1_2x2_free")
+    n, lt = g["field0"].shape
+    lamb = float(g["lamb"])
+    fields = np.stack([so.initial_field(n, lt, seed=s) for s in (7, 8)])
+    with _engine(g["exp_k"], lamb, lt, n_chains=2, trace=True, chain_offset=5) as eng:
+        eng.set_field(fields)
+        eng.sweep(3, None, seed=1234)
+        acc, ratio = eng.get_trace()
+        gg = eng.get_g()
+        assert eng.info()["sweep_counter"] == 3
+    for c in range(2):
+        h = fields[c].copy()
+        for s in range(3):
+            u = philox_uniforms(1234, 5 + c, s, n * lt).reshape(lt, n)
+            gu, gd, r, a = so.update_step(h, g["exp_k"], lamb, u)
+            assert np.array_equal(a, acc[c, s])
+        assert _close(gg[c, 0], gu) and _close(gg[c, 1], gd)
+
+
+def test_measure_accumulates_in_sweep_order(golden):
+    g = golden("small_3x2_free")
+    n, lt = g["field0"].shape
+    lamb = float(g["lamb"])
+    with _engine(g["exp_k"], lamb, lt) as eng:
+        eng.set_field(g["field0"][None])
+        tot = np.zeros((2, n, n))
+        for s in range(3):
+            eng.sweep(1, g["uniforms"][s][None, None])
+            tot += eng.get_g()[0]
+    with _engine(g["exp_k"], lamb, lt) as eng:
+        eng.set_field(g["field0"][None])
+        eng.sweep(3, g["uniforms"][None], measure=True)
+        m = eng.get_measurements()
+    assert np.array_equal(m["g_sum"][0], tot)
+
+
+# ------------------------------------------------------------------------------------------------
+# error behaviour at the boundary
+# ------------------------------------------------------------------------------------------------
+
+def test_bad_arguments_raise(golden):
+    g = golden("small_3x2_free")
+    n, lt = g["field0"].shape
+    with _engine(g["exp_k"], float(g["lamb"]), lt) as eng:
+        bad = g["field0"].copy()
+        bad[0, 0] = 0
+        with pytest.raises(ValueError):
+            eng.set_field(bad[None])
+        with pytest.raises(ValueError):
+            eng.slice(lt, None)
+        with pytest.raises(ValueError):
+            eng.wrap(0)
+        with pytest.raises(ValueError):
+            eng.get_trace()       # engine created without trace
+
+
+def test_drop_in_latticeqmc_update_step(golden):
+    """`lqmc.LatticeQMC._update_step()` as a drop-in: seeded global NumPy stream in, same field,
+    same (gf_up, gf_dn), same stream position out as the reference run recorded in the golden."""
+    import lqmc
+    g = golden("cfg1_2x2_free")
+    model = lqmc.HubbardModel(u=4, t=1)
+    model.build_square(2)
+    np.random.seed(11)
+    solver = lqmc.LatticeQMC(model, 2.0, 20, warmup=0, sweeps=0, log_lvl=None)
+    assert np.array_equal(solver.config.config, g["field0"])
+    assert np.array_equal(solver.exp_k, g["exp_k"]) and float(solver.lamb) == float(g["lamb"])
+    for s in range(4):
+        gu, gd = solver._update_step()
+        assert np.array_equal(solver.config.config, g["fields"][s])
+        assert _close(gu, g["gf_up"][s]) and _close(gd, g["gf_dn"][s])
+        assert solver.acc == bool(g["accs"][s, -1, -1])
+    # the global stream advanced by exactly 4*N*L draws
+    state = np.random.get_state()
+    np.random.seed(11)
+    np.random.randint(0, 2, size=(4, 20))
+    np.random.rand(4 * 80)
+    assert np.array_equal(np.random.get_state()[1], state[1]) and np.random.get_state()[2] == state[2]

@@ -1,0 +1,68 @@
+"""Host-side drop-in API: lattice / model / configuration behave like the reference's
+(`/root/reference/lqmc/{lattice,hubbard,configuration,tools}.py`)."""
+import numpy as np
+import pytest
+
+from oracle import sweep_oracle as so
+
+
+def test_kinetic_matches_reference_builder(golden):
+    from latticeqmc_b200 import HubbardModel
+    g = golden("lattice_ham")
+    for size in (2, 3, 4, 5, 8):
+        m = HubbardModel(u=4, t=1)
+        m.build_square(size)
+        assert np.array_equal(m.ham_kinetic(), g[f"square{size}"]), size
+    m = HubbardModel(u=8, t=1)
+    m.build(64)
+    assert np.array_equal(m.ham_kinetic(), g["ring64"])
+    m = HubbardModel(u=0, t=1, mu=0)
+    m.build(10, cycling=None)
+    assert np.array_equal(m.ham_kinetic(), g["open10"])
+    m = HubbardModel(u=6, t=1)
+    m.build(3, 2, cycling=0)
+    assert np.array_equal(m.ham_kinetic(), g["rect3x2_c0"])
+
+
+@pytest.mark.parametrize("size", [6, 11, 16, 24])
+def test_square_lattices_the_reference_cannot_build(size):
+    """the reference fails at L=6,11,16; the drop-in must give the ideal K."""
+    from latticeqmc_b200 import HubbardModel
+    m = HubbardModel(u=4, t=1)
+    m.build_square(size)
+    ham = m.ham_kinetic()
+    assert np.array_equal(ham, so.ideal_square_kinetic(size, 1.0, 2.0))
+    assert all(len(set(m.lattice.nearest_neighbours(i))) == 4 for i in range(size * size))
+
+
+def test_configuration_stream_and_ops():
+    """configuration.py:123-136 + SURVEY.md B.8 reference values of the legacy stream."""
+    from latticeqmc_b200 import Configuration
+    np.random.seed(12345)
+    assert np.allclose(np.random.rand(3), [0.92961609, 0.31637555, 0.18391881])
+    np.random.seed(12345)
+    c = Configuration(2, 3)
+    assert c.config.dtype == np.int8 and c.config.shape == (2, 3)
+    assert np.array_equal(c.config, [[-1, 1, 1], [1, -1, 1]])
+    assert np.random.rand() == 0.2045602785530397
+    c.update(0, 1)
+    assert c.get(0, 1) == -1 and c[0, 1] == -1
+    d = c.copy()
+    assert d == c
+    d.update(1, 1)
+    assert not (d == c)
+    assert c.mean() == np.mean(c.config) and c.var() == np.var(c.config)
+    assert str(c).count("\n") == 2
+
+
+def test_tools_observables():
+    from latticeqmc_b200 import filling, local_moment, local_gf, fermi_fct, compute_pole_gf_tau
+    g = np.array([[0.3, 0.1], [0.1, 0.6]])
+    assert np.allclose(filling(g), [0.7, 0.4])
+    assert np.allclose(local_moment(g, g), 2 * np.array([0.7, 0.4]) - 2 * np.array([0.49, 0.16]))
+    assert np.allclose(local_gf(g), [0.3, 0.6])
+    assert np.isclose(fermi_fct(0.0, 3.0), 0.5)
+    ham = so.ideal_ring_kinetic(6, 1.0, 0.0)
+    tau, gf = compute_pole_gf_tau(ham, 2.0)
+    from scipy.linalg import expm
+    assert np.allclose(-gf[:, :, 0], np.linalg.inv(np.eye(6) + expm(-2.0 * ham)), atol=1e-12)

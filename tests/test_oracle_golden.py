@@ -1,0 +1,147 @@
+"""Pin the oracle: replay every golden vector recorded from the unmodified reference
+(`tests/golden/make_golden.py`) through `oracle/sweep_oracle.py` and demand bit-equality.
+
+The oracle calls the same NumPy/OpenBLAS/SciPy routines in the same order as
+`/root/reference/lqmc/lqmc.py:301-347`, so in the container that produced the fixtures equality
+is exact.  On another host (different OpenBLAS kernel selection) the dense products may differ in
+the last bits; there the comparison falls back to a tolerance derived from the recorded
+amplification, and the accept/reject trace is still required to match on the well-conditioned
+cases."""
+import numpy as np
+import pytest
+
+from oracle import sweep_oracle as so
+
+
+def _bitwise_or_close(a, b, rtol):
+    if np.array_equal(a, b):
+        return True
+    scale = np.max(np.abs(b))
+    return np.max(np.abs(a - b)) <= rtol * scale
+
+
+@pytest.mark.parametrize("name", ["cfg1_2x2_free", "small_4x4_free", "small_3x2_free"])
+def test_free_running_small(golden, name):
+    g = golden(name)
+    h = g["field0"].copy()
+    lamb = float(g["lamb"])
+    dtau, lamb2, exp_k = so.set_beta_constants(g["ham"], float(g["u"]), float(g["beta"]), h.shape[1])
+    assert lamb2 == lamb
+    assert np.array_equal(exp_k, g["exp_k"]) or np.allclose(exp_k, g["exp_k"], rtol=1e-14, atol=0)
+    for s in range(g["uniforms"].shape[0]):
+        gu, gd, ratios, accs = so.update_step(h, g["exp_k"], lamb, g["uniforms"][s])
+        assert np.array_equal(accs, g["accs"][s]), f"accept/reject differs in sweep {s}"
+        assert np.array_equal(h, g["fields"][s])
+        assert _bitwise_or_close(ratios, g["ratios"][s], 1e-9)
+        assert _bitwise_or_close(gu, g["gf_up"][s], 1e-9)
+        assert _bitwise_or_close(gd, g["gf_dn"][s], 1e-9)
+
+
+def test_literal_loop_equals_outer(golden):
+    """The interpreted element loop (lqmc.py:328-331) and `G - outer(e, c)` are bit-equal."""
+    g = golden("cfg1_2x2_free")
+    h1, h2 = g["field0"].copy(), g["field0"].copy()
+    lamb = float(g["lamb"])
+    for s in range(3):
+        a = so.update_step(h1, g["exp_k"], lamb, g["uniforms"][s], literal=True)
+        b = so.update_step(h2, g["exp_k"], lamb, g["uniforms"][s], literal=False)
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+
+
+def test_global_stream_consumption(golden):
+    """`uniforms=None` draws one np.random.rand() per proposal from the legacy global stream, like
+    lqmc.py:317 - same trace as feeding the pre-drawn uniforms."""
+    g = golden("small_3x2_free")
+    lamb = float(g["lamb"])
+    h1, h2 = g["field0"].copy(), g["field0"].copy()
+    np.random.seed(1234)
+    u = np.random.rand(*g["uniforms"][0].shape)
+    probe = np.random.rand()
+    np.random.seed(1234)
+    a = so.update_step(h1, g["exp_k"], lamb, None)
+    assert np.random.rand() == probe
+    b = so.update_step(h2, g["exp_k"], lamb, u)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+
+
+@pytest.mark.parametrize("name", ["cfg2_8x8_sweep", "cfg3_ring64_sweep"])
+def test_full_sweep_n64(golden, name):
+    g = golden(name)
+    h = g["field0"].copy()
+    lamb = float(g["lamb"])
+    snaps = {}
+    gu, gd, ratios, accs = so.update_step(h, g["exp_k"], lamb, g["uniforms"], snapshots=snaps)
+    if np.array_equal(gu, g["gf_up"]):
+        # same BLAS as the generating container: everything must be bit-equal
+        assert np.array_equal(accs, g["accs"]) and np.array_equal(ratios, g["ratios"])
+        assert np.array_equal(h, g["field1"]) and np.array_equal(gd, g["gf_dn"])
+        for l in g["snap_slices"]:
+            assert np.array_equal(snaps[("post", int(l))][0], g[f"post{int(l)}_up"])
+            assert np.array_equal(snaps[("post", int(l))][1], g[f"post{int(l)}_dn"])
+    else:
+        # other BLAS: the recurrence amplifies 1e-16 to O(1) at beta>=4; check the
+        # teacher-forced single slices instead
+        for l in g["snap_slices"]:
+            l = int(l)
+            if f"post{l - 1}_up" not in g:
+                continue
+            _check_slice_pair(g, l, lamb)
+
+
+def _check_slice_pair(g, l, lamb):
+    lt = g["field0"].shape[1]
+    # field as it stood after the proposals of slice l: replay flips of slices L-1..l
+    h = g["field0"].copy()
+    for step in range(lt - l):
+        sl = lt - 1 - step
+        h[g["accs"][step], sl] *= -1
+    gu, gd = so.wrap(g[f"post{l}_up"], g[f"post{l}_dn"], h, l, g["exp_k"], lamb)
+    step = lt - l
+    ratios, accs = so.slice_proposals(gu, gd, h, l - 1, lamb, g["uniforms"][step])
+    assert np.array_equal(accs, g["accs"][step])
+    assert np.allclose(gu, g[f"post{l - 1}_up"], rtol=1e-9, atol=1e-9 * np.abs(g[f"post{l - 1}_up"]).max())
+
+
+def test_cfg2_teacher_forced_slices(golden):
+    g = golden("cfg2_8x8_sweep")
+    for l in (39, 20, 1):
+        _check_slice_pair(g, l, float(g["lamb"]))
+
+
+def test_cfg4_two_slices(golden):
+    """16x16: sweep-start G, proposals(79), wrap, proposals(78) against the reference."""
+    g = golden("cfg4_16x16_slices")
+    h = g["field0"].copy()
+    lamb = float(g["lamb"])
+    gu, gd = so.sweep_start_g(h, g["exp_k"], lamb)
+    same_blas = np.array_equal(gu, g["g0_up"])
+    if not same_blas:
+        gu, gd = g["g0_up"].copy(), g["g0_dn"].copy()
+    r79, a79 = so.slice_proposals(gu, gd, h, 79, lamb, g["uniforms"][0])
+    assert np.array_equal(a79, g["accs"][0])
+    assert np.allclose(gu, g["post79_up"], rtol=0, atol=1e-10 * np.abs(g["post79_up"]).max())
+    gu, gd = so.wrap(gu, gd, h, 79, g["exp_k"], lamb)
+    r78, a78 = so.slice_proposals(gu, gd, h, 78, lamb, g["uniforms"][1])
+    assert np.array_equal(a78, g["accs"][1])
+    assert np.array_equal(h, g["field1"])
+    if same_blas:
+        assert np.array_equal(gu, g["post78_up"]) and np.array_equal(gd, g["post78_dn"])
+        assert np.array_equal(r78, g["ratios"][1])
+
+
+def test_u0_known_answer(golden):
+    """exact.py:27-54 / tools.py:182-200: at U=0 every ratio is exactly 1, every proposal is
+    accepted, and G equals (I + exp(-beta K))^-1 = -G_pole(tau=0)."""
+    g = golden("u0_chain10")
+    h = g["field0"].copy()
+    gu, gd, ratios, accs = so.update_step(h, g["exp_k"], float(g["lamb"]), g["uniforms"])
+    assert float(g["lamb"]) == 0.0
+    assert np.all(ratios == 1.0) and accs.all()
+    assert np.array_equal(h, -g["field0"])
+    assert np.array_equal(gu, g["gf_up"]) or np.allclose(gu, g["gf_up"], rtol=0, atol=1e-12)
+    from scipy.linalg import expm
+    exact = np.linalg.inv(np.eye(10) + expm(-4.0 * g["ham"]))
+    assert np.max(np.abs(gu - exact)) < 1e-9
+    assert np.max(np.abs(gu + g["pole_gf_tau0"])) < 1e-9
