@@ -59,8 +59,8 @@ struct lqmc_engine {
   long long sweep_counter = 0;
   long long chain0 = 0;
   long long launches = 0;
-  std::vector<int8_t> hostField;   // staging for layout conversion
-  std::vector<double> hostG;
+  int8_t* hostField = nullptr;     // pinned staging for the layout conversions
+  double* hostG = nullptr;
 };
 
 namespace {
@@ -204,6 +204,8 @@ int lqmc_create(lqmc_engine** out, int device, int n_sites, int n_slices, int n_
       cudaMalloc(&e->dNmeas, (size_t)e->C * sizeof(long long)) != cudaSuccess ||
       cudaMalloc(&e->dNacc, (size_t)e->C * sizeof(long long)) != cudaSuccess)
     return cleanup(fail(LQMC_ERR_NOMEM, "cudaMalloc of chain state failed (%d chains, N=%d)", e->C, N));
+  if (cudaMallocHost(&e->hostField, field_bytes(e)) != cudaSuccess || cudaMallocHost(&e->hostG, nG * sizeof(double)) != cudaSuccess)
+    return cleanup(fail(LQMC_ERR_NOMEM, "cudaMallocHost of the staging buffers failed"));
   cudaMemset(e->dField, 1, field_bytes(e));
   cudaMemset(e->dG, 0, nG * sizeof(double));
   if (!e->family_reg) {
@@ -223,6 +225,8 @@ void lqmc_destroy(lqmc_engine* e) {
   for (void* p : ptrs)
     if (p) cudaFree(p);
   lqmc::l2_free(e->l2);
+  if (e->hostField) cudaFreeHost(e->hostField);
+  if (e->hostG) cudaFreeHost(e->hostG);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
 }
@@ -231,7 +235,7 @@ int lqmc_set_field(lqmc_engine* e, const int8_t* field) {
   if (!e || !field) return fail(LQMC_ERR_INVALID, "engine or field is NULL");
   CU(cudaSetDevice(e->device));
   const int N = e->N, L = e->L, NP = e->NP;
-  e->hostField.assign(field_bytes(e), 1);
+  memset(e->hostField, 1, field_bytes(e));
   for (int c = 0; c < e->C; ++c)
     for (int i = 0; i < N; ++i)
       for (int l = 0; l < L; ++l) {
@@ -239,7 +243,7 @@ int lqmc_set_field(lqmc_engine* e, const int8_t* field) {
         if (v != 1 && v != -1) return fail(LQMC_ERR_INVALID, "field[%d][%d][%d] = %d is not +-1", c, i, l, (int)v);
         e->hostField[((size_t)c * L + l) * NP + i] = v;
       }
-  CU(cudaMemcpyAsync(e->dField, e->hostField.data(), field_bytes(e), cudaMemcpyHostToDevice, e->stream));
+  CU(cudaMemcpyAsync(e->dField, e->hostField, field_bytes(e), cudaMemcpyHostToDevice, e->stream));
   CU(cudaStreamSynchronize(e->stream));
   return LQMC_OK;
 }
@@ -248,8 +252,7 @@ int lqmc_get_field(lqmc_engine* e, int8_t* field) {
   if (!e || !field) return fail(LQMC_ERR_INVALID, "engine or field is NULL");
   CU(cudaSetDevice(e->device));
   const int N = e->N, L = e->L, NP = e->NP;
-  e->hostField.resize(field_bytes(e));
-  CU(cudaMemcpyAsync(e->hostField.data(), e->dField, field_bytes(e), cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaMemcpyAsync(e->hostField, e->dField, field_bytes(e), cudaMemcpyDeviceToHost, e->stream));
   CU(cudaStreamSynchronize(e->stream));
   for (int c = 0; c < e->C; ++c)
     for (int i = 0; i < N; ++i)
@@ -261,13 +264,13 @@ int lqmc_set_g(lqmc_engine* e, const double* g) {
   if (!e || !g) return fail(LQMC_ERR_INVALID, "engine or g is NULL");
   CU(cudaSetDevice(e->device));
   const int N = e->N, NP = e->NP;
-  e->hostG.assign(g_elems(e), 0.0);
+  memset(e->hostG, 0, g_elems(e) * sizeof(double));
   for (size_t m = 0; m < (size_t)e->C * 2; ++m) {
-    double* dst = e->hostG.data() + m * NP * NP;
+    double* dst = e->hostG + m * NP * NP;
     for (int i = 0; i < NP; ++i) dst[(size_t)i * NP + i] = 1.0;
     for (int i = 0; i < N; ++i) memcpy(dst + (size_t)i * NP, g + (m * N + i) * N, sizeof(double) * N);
   }
-  CU(cudaMemcpyAsync(e->dG, e->hostG.data(), g_elems(e) * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+  CU(cudaMemcpyAsync(e->dG, e->hostG, g_elems(e) * sizeof(double), cudaMemcpyHostToDevice, e->stream));
   CU(cudaStreamSynchronize(e->stream));
   return LQMC_OK;
 }
@@ -276,11 +279,10 @@ int lqmc_get_g(lqmc_engine* e, double* g) {
   if (!e || !g) return fail(LQMC_ERR_INVALID, "engine or g is NULL");
   CU(cudaSetDevice(e->device));
   const int N = e->N, NP = e->NP;
-  e->hostG.resize(g_elems(e));
-  CU(cudaMemcpyAsync(e->hostG.data(), e->dG, g_elems(e) * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaMemcpyAsync(e->hostG, e->dG, g_elems(e) * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
   CU(cudaStreamSynchronize(e->stream));
   for (size_t m = 0; m < (size_t)e->C * 2; ++m)
-    for (int i = 0; i < N; ++i) memcpy(g + (m * N + i) * N, e->hostG.data() + m * NP * NP + (size_t)i * NP, sizeof(double) * N);
+    for (int i = 0; i < N; ++i) memcpy(g + (m * N + i) * N, e->hostG + m * NP * NP + (size_t)i * NP, sizeof(double) * N);
   return LQMC_OK;
 }
 
