@@ -239,7 +239,8 @@ def run_ours(args):
     eng = SweepEngine(w["exp_k"], w["lamb"], lt, n_chains=chains, exp_k_inv=w["exp_k_inv"], device=local,
                       mode="parity", arith=args.arith, chain_offset=rank * chains)
     eng.set_field(fields)
-    stream = torch.cuda.current_stream(dev)
+    stream = torch.cuda.Stream(dev)          # a real (non-default) stream: its handle goes to the C ABI, events see it
+    torch.cuda.set_stream(stream)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
 
     def barrier():

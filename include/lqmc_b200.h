@@ -124,6 +124,11 @@ int lqmc_set_chain_offset(lqmc_engine* e, int64_t chain0);
  * uniforms chain `chain` consumes in global sweep `sweep` under `seed` (visiting order). */
 void lqmc_philox_uniforms(uint64_t seed, uint64_t chain, uint64_t sweep, int n_proposals, double* out);
 
+/* Device self-test: the sweep divides a whole column by one denominator through a shared reciprocal
+ * and two FMA corrections; this checks n_samples random (x, d) pairs, including all-ones / sparse
+ * mantissas, for bit-equality with IEEE division (what np.divide does in lqmc.py:326-327). */
+int lqmc_selftest_division(int device, uint64_t n_samples, uint64_t seed, uint64_t* mismatches);
+
 const char* lqmc_last_error(void);
 const char* lqmc_version(void);
 

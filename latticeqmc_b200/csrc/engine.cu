@@ -93,22 +93,22 @@ int stage_uniforms(lqmc_engine* e, const double* host, size_t count, cudaStream_
   return LQMC_OK;
 }
 
-template <int NP>
+template <class C>
 int launch_reg(lqmc_engine* e, const lqmc::SweepParams& p, cudaStream_t s) {
   const bool exact = !(e->flags & LQMC_ARITH_FMA);
   const bool phys = (e->flags & LQMC_MODE_PHYSICS) != 0;
-  const size_t smem = lqmc::RegCfg<NP>::smem_bytes;
+  const size_t smem = C::smem_bytes;
   auto go = [&](auto kernel) -> int {
     CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kernel<<<e->C, 128, smem, s>>>(p);
+    kernel<<<e->C, C::THREADS, smem, s>>>(p);
     CU(cudaGetLastError());
     e->launches += 1;
     return LQMC_OK;
   };
-  if (exact && !phys) return go(lqmc::sweep_reg_kernel<NP, true, false>);
-  if (!exact && !phys) return go(lqmc::sweep_reg_kernel<NP, false, false>);
-  if (exact && phys) return go(lqmc::sweep_reg_kernel<NP, true, true>);
-  return go(lqmc::sweep_reg_kernel<NP, false, true>);
+  if (exact && !phys) return go(lqmc::sweep_reg_kernel<C, true, false>);
+  if (!exact && !phys) return go(lqmc::sweep_reg_kernel<C, false, false>);
+  if (exact && phys) return go(lqmc::sweep_reg_kernel<C, true, true>);
+  return go(lqmc::sweep_reg_kernel<C, false, true>);
 }
 
 // One entry for every phase combination: n_sweeps x [recompute?] + steps [step_lo, step_hi) x [propose?][wrap?]
@@ -135,9 +135,9 @@ int run(lqmc_engine* e, int n_sweeps, int step_lo, int step_hi, bool recompute, 
   int rc;
   if (e->family_reg) {
     switch (e->NP) {
-      case 16: rc = launch_reg<16>(e, p, s); break;
-      case 32: rc = launch_reg<32>(e, p, s); break;
-      case 64: rc = launch_reg<64>(e, p, s); break;
+      case 16: rc = launch_reg<lqmc::RegCfg<16, 8, 8>>(e, p, s); break;
+      case 32: rc = launch_reg<lqmc::RegCfg<32, 8, 8>>(e, p, s); break;
+      case 64: rc = launch_reg<lqmc::RegCfg<64, 16, 8>>(e, p, s); break;
       default: return fail(LQMC_ERR_UNSUPPORTED, "no register-resident kernel for padded size %d", e->NP);
     }
   } else {
@@ -425,6 +425,24 @@ int lqmc_set_sweep_counter(lqmc_engine* e, int64_t counter) {
 int lqmc_set_chain_offset(lqmc_engine* e, int64_t chain0) {
   if (!e) return fail(LQMC_ERR_INVALID, "engine is NULL");
   e->chain0 = chain0;
+  return LQMC_OK;
+}
+
+int lqmc_selftest_division(int device, uint64_t n_samples, uint64_t seed, uint64_t* mismatches) {
+  if (!mismatches) return fail(LQMC_ERR_INVALID, "mismatches is NULL");
+  CU(cudaSetDevice(device));
+  unsigned long long* d_bad = nullptr;
+  CU(cudaMalloc(&d_bad, sizeof(unsigned long long)));
+  CU(cudaMemset(d_bad, 0, sizeof(unsigned long long)));
+  const int blocks = 148 * 8, threads = 256;
+  const unsigned long long per_thread = (n_samples + (uint64_t)blocks * threads - 1) / ((uint64_t)blocks * threads);
+  lqmc::division_selftest_kernel<<<blocks, threads>>>(per_thread, seed, d_bad);
+  CU(cudaGetLastError());
+  CU(cudaDeviceSynchronize());
+  unsigned long long bad = 0;
+  CU(cudaMemcpy(&bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost));
+  cudaFree(d_bad);
+  *mismatches = bad;
   return LQMC_OK;
 }
 

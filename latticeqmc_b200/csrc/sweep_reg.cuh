@@ -4,27 +4,29 @@
 // (/root/reference/lqmc/lqmc.py:301-347) and the helpers it calls (get_m :156-185, get_exp_v :132-154,
 // np.linalg.inv :306-307, Configuration.update configuration.py:126-136, measure_loop :356-375).
 //
-// Layout.  128 threads = 2 spins x (8 x 8) threads.  Each thread owns a TR x TR register tile of its
-// spin's Green's function (TR = NP/8; NP = N padded to 16/32/64): rows {2*ty + 16*q + s}, columns
-// {2*tx + 16*q + s}.  The interleave makes every shared-memory fragment access of the GEMMs a
-// conflict-free LDS.128 and lets the site loop be unrolled so that "the row / column of site i" is a
-// compile-time register index.  G never leaves the register file during the N proposals of a slice:
-// a flip publishes row i and column i (2*NP doubles per spin) through shared memory, one bar.sync,
-// then every thread applies the rank-1 update to its own tile.  Per flip that is ~1 KB of shared
-// traffic instead of the 16*N^2 B a shared-memory-resident G would move, so the phase is bound by
-// the FP64 pipe (2*N^2 DFMA per flip), not by shared-memory bandwidth.
+// Layout.  A CTA = 2 spins x (GY x GX) threads.  Each thread owns a TR x TC register tile of its
+// spin's Green's function (TR = NP/GY rows, TC = NP/GX columns; NP = N padded to 16/32/64): rows
+// {2*ty + 2*GY*q + s}, columns {2*tx + 2*GX*q + s}.  The pairwise interleave makes every shared-memory
+// fragment access of the GEMMs, and both the plain and the transposed tile store, a conflict-free (or
+// minimum-wavefront) 128-bit access with the row stride S = NP+2, and lets the site loop be unrolled
+// so that "the row / column of site i" is a compile-time register index.  G never leaves the register
+// file during the N proposals of a slice: a flip publishes row i and column i (2*NP doubles per spin)
+// through shared memory, one bar.sync, then every thread applies the rank-1 update to its own tile.
+// Per flip that is ~1 KB of shared traffic instead of the 16*N^2 B a shared-memory-resident G would
+// move, so the phase is bound by the FP64 pipe (2*N^2 DFMA per flip), not by shared-memory bandwidth.
 //
-// The wrap G <- B G B^-1 and the sweep-start product are register-tiled DFMA GEMMs: one operand
-// staged in shared memory (the chain's own G / running product), the other (exp(-dtau K) or its
-// inverse, shared by every chain on the SM) read through L1 with ld.global.nc.  exp(V_l) is
-// diagonal and is folded into the epilogue as row / column scales (lqmc.py:339-345 builds it dense).
-// FP64 has no tcgen05 kind and DMMA shares the DFMA pipe on sm_100a (profiles/fp64_peaks_r01.json:
-// 36.8 vs 37.2 TFLOP/s, 30.9 mixed), so the roofline is the DFMA pipe either way.
+// The wrap G <- B G B^-1 and the sweep-start product are register-tiled DFMA GEMMs with k-major
+// operands: one staged in shared memory (the chain's own G / running product, stored transposed when
+// it is the left operand), the other (exp(-dtau K) or its inverse, shared by every chain on the SM)
+// read through L1 with ld.global.nc.  exp(V_l) is diagonal and is folded into the epilogue as row /
+// column scales (lqmc.py:339-345 builds it dense).  FP64 has no tcgen05 kind and DMMA issues to the
+// same pipe as DFMA on sm_100a (profiles/fp64_peaks_r01.json: 36.8 vs 37.2 TFLOP/s alone, 30.9 mixed),
+// so the roofline is the FP64 pipe either way.
 //
 // Arithmetic modes (template flags):
 //   EXACT  - ratio, rank-1 vectors and update use the reference's roundings: separate multiply and
-//            subtract, true division (lqmc.py:314-331).  Given the same G, field and uniforms the
-//            accept/reject decisions and the updated G of a slice are bit-identical to NumPy's.
+//            subtract, correctly rounded division (lqmc.py:314-331).  Given the same G, field and
+//            uniforms the decisions and the updated G of a slice are bit-identical to NumPy's.
 //   !EXACT - update contracted to one FMA, e = column * (1/denominator).
 //   PHYS   - textbook DQMC instead of the reference recurrence.
 #pragma once
@@ -57,41 +59,52 @@ struct SweepParams {
   double exp_pl, exp_ml, f_p2, f_m2;  // exp(+lamb), exp(-lamb), exp(+2 lamb)-1, exp(-2 lamb)-1
 };
 
-template <int NP>
+template <int NP_, int GY_, int GX_>
 struct RegCfg {
-  static constexpr int TR = NP / 8;       // tile edge per thread
-  static constexpr int S = NP + 2;        // shared row stride (doubles): even for 16-B vectors, 2 mod 4 for banks
-  static constexpr int THREADS = 128;
-  static constexpr size_t stage_bytes = size_t(2) * NP * S * sizeof(double);
-  static constexpr size_t smem_bytes = stage_bytes + (2 * NP + 4 * NP * 2 + NP) * sizeof(double) + 2 * NP + 64 * 4 + 2 * NP * sizeof(int);
+  static constexpr int NP = NP_, GY = GY_, GX = GX_;
+  static constexpr int TR = NP / GY;      // rows per thread
+  static constexpr int TC = NP / GX;      // columns per thread
+  static constexpr int TPS = GY * GX;     // threads per spin
+  static constexpr int THREADS = 2 * TPS;
+  static constexpr int WPS = TPS / 32;    // warps per spin
+  static constexpr int GMIN = GY < GX ? GY : GX;
+  static constexpr int S = NP + 2;        // shared row stride in doubles: even (16-B vectors), odd/2 (banks)
+  static constexpr int HS = TPS / NP;     // threads per matrix row in the inverse
+  static constexpr size_t smem_bytes = (size_t(2) * NP * S + 2 * NP + 8 * NP + NP + 2 * WPS) * sizeof(double)
+                                       + (2 * WPS + 2 * NP) * sizeof(int) + 2 * NP;
+  static_assert(TR % 2 == 0 && TC % 2 == 0, "tiles are made of element pairs");
+  static_assert(TPS % 32 == 0 && TPS >= NP && TPS % NP == 0, "thread grid");
 };
 
-template <int NP>
+template <class C>
 struct RegSmem {
   double* stage;   // [2][NP][S]
   double* d;       // [2][NP]      diagonal as of the previous accepted flip
   double* e;       // [2 buf][2 spin][NP]
   double* c;       // [2 buf][2 spin][NP]
   double* u;       // [NP]
+  double* red_v;   // [2*WPS] pivot search partials (per warp)
+  int* red_i;      // [2*WPS]
+  int* piv;        // [2][NP]
   int8_t* h;       // [NP] field column of the slice being updated
   int8_t* hn;      // [NP] field column the wrap scales with
-  double* red_v;   // [4] pivot search partials (per warp)
-  int* red_i;      // [4]
-  int* piv;        // [2][NP]
   __device__ explicit RegSmem(unsigned char* base) {
-    constexpr int S = RegCfg<NP>::S;
+    constexpr int NP = C::NP, S = C::S, WPS = C::WPS;
     stage = reinterpret_cast<double*>(base);
     d = stage + 2 * NP * S;
     e = d + 2 * NP;
     c = e + 4 * NP;
     u = c + 4 * NP;
     red_v = u + NP;
-    red_i = reinterpret_cast<int*>(red_v + 4);
-    piv = red_i + 4;
+    red_i = reinterpret_cast<int*>(red_v + 2 * WPS);
+    piv = red_i + 2 * WPS;
     h = reinterpret_cast<int8_t*>(piv + 2 * NP);
     hn = h + NP;
   }
 };
+
+template <class C> __device__ __forceinline__ int row_of(int ty, int a) { return 2 * ty + 2 * C::GY * (a >> 1) + (a & 1); }
+template <class C> __device__ __forceinline__ int col_of(int tx, int b) { return 2 * tx + 2 * C::GX * (b >> 1) + (b & 1); }
 
 template <bool EXACT>
 __device__ __forceinline__ double rank1(double g, double e, double c) {
@@ -99,85 +112,104 @@ __device__ __forceinline__ double rank1(double g, double e, double c) {
   return fma(-e, c, g);
 }
 
-// ---- register-tiled DFMA GEMMs -----------------------------------------------------------------
-// acc[a][b] += sum_k At[k][row_a] * Bs[k][col_b]      (At: global, transposed operand; Bs: shared)
-template <int NP>
-__device__ __forceinline__ void gemm_gT_s(double (&acc)[RegCfg<NP>::TR][RegCfg<NP>::TR], const double* __restrict__ At,
-                                          const double* Bs, int ty, int tx) {
-  constexpr int TR = RegCfg<NP>::TR, S = RegCfg<NP>::S, Q = TR / 2;
-  const double* ap = At + 2 * ty;
-  const double* bp = Bs + 2 * tx;
-#pragma unroll 2
+// ---- correctly rounded x / d from a shared reciprocal --------------------------------------------------
+// IEEE division costs ~50 FP64-pipe issue slots on sm_100a (tools/fp64_peak.cu) and a flip needs N of them
+// per spin with one common denominator.  With r = RN(1/d), two residual corrections
+//     q <- q + fma(-q, d, x) * r
+// give the correctly rounded quotient (Markstein's theorem: r correctly rounded, q faithful after the first
+// correction, exact residual from the FMA).  Operands outside a wide safe exponent window take the
+// IEEE path.  lqmc_selftest_division() checks bit-equality with __ddiv_rn on the device.
+__device__ __forceinline__ bool div_safe(double v) {
+  const unsigned ex = ((unsigned)__double2hiint(v) >> 20) & 0x7ffu;
+  return ex > 0x3ffu - 400u && ex < 0x3ffu + 400u;
+}
+__device__ __forceinline__ double div_shared_rcp(double x, double d, double r, bool d_safe) {
+  if (!(d_safe && (x == 0.0 || div_safe(x)))) return __ddiv_rn(x, d);
+  double q = __dmul_rn(x, r);
+  q = fma(fma(-q, d, x), r, q);
+  q = fma(fma(-q, d, x), r, q);
+  return q;
+}
+
+// ---- register-tiled DFMA GEMM, k-major operands ----------------------------------------------------------
+// acc[a][b] += sum_k A[k*lda + row_a] * B[k*ldb + col_b];  GA / GB: operand is global (read-only path)
+template <class C, bool GA, bool GB>
+__device__ __forceinline__ void gemm_kmajor(double (&acc)[C::TR][C::TC], const double* __restrict__ A, int lda,
+                                            const double* __restrict__ B, int ldb, int ty, int tx) {
+  constexpr int TR = C::TR, TC = C::TC, NP = C::NP;
+  const double* ap = A + 2 * ty;
+  const double* bp = B + 2 * tx;
+#pragma unroll 4
   for (int k = 0; k < NP; ++k) {
-    double a[TR], b[TR];
+    double a[TR], b[TC];
 #pragma unroll
-    for (int q = 0; q < Q; ++q) {
-      const double2 v = __ldg(reinterpret_cast<const double2*>(ap + k * NP + 16 * q));
+    for (int q = 0; q < TR / 2; ++q) {
+      const double2* src = reinterpret_cast<const double2*>(ap + k * lda + 2 * C::GY * q);
+      const double2 v = GA ? __ldg(src) : *src;
       a[2 * q] = v.x; a[2 * q + 1] = v.y;
-      const double2 w = *reinterpret_cast<const double2*>(bp + k * S + 16 * q);
+    }
+#pragma unroll
+    for (int q = 0; q < TC / 2; ++q) {
+      const double2* src = reinterpret_cast<const double2*>(bp + k * ldb + 2 * C::GX * q);
+      const double2 w = GB ? __ldg(src) : *src;
       b[2 * q] = w.x; b[2 * q + 1] = w.y;
     }
 #pragma unroll
     for (int i = 0; i < TR; ++i)
 #pragma unroll
-      for (int j = 0; j < TR; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+      for (int j = 0; j < TC; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
   }
 }
 
-// acc[a][b] += sum_k As[row_a][k] * Bg[k][col_b]      (As: shared, row-major; Bg: global)
-template <int NP>
-__device__ __forceinline__ void gemm_s_g(double (&acc)[RegCfg<NP>::TR][RegCfg<NP>::TR], const double* As,
-                                         const double* __restrict__ Bg, int ty, int tx) {
-  constexpr int TR = RegCfg<NP>::TR, S = RegCfg<NP>::S, Q = TR / 2;
-  const double* bp = Bg + 2 * tx;
-#pragma unroll 1
-  for (int k = 0; k < NP; k += 2) {
-    double2 a[TR];
-    double b0[TR], b1[TR];
+// tile -> shared, row-major M[row][col]
+template <class C>
+__device__ __forceinline__ void store_tile(double* M, const double (&g)[C::TR][C::TC], int ty, int tx) {
 #pragma unroll
-    for (int q = 0; q < Q; ++q) {
+  for (int a = 0; a < C::TR; ++a) {
+    const int row = row_of<C>(ty, a);
 #pragma unroll
-      for (int s = 0; s < 2; ++s) a[2 * q + s] = *reinterpret_cast<const double2*>(As + (2 * ty + 16 * q + s) * S + k);
-      const double2 w0 = __ldg(reinterpret_cast<const double2*>(bp + k * NP + 16 * q));
-      const double2 w1 = __ldg(reinterpret_cast<const double2*>(bp + (k + 1) * NP + 16 * q));
-      b0[2 * q] = w0.x; b0[2 * q + 1] = w0.y;
-      b1[2 * q] = w1.x; b1[2 * q + 1] = w1.y;
-    }
-#pragma unroll
-    for (int i = 0; i < TR; ++i)
-#pragma unroll
-      for (int j = 0; j < TR; ++j) acc[i][j] = fma(a[i].x, b0[j], acc[i][j]);
-#pragma unroll
-    for (int i = 0; i < TR; ++i)
-#pragma unroll
-      for (int j = 0; j < TR; ++j) acc[i][j] = fma(a[i].y, b1[j], acc[i][j]);
+    for (int q = 0; q < C::TC / 2; ++q)
+      *reinterpret_cast<double2*>(M + row * C::S + 2 * tx + 2 * C::GX * q) = make_double2(g[a][2 * q], g[a][2 * q + 1]);
   }
 }
-
-template <int NP>
-__device__ __forceinline__ void store_tile(double* M, const double (&g)[RegCfg<NP>::TR][RegCfg<NP>::TR], int ty, int tx) {
-  constexpr int TR = RegCfg<NP>::TR, S = RegCfg<NP>::S;
+// tile -> shared, transposed M[col][row]  (k-major left operand of the next GEMM)
+template <class C>
+__device__ __forceinline__ void store_tile_t(double* M, const double (&g)[C::TR][C::TC], int ty, int tx) {
 #pragma unroll
-  for (int a = 0; a < TR; ++a) {
-    const int row = 2 * ty + 16 * (a >> 1) + (a & 1);
+  for (int b = 0; b < C::TC; ++b) {
+    const int col = col_of<C>(tx, b);
 #pragma unroll
-    for (int q = 0; q < TR / 2; ++q)
-      *reinterpret_cast<double2*>(M + row * S + 2 * tx + 16 * q) = make_double2(g[a][2 * q], g[a][2 * q + 1]);
+    for (int q = 0; q < C::TR / 2; ++q)
+      *reinterpret_cast<double2*>(M + col * C::S + 2 * ty + 2 * C::GY * q) = make_double2(g[2 * q][b], g[2 * q + 1][b]);
   }
 }
-
-template <int NP>
-__device__ __forceinline__ void load_tile(const double* M, int stride, double (&g)[RegCfg<NP>::TR][RegCfg<NP>::TR], int ty, int tx) {
-  constexpr int TR = RegCfg<NP>::TR;
+template <class C>
+__device__ __forceinline__ void load_tile(const double* M, int stride, double (&g)[C::TR][C::TC], int ty, int tx) {
 #pragma unroll
-  for (int a = 0; a < TR; ++a) {
-    const int row = 2 * ty + 16 * (a >> 1) + (a & 1);
+  for (int a = 0; a < C::TR; ++a) {
+    const int row = row_of<C>(ty, a);
 #pragma unroll
-    for (int q = 0; q < TR / 2; ++q) {
-      const double2 v = *reinterpret_cast<const double2*>(M + row * stride + 2 * tx + 16 * q);
+    for (int q = 0; q < C::TC / 2; ++q) {
+      const double2 v = *reinterpret_cast<const double2*>(M + row * stride + 2 * tx + 2 * C::GX * q);
       g[a][2 * q] = v.x; g[a][2 * q + 1] = v.y;
     }
   }
+}
+template <class C>
+__device__ __forceinline__ void zero_tile(double (&acc)[C::TR][C::TC]) {
+#pragma unroll
+  for (int a = 0; a < C::TR; ++a)
+#pragma unroll
+    for (int b = 0; b < C::TC; ++b) acc[a][b] = 0.0;
+}
+// publish the tile's diagonal entries: dst[row] = g[row][row]
+template <class C>
+__device__ __forceinline__ void store_diag(double* dst, const double (&g)[C::TR][C::TC], int ty, int tx) {
+#pragma unroll
+  for (int a = 0; a < C::TR; ++a)
+#pragma unroll
+    for (int b = 0; b < C::TC; ++b)
+      if (row_of<C>(ty, a) == col_of<C>(tx, b)) dst[row_of<C>(ty, a)] = g[a][b];
 }
 
 // exp(-sigma*lamb*h) for spin index `spin` (0: sigma=+1, 1: sigma=-1)   [get_exp_v, lqmc.py:149-154]
@@ -188,18 +220,21 @@ __device__ __forceinline__ double hs_vinv(int8_t h, int spin, const SweepParams&
   return ((h > 0) != (spin != 0)) ? p.exp_pl : p.exp_ml;
 }
 
-// ---- in-place Gauss-Jordan inverse with partial (row) pivoting, 64 threads per spin -------------------
+// ---- in-place Gauss-Jordan inverse with partial (row) pivoting ------------------------------------------
 // Stands in for np.linalg.inv (LAPACK getrf/getri, lqmc.py:306-307): same pivot rule (first entry of
-// largest magnitude in the column), different elimination order.
-template <int NP>
-__device__ void gj_inverse(double* M, RegSmem<NP>& sm, int spin, int t) {
-  constexpr int S = RegCfg<NP>::S;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+// largest magnitude in the column), different elimination order.  HS threads share a matrix row.
+template <class C>
+__device__ void gj_inverse(double* M, RegSmem<C>& sm, int spin, int t) {
+  constexpr int NP = C::NP, S = C::S, WPS = C::WPS, HS = C::HS, SEG = NP / HS;
+  const int lane = threadIdx.x & 31, warp_in_spin = (t >> 5);
+  const int row = t % NP, seg = t / NP;
   int* piv = sm.piv + spin * NP;
   for (int k = 0; k < NP; ++k) {
-    double pv = (t >= k && t < NP) ? M[t * S + k] : 0.0;
-    double av = (t >= k && t < NP) ? fabs(pv) : -1.0;
-    int idx = t;
+    const double akk = M[k * S + k];
+    const bool cand = (seg == 0 && row >= k);
+    double pv = cand ? M[row * S + k] : 0.0;
+    double av = cand ? fabs(pv) : -1.0;
+    int idx = cand ? row : NP;
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) {
       const double oa = __shfl_down_sync(0xffffffffu, av, off);
@@ -207,15 +242,19 @@ __device__ void gj_inverse(double* M, RegSmem<NP>& sm, int spin, int t) {
       const int oi = __shfl_down_sync(0xffffffffu, idx, off);
       if (oa > av || (oa == av && oi < idx)) { av = oa; pv = op; idx = oi; }
     }
-    if (lane == 0) { sm.red_v[warp] = pv; sm.red_i[warp] = idx; }
+    if (lane == 0) { sm.red_v[spin * WPS + warp_in_spin] = pv; sm.red_i[spin * WPS + warp_in_spin] = idx; }
     __syncthreads();
-    {
-      const double p0 = sm.red_v[2 * spin], p1 = sm.red_v[2 * spin + 1];
-      const int i0 = sm.red_i[2 * spin], i1 = sm.red_i[2 * spin + 1];
-      const bool second = (i1 >= k && i1 < NP) && (!(i0 >= k && i0 < NP) || fabs(p1) > fabs(p0));
-      pv = second ? p1 : p0;
-      idx = second ? i1 : i0;
+    pv = sm.red_v[spin * WPS]; idx = sm.red_i[spin * WPS];
+#pragma unroll
+    for (int w = 1; w < WPS; ++w) {
+      const double ov = sm.red_v[spin * WPS + w];
+      const int oi = sm.red_i[spin * WPS + w];
+      if (oi < NP && (idx >= NP || fabs(ov) > fabs(pv) || (fabs(ov) == fabs(pv) && oi < idx))) { pv = ov; idx = oi; }
     }
+    if (idx >= NP) idx = k;
+    // this row's multiplier, taken before anybody rewrites column k: after the swap row `idx` holds the old
+    // row k, every other row keeps its own entry
+    const double f = (row == idx && idx != k) ? akk : M[row * S + k];
     if (t == 0) piv[k] = idx;
     if (t < NP) {
       const double ak = M[k * S + t];
@@ -225,27 +264,26 @@ __device__ void gj_inverse(double* M, RegSmem<NP>& sm, int spin, int t) {
       if (idx != k) M[idx * S + t] = ak;
     }
     __syncthreads();
-    if (t < NP && t != k) {
-      double* row = M + t * S;
+    if (row != k) {
+      double* rp = M + row * S;
       const double* rk = M + k * S;
-      const double f = row[k];
-      row[k] = 0.0;
 #pragma unroll 4
-      for (int j = 0; j < NP; j += 2) {
-        double2 r = *reinterpret_cast<double2*>(row + j);
+      for (int j = seg * SEG; j < (seg + 1) * SEG; j += 2) {
+        double2 r = *reinterpret_cast<double2*>(rp + j);
         const double2 q = *reinterpret_cast<const double2*>(rk + j);
+        if (j == (k & ~1)) { if (k & 1) r.y = 0.0; else r.x = 0.0; }
         r.x = fma(-f, q.x, r.x);
         r.y = fma(-f, q.y, r.y);
-        *reinterpret_cast<double2*>(row + j) = r;
+        *reinterpret_cast<double2*>(rp + j) = r;
       }
     }
     __syncthreads();
   }
-  if (t < NP) {
-    double* row = M + t * S;
+  if (seg == 0) {
+    double* rp = M + row * S;
     for (int k = NP - 1; k >= 0; --k) {
       const int p = piv[k];
-      if (p != k) { const double tmp = row[k]; row[k] = row[p]; row[p] = tmp; }
+      if (p != k) { const double tmp = rp[k]; rp[k] = rp[p]; rp[p] = tmp; }
     }
   }
   __syncthreads();
@@ -255,107 +293,97 @@ __device__ void gj_inverse(double* M, RegSmem<NP>& sm, int spin, int t) {
 // get_m + np.linalg.inv (lqmc.py:156-185,303-307).  The first factor is taken as is (the reference starts
 // its left-to-right product from the scalar 1); each later one costs one GEMM with the column scale
 // exp(V_l) in the epilogue.
-template <int NP>
-__device__ void recompute_g(double (&g)[RegCfg<NP>::TR][RegCfg<NP>::TR], RegSmem<NP>& sm, const SweepParams& p,
-                            const int8_t* field, int l0, int spin, int t, int ty, int tx) {
-  constexpr int TR = RegCfg<NP>::TR, S = RegCfg<NP>::S;
+template <class C>
+__device__ void recompute_g(double (&g)[C::TR][C::TC], RegSmem<C>& sm, const SweepParams& p, const int8_t* field, int l0,
+                            int spin, int t, int ty, int tx) {
+  constexpr int TR = C::TR, TC = C::TC, NP = C::NP, S = C::S;
   const int L = p.n_slices;
   double* stage = sm.stage + spin * NP * S;
   int l = (l0 - 1 + L) % L;
   {
     const int8_t* hl = field + l * NP;
 #pragma unroll
-    for (int a = 0; a < TR; ++a) {
-      const int row = 2 * ty + 16 * (a >> 1) + (a & 1);
+    for (int b = 0; b < TC; ++b) {
+      const int col = col_of<C>(tx, b);
+      const double v = hs_v(hl[col], spin, p);
 #pragma unroll
-      for (int b = 0; b < TR; ++b) {
-        const int col = 2 * tx + 16 * (b >> 1) + (b & 1);
-        g[a][b] = p.E[row * NP + col] * hs_v(hl[col], spin, p);
-      }
+      for (int a = 0; a < TR; ++a) g[a][b] = p.E[row_of<C>(ty, a) * NP + col] * v;
     }
   }
   for (int m = 1; m < L; ++m) {
     l = (l0 - 1 - m + 2 * L) % L;
     __syncthreads();                 // everyone is done reading the previous stage contents
-    store_tile<NP>(stage, g, ty, tx);
+    store_tile_t<C>(stage, g, ty, tx);
     __syncthreads();
-    double acc[TR][TR];
-#pragma unroll
-    for (int a = 0; a < TR; ++a)
-#pragma unroll
-      for (int b = 0; b < TR; ++b) acc[a][b] = 0.0;
-    gemm_s_g<NP>(acc, stage, p.E, ty, tx);
+    double acc[TR][TC];
+    zero_tile<C>(acc);
+    gemm_kmajor<C, false, true>(acc, stage, S, p.E, NP, ty, tx);
     const int8_t* hl = field + l * NP;
 #pragma unroll
-    for (int b = 0; b < TR; ++b) {
-      const int col = 2 * tx + 16 * (b >> 1) + (b & 1);
-      const double v = hs_v(hl[col], spin, p);
+    for (int b = 0; b < TC; ++b) {
+      const double v = hs_v(hl[col_of<C>(tx, b)], spin, p);
 #pragma unroll
       for (int a = 0; a < TR; ++a) g[a][b] = acc[a][b] * v;
     }
   }
-  if (ty == tx) {
 #pragma unroll
-    for (int a = 0; a < TR; ++a) g[a][a] += 1.0;
-  }
+  for (int a = 0; a < TR; ++a)
+#pragma unroll
+    for (int b = 0; b < TC; ++b)
+      if (row_of<C>(ty, a) == col_of<C>(tx, b)) g[a][b] += 1.0;
   __syncthreads();
-  store_tile<NP>(stage, g, ty, tx);
+  store_tile<C>(stage, g, ty, tx);
   __syncthreads();
-  gj_inverse<NP>(stage, sm, spin, t);
-  load_tile<NP>(stage, S, g, ty, tx);
+  gj_inverse<C>(stage, sm, spin, t);
+  load_tile<C>(stage, S, g, ty, tx);
 }
 
 // ---- wrap from slice l to l-1 ------------------------------------------------------------------------
 // parity : G <- diag(v) E G E^-1 diag(1/v),   v = exp(-sigma lamb h[:, l-1])   (lqmc.py:338-345)
 // physics: G <- diag(1/v) E^-1 G E diag(v)                                      (Appendix C)
-template <int NP, bool PHYS>
-__device__ void wrap_g(double (&g)[RegCfg<NP>::TR][RegCfg<NP>::TR], RegSmem<NP>& sm, const SweepParams& p, int spin, int ty, int tx) {
-  constexpr int TR = RegCfg<NP>::TR, S = RegCfg<NP>::S;
+template <class C, bool PHYS>
+__device__ void wrap_g(double (&g)[C::TR][C::TC], RegSmem<C>& sm, const SweepParams& p, int spin, int ty, int tx) {
+  constexpr int TR = C::TR, TC = C::TC, NP = C::NP, S = C::S;
   double* stage = sm.stage + spin * NP * S;
-  store_tile<NP>(stage, g, ty, tx);
+  store_tile<C>(stage, g, ty, tx);
   __syncthreads();
-  double acc[TR][TR];
-#pragma unroll
-  for (int a = 0; a < TR; ++a)
-#pragma unroll
-    for (int b = 0; b < TR; ++b) acc[a][b] = 0.0;
-  gemm_gT_s<NP>(acc, PHYS ? p.Eit : p.Et, stage, ty, tx);
+  double acc[TR][TC];
+  zero_tile<C>(acc);
+  gemm_kmajor<C, true, false>(acc, PHYS ? p.Eit : p.Et, NP, stage, S, ty, tx);
   __syncthreads();
-  store_tile<NP>(stage, acc, ty, tx);
+  store_tile_t<C>(stage, acc, ty, tx);
   __syncthreads();
-#pragma unroll
-  for (int a = 0; a < TR; ++a)
-#pragma unroll
-    for (int b = 0; b < TR; ++b) acc[a][b] = 0.0;
-  gemm_s_g<NP>(acc, stage, PHYS ? p.E : p.Ei, ty, tx);
-  double rs[TR], cs[TR];
+  zero_tile<C>(acc);
+  gemm_kmajor<C, false, true>(acc, stage, S, PHYS ? p.E : p.Ei, NP, ty, tx);
+  double rs[TR], cs[TC];
 #pragma unroll
   for (int a = 0; a < TR; ++a) {
-    const int8_t hr = sm.hn[2 * ty + 16 * (a >> 1) + (a & 1)];
-    const int8_t hc = sm.hn[2 * tx + 16 * (a >> 1) + (a & 1)];
+    const int8_t hr = sm.hn[row_of<C>(ty, a)];
     rs[a] = PHYS ? hs_vinv(hr, spin, p) : hs_v(hr, spin, p);
-    cs[a] = PHYS ? hs_v(hc, spin, p) : hs_vinv(hc, spin, p);
+  }
+#pragma unroll
+  for (int b = 0; b < TC; ++b) {
+    const int8_t hc = sm.hn[col_of<C>(tx, b)];
+    cs[b] = PHYS ? hs_v(hc, spin, p) : hs_vinv(hc, spin, p);
   }
 #pragma unroll
   for (int a = 0; a < TR; ++a)
 #pragma unroll
-    for (int b = 0; b < TR; ++b) g[a][b] = acc[a][b] * rs[a] * cs[b];
+    for (int b = 0; b < TC; ++b) g[a][b] = acc[a][b] * rs[a] * cs[b];
 }
 
 // ---- the N proposals of one time slice ---------------------------------------------------------------
-// lqmc.py:311-335.  All 128 threads evaluate the same ratio from the same shared-memory numbers, so the
+// lqmc.py:311-335.  Every thread evaluates the same ratio from the same shared-memory numbers, so the
 // accept decision is CTA-uniform without communication.  The diagonal is kept lazily: d[] holds G_jj as of
 // the previous accepted flip and the current value is d[j] - e[j]*c[j] with that flip's vectors, which is
 // exactly the arithmetic the tile owner applies.  One bar.sync per accepted flip, none per rejected one.
-template <int NP, bool EXACT, bool PHYS>
-__device__ void propose_slice(double (&g)[RegCfg<NP>::TR][RegCfg<NP>::TR], RegSmem<NP>& sm, const SweepParams& p,
-                              long long trace_base, int spin, int t, int ty, int tx, int& n_accepted) {
-  constexpr int TR = RegCfg<NP>::TR;
+template <class C, bool EXACT, bool PHYS>
+__device__ void propose_slice(double (&g)[C::TR][C::TC], RegSmem<C>& sm, const SweepParams& p, long long trace_base, int spin,
+                              int t, int ty, int tx, int& n_accepted) {
+  constexpr int TR = C::TR, TC = C::TC, NP = C::NP, GY = C::GY, GX = C::GX, GMIN = C::GMIN;
+  constexpr int RY = GY / GMIN, RX = GX / GMIN;
   const int N = p.n_sites;
-  if (ty == tx) {
-#pragma unroll
-    for (int a = 0; a < TR; ++a) sm.d[spin * NP + 2 * ty + 16 * (a >> 1) + (a & 1)] = g[a][a];
-  }
+  store_diag<C>(sm.d + spin * NP, g, ty, tx);
   if (t < NP) {
     sm.e[spin * NP + t] = 0.0; sm.e[2 * NP + spin * NP + t] = 0.0;
     sm.c[spin * NP + t] = 0.0; sm.c[2 * NP + spin * NP + t] = 0.0;
@@ -363,13 +391,14 @@ __device__ void propose_slice(double (&g)[RegCfg<NP>::TR][RegCfg<NP>::TR], RegSm
   __syncthreads();
   int cur = 0;
 #pragma unroll
-  for (int q = 0; q < TR / 2; ++q) {
+  for (int j = 0; j < NP / (2 * GMIN); ++j) {
 #pragma unroll 1
-    for (int tyi = 0; tyi < 8; ++tyi) {
+    for (int m = 0; m < GMIN; ++m) {
 #pragma unroll
       for (int s = 0; s < 2; ++s) {
-        const int i = 16 * q + 2 * tyi + s;
-        const int li = 2 * q + s;               // local row / column index of site i in its owners' tiles
+        const int i = 2 * GMIN * j + 2 * m + s;
+        const int ty_i = GMIN * (j % RY) + m, tx_i = GMIN * (j % RX) + m;   // owners of row i / column i
+        const int ai = 2 * (j / RY) + s, bi = 2 * (j / RX) + s;            // their local row / column index
         if (i < N) {
           const int8_t h = sm.h[i];
           const double* ec = sm.e + cur * 2 * NP;
@@ -396,64 +425,69 @@ __device__ void propose_slice(double (&g)[RegCfg<NP>::TR][RegCfg<NP>::TR], RegSm
             if (!PHYS) {
               // parity: gamma_up = exp(-arg)-1, gamma_dn = exp(+arg)-1 (lqmc.py:320-323)
               const double gamma = spin ? fu : fd;
-              if (ty == tyi) {
-                double cv[TR];
+              if (ty == ty_i) {
+                double cv[TC];
 #pragma unroll
-                for (int b = 0; b < TR; ++b) cv[b] = __dmul_rn(-gamma, g[li][b]);
-                if (tx == tyi) cv[li] = __dadd_rn(cv[li], gamma);
+                for (int b = 0; b < TC; ++b) cv[b] = __dmul_rn(-gamma, g[ai][b]);
+                if (tx == tx_i) cv[bi] = __dadd_rn(cv[bi], gamma);
 #pragma unroll
-                for (int b = 0; b < TR; b += 2)
-                  *reinterpret_cast<double2*>(cn + 2 * tx + 16 * (b >> 1)) = make_double2(cv[b], cv[b + 1]);
+                for (int b = 0; b < TC; b += 2)
+                  *reinterpret_cast<double2*>(cn + 2 * tx + 2 * GX * (b >> 1)) = make_double2(cv[b], cv[b + 1]);
               }
-              if (tx == tyi) {
+              if (tx == tx_i) {
                 const double ci = __dadd_rn(__dmul_rn(-gamma, gs), gamma);
                 const double den = __dadd_rn(1.0, ci);
+                const double r = __drcp_rn(den);
                 double ev[TR];
                 if (EXACT) {
+                  const bool ok = div_safe(den);
 #pragma unroll
-                  for (int a = 0; a < TR; ++a) ev[a] = __ddiv_rn(g[a][li], den);
+                  for (int a = 0; a < TR; ++a) ev[a] = div_shared_rcp(g[a][bi], den, r, ok);
                 } else {
-                  const double r = __drcp_rn(den);
 #pragma unroll
-                  for (int a = 0; a < TR; ++a) ev[a] = g[a][li] * r;
+                  for (int a = 0; a < TR; ++a) ev[a] = g[a][bi] * r;
                 }
 #pragma unroll
                 for (int a = 0; a < TR; a += 2)
-                  *reinterpret_cast<double2*>(en + 2 * ty + 16 * (a >> 1)) = make_double2(ev[a], ev[a + 1]);
+                  *reinterpret_cast<double2*>(en + 2 * ty + 2 * GY * (a >> 1)) = make_double2(ev[a], ev[a + 1]);
               }
             } else {
               // physics: G <- G - (e_i - G[:,i]) (Delta/R) G[i,:],  Delta = exp(2 sigma lamb h) - 1
               const double delta = spin ? fd : fu;
               const double rr = spin ? dd : du;
-              if (ty == tyi) {
+              if (ty == ty_i) {
 #pragma unroll
-                for (int b = 0; b < TR; b += 2)
-                  *reinterpret_cast<double2*>(cn + 2 * tx + 16 * (b >> 1)) = make_double2(g[li][b], g[li][b + 1]);
+                for (int b = 0; b < TC; b += 2)
+                  *reinterpret_cast<double2*>(cn + 2 * tx + 2 * GX * (b >> 1)) = make_double2(g[ai][b], g[ai][b + 1]);
               }
-              if (tx == tyi) {
+              if (tx == tx_i) {
                 const double fac = delta / rr;
                 double ev[TR];
 #pragma unroll
-                for (int a = 0; a < TR; ++a) ev[a] = -g[a][li] * fac;
-                if (ty == tyi) ev[li] = (1.0 - g[li][li]) * fac;
+                for (int a = 0; a < TR; ++a) ev[a] = -g[a][bi] * fac;
+                if (ty == ty_i) ev[ai] = (1.0 - g[ai][bi]) * fac;
 #pragma unroll
                 for (int a = 0; a < TR; a += 2)
-                  *reinterpret_cast<double2*>(en + 2 * ty + 16 * (a >> 1)) = make_double2(ev[a], ev[a + 1]);
+                  *reinterpret_cast<double2*>(en + 2 * ty + 2 * GY * (a >> 1)) = make_double2(ev[a], ev[a + 1]);
               }
             }
             __syncthreads();
             cur = nxt;
-            double ev[TR], cv[TR];
+            double ev[TR], cv[TC];
 #pragma unroll
             for (int a = 0; a < TR; a += 2) {
-              const double2 x = *reinterpret_cast<const double2*>(en + 2 * ty + 16 * (a >> 1));
-              const double2 y = *reinterpret_cast<const double2*>(cn + 2 * tx + 16 * (a >> 1));
-              ev[a] = x.x; ev[a + 1] = x.y; cv[a] = y.x; cv[a + 1] = y.y;
+              const double2 x = *reinterpret_cast<const double2*>(en + 2 * ty + 2 * GY * (a >> 1));
+              ev[a] = x.x; ev[a + 1] = x.y;
+            }
+#pragma unroll
+            for (int b = 0; b < TC; b += 2) {
+              const double2 y = *reinterpret_cast<const double2*>(cn + 2 * tx + 2 * GX * (b >> 1));
+              cv[b] = y.x; cv[b + 1] = y.y;
             }
 #pragma unroll
             for (int a = 0; a < TR; ++a)
 #pragma unroll
-              for (int b = 0; b < TR; ++b) g[a][b] = rank1<EXACT>(g[a][b], ev[a], cv[b]);
+              for (int b = 0; b < TC; ++b) g[a][b] = rank1<EXACT>(g[a][b], ev[a], cv[b]);
             if (threadIdx.x == 0) sm.h[i] = -h;
             ++n_accepted;
           }
@@ -463,25 +497,25 @@ __device__ void propose_slice(double (&g)[RegCfg<NP>::TR][RegCfg<NP>::TR], RegSm
   }
 }
 
-template <int NP, bool EXACT, bool PHYS>
-__global__ void __launch_bounds__(128, (NP == 64) ? 3 : 4) sweep_reg_kernel(const SweepParams p) {
-  constexpr int TR = RegCfg<NP>::TR;
+template <class C, bool EXACT, bool PHYS>
+__global__ void __launch_bounds__(C::THREADS, (C::THREADS == 256) ? 2 : 4) sweep_reg_kernel(const SweepParams p) {
+  constexpr int TR = C::TR, TC = C::TC, NP = C::NP, GY = C::GY, TPS = C::TPS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  RegSmem<NP> sm(smem_raw);
+  RegSmem<C> sm(smem_raw);
   const int chain = blockIdx.x;
   const int tid = threadIdx.x;
-  const int spin = tid >> 6, t = tid & 63, ty = t >> 3, tx = t & 7;
+  const int spin = tid / TPS, t = tid % TPS, ty = t % GY, tx = t / GY;
   const int N = p.n_sites, L = p.n_slices;
   int8_t* field = p.field + (size_t)chain * L * NP;
   double* Gc = p.G + ((size_t)chain * 2 + spin) * NP * NP;
   const int n_steps = p.step_hi - p.step_lo;
-  double g[TR][TR];
+  double g[TR][TC];
   int n_accepted = 0;
 
-  if (!p.do_recompute) load_tile<NP>(Gc, NP, g, ty, tx);
+  if (!p.do_recompute) load_tile<C>(Gc, NP, g, ty, tx);
 
   for (int sweep = 0; sweep < p.n_sweeps; ++sweep) {
-    if (p.do_recompute) recompute_g<NP>(g, sm, p, field, p.recompute_l0, spin, t, ty, tx);
+    if (p.do_recompute) recompute_g<C>(g, sm, p, field, p.recompute_l0, spin, t, ty, tx);
     for (int step = p.step_lo; step < p.step_hi; ++step) {
       const int l = L - 1 - step;
       const long long base = (((long long)chain * p.n_sweeps + sweep) * n_steps + (step - p.step_lo)) * N;
@@ -498,7 +532,7 @@ __global__ void __launch_bounds__(128, (NP == 64) ? 3 : 4) sweep_reg_kernel(cons
           sm.u[tid] = u;
         }
         // propose_slice starts with its own barrier after the diagonal / buffer setup
-        propose_slice<NP, EXACT, PHYS>(g, sm, p, base, spin, t, ty, tx, n_accepted);
+        propose_slice<C, EXACT, PHYS>(g, sm, p, base, spin, t, ty, tx, n_accepted);
         __syncthreads();
         if (tid < NP) field[l * NP + tid] = sm.h[tid];
       }
@@ -506,25 +540,22 @@ __global__ void __launch_bounds__(128, (NP == 64) ? 3 : 4) sweep_reg_kernel(cons
         __syncthreads();
         if (tid < NP) sm.hn[tid] = field[(l - 1) * NP + tid];
         // wrap_g's first barrier (after store_tile) also publishes sm.hn
-        wrap_g<NP, PHYS>(g, sm, p, spin, ty, tx);
+        wrap_g<C, PHYS>(g, sm, p, spin, ty, tx);
       }
     }
     if (p.measure) {
       double* gs = p.g_sum + ((size_t)chain * 2 + spin) * N * N;
 #pragma unroll
       for (int a = 0; a < TR; ++a) {
-        const int row = 2 * ty + 16 * (a >> 1) + (a & 1);
+        const int row = row_of<C>(ty, a);
 #pragma unroll
-        for (int b = 0; b < TR; ++b) {
-          const int col = 2 * tx + 16 * (b >> 1) + (b & 1);
+        for (int b = 0; b < TC; ++b) {
+          const int col = col_of<C>(tx, b);
           if (row < N && col < N) gs[row * N + col] += g[a][b];
         }
       }
       __syncthreads();
-      if (ty == tx) {
-#pragma unroll
-        for (int a = 0; a < TR; ++a) sm.d[spin * NP + 2 * ty + 16 * (a >> 1) + (a & 1)] = g[a][a];
-      }
+      store_diag<C>(sm.d + spin * NP, g, ty, tx);
       __syncthreads();
       if (tid < N) {
         const double nu = 1.0 - sm.d[tid], nd = 1.0 - sm.d[NP + tid];
@@ -539,12 +570,38 @@ __global__ void __launch_bounds__(128, (NP == 64) ? 3 : 4) sweep_reg_kernel(cons
   // hand the Green's functions back (lqmc.py:347) and account the accepted flips
 #pragma unroll
   for (int a = 0; a < TR; ++a) {
-    const int row = 2 * ty + 16 * (a >> 1) + (a & 1);
+    const int row = row_of<C>(ty, a);
 #pragma unroll
-    for (int q = 0; q < TR / 2; ++q)
-      *reinterpret_cast<double2*>(Gc + row * NP + 2 * tx + 16 * q) = make_double2(g[a][2 * q], g[a][2 * q + 1]);
+    for (int q = 0; q < TC / 2; ++q)
+      *reinterpret_cast<double2*>(Gc + row * NP + 2 * tx + 2 * C::GX * q) = make_double2(g[a][2 * q], g[a][2 * q + 1]);
   }
   if (tid == 0 && n_accepted) p.n_acc[chain] += n_accepted;
+}
+
+// ---- device self-test of the shared-reciprocal division ---------------------------------------------------
+__global__ void division_selftest_kernel(unsigned long long n_per_thread, uint64_t seed, unsigned long long* mismatches) {
+  const uint64_t tid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  unsigned long long bad = 0;
+  for (unsigned long long it = 0; it < n_per_thread; ++it) {
+    uint32_t c[4] = {(uint32_t)it, (uint32_t)(it >> 32), (uint32_t)tid, (uint32_t)(tid >> 32)};
+    lqmc_philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    // mantissas fully random; exponents within +-300 of 1; every 8th denominator gets an all-ones or
+    // one-hot mantissa tail (the hard cases for reciprocal-based division)
+    uint64_t mx = ((uint64_t)c[0] << 20) ^ c[1];
+    uint64_t md = ((uint64_t)c[2] << 20) ^ c[3];
+    mx &= 0x000fffffffffffffull; md &= 0x000fffffffffffffull;
+    if ((it & 7) == 1) md |= 0x000ffffffffff000ull;
+    if ((it & 7) == 2) md &= 0x000ff00000000001ull;
+    if ((it & 7) == 3) mx |= 0x000fffffffffff00ull;
+    const int ex = (int)(c[0] % 601u) - 300, ed = (int)(c[3] % 601u) - 300;
+    const uint64_t sx = (uint64_t)(c[1] & 1u) << 63, sd = (uint64_t)(c[2] & 1u) << 63;
+    const double x = __longlong_as_double((long long)(sx | ((uint64_t)(1023 + ex) << 52) | mx));
+    const double d = __longlong_as_double((long long)(sd | ((uint64_t)(1023 + ed) << 52) | md));
+    const double ref = __ddiv_rn(x, d);
+    const double got = div_shared_rcp(x, d, __drcp_rn(d), div_safe(d));
+    if (__double_as_longlong(ref) != __double_as_longlong(got)) ++bad;
+  }
+  if (bad) atomicAdd(mismatches, bad);
 }
 
 }  // namespace lqmc

@@ -23,7 +23,7 @@ EXPORTS = (
     "lqmc_recompute", "lqmc_slice", "lqmc_wrap", "lqmc_sweep", "lqmc_sweep_async", "lqmc_sync",
     "lqmc_get_trace", "lqmc_get_measurements", "lqmc_reset_measurements", "lqmc_device_ptr", "lqmc_info",
     "lqmc_set_sweep_counter", "lqmc_set_chain_offset", "lqmc_philox_uniforms", "lqmc_last_error",
-    "lqmc_version",
+    "lqmc_version", "lqmc_selftest_division",
 )
 
 
@@ -71,6 +71,7 @@ def load_library(path=None):
     lib.lqmc_set_chain_offset.argtypes = [vp, ctypes.c_int64]
     lib.lqmc_philox_uniforms.argtypes = [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int, c_dp]
     lib.lqmc_philox_uniforms.restype = None
+    lib.lqmc_selftest_division.argtypes = [ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint64)]
     lib.lqmc_last_error.restype = ctypes.c_char_p
     lib.lqmc_version.restype = ctypes.c_char_p
     for name in EXPORTS:
@@ -88,6 +89,16 @@ def philox_uniforms(seed, chain, sweep, n_proposals):
     out = np.empty(n_proposals, dtype=np.float64)
     load_library().lqmc_philox_uniforms(seed, chain, sweep, n_proposals, out.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
     return out
+
+
+def selftest_division(n_samples=1 << 28, seed=1, device=0):
+    """Number of (x, d) pairs for which the kernel's shared-reciprocal division differs from IEEE."""
+    bad = ctypes.c_uint64()
+    lib = load_library()
+    rc = lib.lqmc_selftest_division(device, n_samples, seed, ctypes.byref(bad))
+    if rc:
+        raise EngineError(lib.lqmc_last_error().decode())
+    return bad.value
 
 
 def hs_constants(lamb):

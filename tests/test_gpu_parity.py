@@ -305,3 +305,12 @@ def test_drop_in_latticeqmc_update_step(golden):
     np.random.randint(0, 2, size=(4, 20))
     np.random.rand(4 * 80)
     assert np.array_equal(np.random.get_state()[1], state[1]) and np.random.get_state()[2] == state[2]
+
+
+def test_shared_reciprocal_division_is_ieee():
+    """The EXACT mode divides column i by one denominator through r = RN(1/d) and two FMA corrections
+    (sweep_reg.cuh: div_shared_rcp).  2^28 random pairs incl. all-ones / sparse mantissas must be
+    bit-identical to IEEE division - what np.divide does at lqmc.py:326-327."""
+    from latticeqmc_b200.engine import selftest_division
+    assert selftest_division(1 << 28, seed=12345) == 0
+    assert selftest_division(1 << 26, seed=777) == 0
