@@ -141,7 +141,7 @@ int run(lqmc_engine* e, int n_sweeps, int step_lo, int step_hi, bool recompute, 
       default: return fail(LQMC_ERR_UNSUPPORTED, "no register-resident kernel for padded size %d", e->NP);
     }
   } else {
-    rc = lqmc::launch_l2(e->l2, p, e->flags, s, &e->launches, g_err, sizeof(g_err));
+    rc = lqmc::launch_l2(e->l2, p, e->NP, e->flags, s, &e->launches, g_err, sizeof(g_err));
     if (rc) return rc;
   }
   return rc;

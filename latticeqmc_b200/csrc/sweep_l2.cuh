@@ -1,7 +1,30 @@
-// Large-lattice sweep path (N > 64): G lives in HBM / L2, one CTA per chain.
-// Placeholder interface; the kernels land in the next milestone.
+// Large-lattice sweep kernel (64 < N <= 1024): one CTA per Markov chain, Green's functions in HBM / L2.
+//
+// Same reference path as sweep_reg.cuh (LatticeQMC._update_step, /root/reference/lqmc/lqmc.py:301-347), for
+// lattices whose two N x N FP64 Green's functions (1 MiB at 16x16, 5 MiB at 24x24) no longer fit one SM's
+// registers.  Three things change:
+//
+//  * Delayed rank-k updates.  An accepted flip does not touch G in memory.  Its Sherman-Morrison vectors
+//    (e, c) are appended to shared-memory buffers U, W; the row and column of the *current* G that the next
+//    flip needs are rebuilt on the fly as  G0[i,:] - sum_m U_m[i] W_m[:]  (and likewise the column), and the
+//    diagonal is carried along in shared memory.  After KD flips (or at the end of the slice) the block
+//    G0 <- G0 - U W^T is applied in one pass.  The undelayed update moves 32 N^2 bytes per accepted flip
+//    (2 MiB at N = 256); delaying divides that by KD.  In EXACT mode every element sees the same sequence of
+//    multiply-then-subtract roundings as the reference's one-flip-at-a-time loop (lqmc.py:328-331), so the
+//    delayed path is bit-identical to the undelayed one, not merely close.
+//  * The accept/reject scan is lane-parallel: a warp evaluates the ratios of the next 32 sites at once from
+//    the shared diagonal; the first accepted site is found with a ballot, everything before it is rejected
+//    for free (no flip happened in between, so those ratios were final).
+//  * Wrap and sweep-start product are tiled GEMMs (64 x 128 block tile, 4 x 8 per thread, k-major operand
+//    panels staged global -> shared with cp.async double buffering); the left operand is always kept
+//    k-major (transposed) in memory so both panels are contiguous row copies.  exp(V_l) is applied as a
+//    row / column scale in the epilogue.
+//
+// FP64 has no tcgen05 kind, and DMMA issues to the same pipe as DFMA on sm_100a (profiles/fp64_peaks_r01.json),
+// so these GEMMs are register-tiled DFMA kernels measured against the FP64 pipe peak.
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_pipeline_primitives.h>
 #include <stdint.h>
 #include <stdio.h>
 #include "sweep_reg.cuh"
@@ -9,20 +32,599 @@
 namespace lqmc {
 
 struct L2Workspace {
-  double* T = nullptr;      // [chain][2][NP][NP] scratch for the two-GEMM wrap / running product
+  double* T = nullptr;      // [chain][2][NP][NP] second matrix buffer (two-GEMM wrap, running product)
+  int kd = 0;               // delay depth the shared-memory budget allows
+  size_t smem = 0;          // dynamic shared memory per CTA
 };
 
-inline int l2_padded_size(int n_sites) { (void)n_sites; return -1; }
+constexpr int L2_THREADS = 256;
+constexpr int L2_BM = 64, L2_BN = 128, L2_BK = 16;     // block tile and k-panel depth
+constexpr int L2_GY = 16, L2_GX = 16;                  // thread grid inside a block tile: 4 x 8 per thread
+constexpr int L2_MAXQ = 4;                             // indices per thread in the vector phases (NP <= 1024)
 
-inline int l2_alloc(L2Workspace&, int, int, int, int, char* err, size_t errlen) {
-  snprintf(err, errlen, "large-lattice path not built yet");
-  return 3;
+inline int l2_padded_size(int n_sites) {
+  const int np = (n_sites + 127) / 128 * 128;
+  return np <= 1024 ? np : -1;
+}
+
+struct L2Smem {
+  // vector phase
+  double* U;      // [2 spin][KD][NP]   e vectors of the delayed flips
+  double* W;      // [2 spin][KD][NP]   c vectors
+  double* d;      // [2 buf][2 spin][NP] current diagonal, double-buffered across flips
+  double* u;      // [NP]               uniforms of the slice
+  double* red_v;  // [16]
+  int* red_i;     // [16]
+  int8_t* h;      // [NP]
+  int8_t* hn;     // [NP]
+  // GEMM phase (aliases U / W)
+  double* pa;     // [2 stage][BK][BM]
+  double* pb;     // [2 stage][BK][BN]
+  __device__ L2Smem(unsigned char* base, int NP, int KD) {
+    U = reinterpret_cast<double*>(base);
+    W = U + (size_t)2 * KD * NP;
+    pa = U;
+    pb = pa + 2 * L2_BK * L2_BM;
+    double* tail = W + (size_t)2 * KD * NP;
+    const size_t gemm_end = (size_t)2 * L2_BK * (L2_BM + L2_BN);
+    if ((size_t)4 * KD * NP < gemm_end) tail = U + gemm_end;
+    d = tail;
+    u = d + 4 * NP;
+    red_v = u + NP;
+    red_i = reinterpret_cast<int*>(red_v + 16);
+    h = reinterpret_cast<int8_t*>(red_i + 16);
+    hn = h + NP;
+  }
+};
+
+inline size_t l2_smem_bytes(int NP, int KD) {
+  size_t vec = (size_t)4 * KD * NP;
+  const size_t gemm = (size_t)2 * L2_BK * (L2_BM + L2_BN);
+  if (vec < gemm) vec = gemm;
+  return (vec + 5 * (size_t)NP + 16) * sizeof(double) + 16 * sizeof(int) + 2 * (size_t)NP + 16;
+}
+
+// ---- tiled GEMM:  C = A * B  with A given k-major (At[k*NP + i] = A[i][k]) and B row-major ------------------
+// Epilogue: C[i][j] *= rs(i) * cs(j) (+ 1 on the diagonal if add_identity); stored row-major or transposed.
+struct L2Epilogue {
+  const int8_t* hrow = nullptr;   // field column for the row scale, nullptr = 1
+  const int8_t* hcol = nullptr;   // field column for the column scale, nullptr = 1
+  bool row_inv = false;           // row scale uses exp(+sigma lamb h) instead of exp(-sigma lamb h)
+  bool col_inv = false;
+  bool transposed_out = false;
+  bool add_identity = false;
+};
+
+__device__ __forceinline__ void l2_issue_panel(const double* __restrict__ At, const double* __restrict__ B, int NP, int i0, int j0,
+                                               int k0, double* pa, double* pb, int tid) {
+  // A panel: BK rows of BM doubles (512 B each); B panel: BK rows of BN doubles (1 KiB each); 16-byte chunks
+  for (int c = tid; c < L2_BK * (L2_BM / 2); c += L2_THREADS) {
+    const int r = c / (L2_BM / 2), x = c % (L2_BM / 2);
+    __pipeline_memcpy_async(pa + r * L2_BM + 2 * x, At + (size_t)(k0 + r) * NP + i0 + 2 * x, 16);
+  }
+  for (int c = tid; c < L2_BK * (L2_BN / 2); c += L2_THREADS) {
+    const int r = c / (L2_BN / 2), x = c % (L2_BN / 2);
+    __pipeline_memcpy_async(pb + r * L2_BN + 2 * x, B + (size_t)(k0 + r) * NP + j0 + 2 * x, 16);
+  }
+  __pipeline_commit();
+}
+
+__device__ void l2_gemm(const double* __restrict__ At, const double* __restrict__ B, double* __restrict__ Cout, int NP, int spin,
+                        const L2Epilogue& ep, const SweepParams& p, L2Smem& sm) {
+  const int tid = threadIdx.x;
+  const int ty = tid % L2_GY, tx = tid / L2_GY;
+  const int nk = NP / L2_BK;
+  for (int i0 = 0; i0 < NP; i0 += L2_BM) {
+    for (int j0 = 0; j0 < NP; j0 += L2_BN) {
+      double acc[4][8];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) acc[a][b] = 0.0;
+      __syncthreads();                       // previous users of the panels are done
+      l2_issue_panel(At, B, NP, i0, j0, 0, sm.pa, sm.pb, tid);
+      for (int kp = 0; kp < nk; ++kp) {
+        const int st = kp & 1;
+        if (kp + 1 < nk) {
+          l2_issue_panel(At, B, NP, i0, j0, (kp + 1) * L2_BK, sm.pa + (st ^ 1) * L2_BK * L2_BM, sm.pb + (st ^ 1) * L2_BK * L2_BN, tid);
+          __pipeline_wait_prior(1);
+        } else {
+          __pipeline_wait_prior(0);
+        }
+        __syncthreads();
+        const double* ap = sm.pa + st * L2_BK * L2_BM + 2 * ty;
+        const double* bp = sm.pb + st * L2_BK * L2_BN + 2 * tx;
+#pragma unroll 4
+        for (int k = 0; k < L2_BK; ++k) {
+          double a[4], b[8];
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const double2 v = *reinterpret_cast<const double2*>(ap + k * L2_BM + 2 * L2_GY * q);
+            a[2 * q] = v.x; a[2 * q + 1] = v.y;
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const double2 w = *reinterpret_cast<const double2*>(bp + k * L2_BN + 2 * L2_GX * q);
+            b[2 * q] = w.x; b[2 * q + 1] = w.y;
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();                     // stage st may be refilled two iterations from now
+      }
+      // epilogue
+      double rs[4], cs[8];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const int row = i0 + 2 * ty + 2 * L2_GY * (a >> 1) + (a & 1);
+        rs[a] = ep.hrow ? (ep.row_inv ? hs_vinv(ep.hrow[row], spin, p) : hs_v(ep.hrow[row], spin, p)) : 1.0;
+      }
+#pragma unroll
+      for (int b = 0; b < 8; ++b) {
+        const int col = j0 + 2 * tx + 2 * L2_GX * (b >> 1) + (b & 1);
+        cs[b] = ep.hcol ? (ep.col_inv ? hs_vinv(ep.hcol[col], spin, p) : hs_v(ep.hcol[col], spin, p)) : 1.0;
+      }
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const int row = i0 + 2 * ty + 2 * L2_GY * (a >> 1) + (a & 1);
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+          const int col = j0 + 2 * tx + 2 * L2_GX * (b >> 1) + (b & 1);
+          double v = acc[a][b];
+          if (ep.hrow) v *= rs[a];
+          if (ep.hcol) v *= cs[b];
+          if (ep.add_identity && row == col) v += 1.0;
+          acc[a][b] = v;
+        }
+      }
+      if (!ep.transposed_out) {
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          const int row = i0 + 2 * ty + 2 * L2_GY * (a >> 1) + (a & 1);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<double2*>(Cout + (size_t)row * NP + j0 + 2 * tx + 2 * L2_GX * q) = make_double2(acc[a][2 * q], acc[a][2 * q + 1]);
+        }
+      } else {
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+          const int col = j0 + 2 * tx + 2 * L2_GX * (b >> 1) + (b & 1);
+#pragma unroll
+          for (int q = 0; q < 2; ++q)
+            *reinterpret_cast<double2*>(Cout + (size_t)col * NP + i0 + 2 * ty + 2 * L2_GY * q) = make_double2(acc[2 * q][b], acc[2 * q + 1][b]);
+        }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// ---- G0 <- G0 - sum_m U_m W_m^T for both spins (the delayed block update) -----------------------------------
+template <bool EXACT>
+__device__ void l2_flush(double* __restrict__ Gc, int NP, int nd, L2Smem& sm, int KD) {
+  const int tid = threadIdx.x;
+  const int ty = tid % L2_GY, tx = tid / L2_GY;
+  for (int spin = 0; spin < 2; ++spin) {
+    double* G = Gc + (size_t)spin * NP * NP;
+    const double* U = sm.U + (size_t)spin * KD * NP;
+    const double* W = sm.W + (size_t)spin * KD * NP;
+    for (int i0 = 0; i0 < NP; i0 += L2_BM) {
+      for (int j0 = 0; j0 < NP; j0 += L2_BN) {
+        double g[4][8];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          const int row = i0 + 2 * ty + 2 * L2_GY * (a >> 1) + (a & 1);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const double2 v = *reinterpret_cast<const double2*>(G + (size_t)row * NP + j0 + 2 * tx + 2 * L2_GX * q);
+            g[a][2 * q] = v.x; g[a][2 * q + 1] = v.y;
+          }
+        }
+        for (int m = 0; m < nd; ++m) {
+          double e[4], c[8];
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const double2 v = *reinterpret_cast<const double2*>(U + (size_t)m * NP + i0 + 2 * ty + 2 * L2_GY * q);
+            e[2 * q] = v.x; e[2 * q + 1] = v.y;
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const double2 w = *reinterpret_cast<const double2*>(W + (size_t)m * NP + j0 + 2 * tx + 2 * L2_GX * q);
+            c[2 * q] = w.x; c[2 * q + 1] = w.y;
+          }
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 8; ++b) g[a][b] = rank1<EXACT>(g[a][b], e[a], c[b]);
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          const int row = i0 + 2 * ty + 2 * L2_GY * (a >> 1) + (a & 1);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<double2*>(G + (size_t)row * NP + j0 + 2 * tx + 2 * L2_GX * q) = make_double2(g[a][2 * q], g[a][2 * q + 1]);
+        }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// ---- the N proposals of one slice with delayed updates ------------------------------------------------------
+template <bool EXACT, bool PHYS>
+__device__ void l2_propose_slice(double* __restrict__ Gc, int NP, int KD, L2Smem& sm, const SweepParams& p, long long trace_base,
+                                 int& n_accepted) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int N = p.n_sites;
+  // diagonal of both spins
+  for (int x = tid; x < 2 * NP; x += L2_THREADS) {
+    const int spin = x / NP, j = x % NP;
+    sm.d[x] = Gc[(size_t)spin * NP * NP + (size_t)j * NP + j];
+  }
+  __syncthreads();
+  int nd = 0;
+  int i0 = 0;
+  int cur = 0;                  // diagonal buffer the scan reads; a flip writes the other one (slower warps may still be scanning)
+  while (i0 < N) {
+    const double* dcur = sm.d + cur * 2 * NP;
+    double* dnxt = sm.d + (cur ^ 1) * 2 * NP;
+    // lane-parallel scan of sites i0 .. i0+31
+    const int i = i0 + lane;
+    bool acc = false;
+    double gu = 0.0, gd = 0.0, ratio = 0.0;
+    int8_t h = 1;
+    if (i < N) {
+      h = sm.h[i];
+      gu = dcur[i];
+      gd = dcur[NP + i];
+      const double fu = (h > 0) ? p.f_p2 : p.f_m2;
+      const double fd = (h > 0) ? p.f_m2 : p.f_p2;
+      const double du = __dadd_rn(1.0, __dmul_rn(__dsub_rn(1.0, gu), fu));
+      const double dd = __dadd_rn(1.0, __dmul_rn(__dsub_rn(1.0, gd), fd));
+      ratio = __dmul_rn(du, dd);
+      acc = sm.u[i] <= ratio;
+    }
+    const unsigned ballot = __ballot_sync(0xffffffffu, acc);
+    const int first = ballot ? (__ffs(ballot) - 1) : 32;
+    if (p.tr_ratio != nullptr && tid < 32 && i < N && lane <= first) {
+      p.tr_ratio[trace_base + i] = ratio;
+      p.tr_acc[trace_base + i] = (lane == first) ? 1 : 0;
+    }
+    if (!ballot) { i0 += 32; continue; }
+    const int is = i0 + first;
+    gu = __shfl_sync(0xffffffffu, gu, first);
+    gd = __shfl_sync(0xffffffffu, gd, first);
+    const int hs = __shfl_sync(0xffffffffu, (int)h, first);
+    const double fu = (hs > 0) ? p.f_p2 : p.f_m2;
+    const double fd = (hs > 0) ? p.f_m2 : p.f_p2;
+    // rebuild row `is` and column `is` of the current G: thread handles entries j = tid + 256 q of both spins
+#pragma unroll
+    for (int spin = 0; spin < 2; ++spin) {
+      const double* G = Gc + (size_t)spin * NP * NP;
+      const double* U = sm.U + (size_t)spin * KD * NP;
+      const double* W = sm.W + (size_t)spin * KD * NP;
+      const double gs = spin ? gd : gu;
+      double row[L2_MAXQ], col[L2_MAXQ];
+#pragma unroll
+      for (int q = 0; q < L2_MAXQ; ++q) {
+        const int j = tid + L2_THREADS * q;
+        if (j < NP) { row[q] = G[(size_t)is * NP + j]; col[q] = G[(size_t)j * NP + is]; }
+      }
+      for (int m = 0; m < nd; ++m) {
+        const double ui = U[(size_t)m * NP + is], wi = W[(size_t)m * NP + is];
+#pragma unroll
+        for (int q = 0; q < L2_MAXQ; ++q) {
+          const int j = tid + L2_THREADS * q;
+          if (j < NP) {
+            row[q] = rank1<EXACT>(row[q], ui, W[(size_t)m * NP + j]);
+            col[q] = rank1<EXACT>(col[q], U[(size_t)m * NP + j], wi);
+          }
+        }
+      }
+      double* Un = sm.U + ((size_t)spin * KD + nd) * NP;
+      double* Wn = sm.W + ((size_t)spin * KD + nd) * NP;
+      if (!PHYS) {
+        const double gamma = spin ? fu : fd;            // exp(-arg)-1 for up, exp(+arg)-1 for down (lqmc.py:320-323)
+        const double ci = __dadd_rn(__dmul_rn(-gamma, gs), gamma);
+        const double den = __dadd_rn(1.0, ci);
+        const double r = __drcp_rn(den);
+        const bool ok = div_safe(den);
+#pragma unroll
+        for (int q = 0; q < L2_MAXQ; ++q) {
+          const int j = tid + L2_THREADS * q;
+          if (j < NP) {
+            double c = __dmul_rn(-gamma, row[q]);
+            if (j == is) c = __dadd_rn(c, gamma);
+            const double e = EXACT ? div_shared_rcp(col[q], den, r, ok) : col[q] * r;
+            Un[j] = e; Wn[j] = c;
+            dnxt[spin * NP + j] = rank1<EXACT>(dcur[spin * NP + j], e, c);
+          }
+        }
+      } else {
+        const double delta = spin ? fd : fu;
+        const double rr = __dadd_rn(1.0, __dmul_rn(__dsub_rn(1.0, gs), delta));
+        const double fac = delta / rr;
+#pragma unroll
+        for (int q = 0; q < L2_MAXQ; ++q) {
+          const int j = tid + L2_THREADS * q;
+          if (j < NP) {
+            const double e = ((j == is) ? (1.0 - col[q]) : -col[q]) * fac;
+            const double c = row[q];
+            Un[j] = e; Wn[j] = c;
+            dnxt[spin * NP + j] = rank1<EXACT>(dcur[spin * NP + j], e, c);
+          }
+        }
+      }
+    }
+    ++n_accepted;
+    ++nd;
+    cur ^= 1;
+    __syncthreads();
+    if (tid == 0) sm.h[is] = (int8_t)(-hs);     // after the barrier: no warp is still scanning site `is`
+    if (nd == KD) { l2_flush<EXACT>(Gc, NP, nd, sm, KD); nd = 0; }
+    i0 = is + 1;
+  }
+  if (nd > 0) l2_flush<EXACT>(Gc, NP, nd, sm, KD);
+}
+
+// ---- Gauss-Jordan inverse in global memory (both spins, in place), partial pivoting ----------------------------
+// np.linalg.inv of the sweep-start matrix (lqmc.py:306-307).  One rank-1 pass over the matrix per pivot; rows are
+// swapped physically, columns are un-permuted at the end.  rowk / fcol live in the (idle) U / W buffers.
+__device__ void l2_gj_inverse(double* __restrict__ Gc, int NP, L2Smem& sm, int* piv_global) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ty = tid % L2_GY, tx = tid / L2_GY;
+  for (int spin = 0; spin < 2; ++spin) {
+    double* M = Gc + (size_t)spin * NP * NP;
+    double* rowk = sm.U;          // [NP]
+    double* fcol = sm.U + NP;     // [NP]
+    int* piv = piv_global + spin * NP;
+    for (int k = 0; k < NP; ++k) {
+      // pivot search over rows >= k of column k
+      double pv = 0.0, av = -1.0;
+      int idx = NP;
+      for (int r = k + tid; r < NP; r += L2_THREADS) {
+        const double v = M[(size_t)r * NP + k];
+        const double a = fabs(v);
+        if (a > av) { av = a; pv = v; idx = r; }
+      }
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) {
+        const double oa = __shfl_down_sync(0xffffffffu, av, off);
+        const double op = __shfl_down_sync(0xffffffffu, pv, off);
+        const int oi = __shfl_down_sync(0xffffffffu, idx, off);
+        if (oa > av || (oa == av && oi < idx)) { av = oa; pv = op; idx = oi; }
+      }
+      if (lane == 0) { sm.red_v[warp] = pv; sm.red_i[warp] = idx; }
+      const double akk = M[(size_t)k * NP + k];
+      __syncthreads();
+      pv = sm.red_v[0]; idx = sm.red_i[0];
+#pragma unroll
+      for (int w = 1; w < L2_THREADS / 32; ++w) {
+        const double ov = sm.red_v[w];
+        const int oi = sm.red_i[w];
+        if (oi < NP && (idx >= NP || fabs(ov) > fabs(pv) || (fabs(ov) == fabs(pv) && oi < idx))) { pv = ov; idx = oi; }
+      }
+      if (idx >= NP) idx = k;
+      if (tid == 0) piv[k] = idx;
+      // multipliers (column k before it is rewritten) and the swapped, scaled pivot row
+      for (int r = tid; r < NP; r += L2_THREADS) {
+        double f = (r == idx && idx != k) ? akk : M[(size_t)r * NP + k];
+        if (r == k) f = 0.0;
+        fcol[r] = f;
+      }
+      __syncthreads();
+      for (int c = tid; c < NP; c += L2_THREADS) {
+        const double ak = M[(size_t)k * NP + c];
+        const double ap = M[(size_t)idx * NP + c];
+        const double x = ((c == k) ? 1.0 : ap) / pv;
+        rowk[c] = x;
+        M[(size_t)k * NP + c] = x;
+        if (idx != k) M[(size_t)idx * NP + c] = ak;
+      }
+      __syncthreads();
+      // M[r][c] <- (c == k ? 0 : M[r][c]) - f[r] * rowk[c]   for r != k
+      for (int i0 = 0; i0 < NP; i0 += L2_BM) {
+        for (int j0 = 0; j0 < NP; j0 += L2_BN) {
+#pragma unroll
+          for (int a = 0; a < 4; ++a) {
+            const int row = i0 + 2 * ty + 2 * L2_GY * (a >> 1) + (a & 1);
+            if (row == k) continue;
+            const double f = fcol[row];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int col = j0 + 2 * tx + 2 * L2_GX * q;
+              double2* ptr = reinterpret_cast<double2*>(M + (size_t)row * NP + col);
+              double2 v = *ptr;
+              const double2 rk = *reinterpret_cast<const double2*>(rowk + col);
+              if (col == k) v.x = 0.0;
+              if (col + 1 == k) v.y = 0.0;
+              v.x = fma(-f, rk.x, v.x);
+              v.y = fma(-f, rk.y, v.y);
+              *ptr = v;
+            }
+          }
+        }
+      }
+      __syncthreads();
+    }
+    // undo the row interchanges on the columns, last pivot first
+    for (int r = tid; r < NP; r += L2_THREADS) {
+      double* rp = M + (size_t)r * NP;
+      for (int k = NP - 1; k >= 0; --k) {
+        const int pk = piv[k];
+        if (pk != k) { const double tmp = rp[k]; rp[k] = rp[pk]; rp[pk] = tmp; }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---- sweep-start G = inv(I + prod B) in memory ----------------------------------------------------------------
+__device__ void l2_recompute(double* __restrict__ Gc, double* __restrict__ Tc, int NP, const int8_t* field, int l0,
+                             const SweepParams& p, L2Smem& sm, int* piv_global) {
+  const int L = p.n_slices;
+  const int tid = threadIdx.x;
+  for (int spin = 0; spin < 2; ++spin) {
+    double* G = Gc + (size_t)spin * NP * NP;
+    double* T = Tc + (size_t)spin * NP * NP;
+    // buffers alternate so that the last product reads T and writes row-major into G
+    double* cur = (L % 2 == 0) ? T : G;
+    double* oth = (L % 2 == 0) ? G : T;
+    int l = (l0 - 1 + L) % L;
+    const int8_t* hl = field + (size_t)l * NP;
+    if (L == 1) {
+      for (int x = tid; x < NP * NP; x += L2_THREADS) {
+        const int r = x / NP, c = x % NP;
+        G[x] = p.E[x] * hs_v(hl[c], spin, p) + (r == c ? 1.0 : 0.0);
+      }
+    } else {
+      // first factor, stored k-major (transposed): cur[c][r] = E[r][c] * v_c
+      for (int x = tid; x < NP * NP; x += L2_THREADS) {
+        const int c = x / NP, r = x % NP;
+        cur[x] = p.Et[x] * hs_v(hl[c], spin, p);
+      }
+    }
+    __syncthreads();
+    for (int m = 1; m < L; ++m) {
+      l = (l0 - 1 - m + 2 * L) % L;
+      L2Epilogue ep;
+      ep.hcol = field + (size_t)l * NP;
+      ep.transposed_out = (m != L - 1);
+      ep.add_identity = (m == L - 1);
+      l2_gemm(cur, p.E, oth, NP, spin, ep, p, sm);
+      double* t = cur; cur = oth; oth = t;
+    }
+  }
+  l2_gj_inverse(Gc, NP, sm, piv_global);
+}
+
+// ---- wrap from slice l to l-1 ------------------------------------------------------------------------------
+template <bool PHYS>
+__device__ void l2_wrap(double* __restrict__ Gc, double* __restrict__ Tc, int NP, const int8_t* hprev, const SweepParams& p, L2Smem& sm) {
+  for (int spin = 0; spin < 2; ++spin) {
+    double* G = Gc + (size_t)spin * NP * NP;
+    double* T = Tc + (size_t)spin * NP * NP;
+    L2Epilogue e1;
+    e1.transposed_out = true;
+    l2_gemm(PHYS ? p.Eit : p.Et, G, T, NP, spin, e1, p, sm);           // T^T = (E G)^T   (or E^-1 G)
+    L2Epilogue e2;
+    e2.hrow = hprev; e2.hcol = hprev;
+    e2.row_inv = PHYS; e2.col_inv = !PHYS;
+    l2_gemm(T, PHYS ? p.E : p.Ei, G, NP, spin, e2, p, sm);              // G = D (E G E^-1) D^-1
+  }
+}
+
+struct L2Params {
+  SweepParams p;
+  double* T;
+  int* piv;       // [chain][2][NP] scratch
+  int NP, KD;
+};
+
+template <bool EXACT, bool PHYS>
+__global__ void __launch_bounds__(L2_THREADS, 2) sweep_l2_kernel(const L2Params lp) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const SweepParams& p = lp.p;
+  const int NP = lp.NP, KD = lp.KD;
+  L2Smem sm(smem_raw, NP, KD);
+  const int chain = blockIdx.x, tid = threadIdx.x;
+  const int N = p.n_sites, L = p.n_slices;
+  int8_t* field = p.field + (size_t)chain * L * NP;
+  double* Gc = p.G + (size_t)chain * 2 * NP * NP;
+  double* Tc = lp.T + (size_t)chain * 2 * NP * NP;
+  int* piv = lp.piv + (size_t)chain * 2 * NP;
+  const int n_steps = p.step_hi - p.step_lo;
+  int n_accepted = 0;
+
+  for (int sweep = 0; sweep < p.n_sweeps; ++sweep) {
+    if (p.do_recompute) l2_recompute(Gc, Tc, NP, field, p.recompute_l0, p, sm, piv);
+    for (int step = p.step_lo; step < p.step_hi; ++step) {
+      const int l = L - 1 - step;
+      const long long base = (((long long)chain * p.n_sweeps + sweep) * n_steps + (step - p.step_lo)) * N;
+      if (p.do_propose) {
+        __syncthreads();
+        for (int j = tid; j < NP; j += L2_THREADS) {
+          sm.h[j] = field[(size_t)l * NP + j];
+          double u = 2.0;
+          if (j < N)
+            u = (p.uniforms != nullptr)
+                    ? p.uniforms[base + j]
+                    : lqmc_philox_uniform(p.seed, (uint64_t)(p.chain0 + chain), (uint64_t)(p.sweep0 + sweep), (uint32_t)(step * N + j));
+          sm.u[j] = u;
+        }
+        l2_propose_slice<EXACT, PHYS>(Gc, NP, KD, sm, p, base, n_accepted);
+        __syncthreads();
+        for (int j = tid; j < NP; j += L2_THREADS) field[(size_t)l * NP + j] = sm.h[j];
+      }
+      if (p.do_wrap && l > 0) {
+        __syncthreads();
+        l2_wrap<PHYS>(Gc, Tc, NP, field + (size_t)(l - 1) * NP, p, sm);
+      }
+    }
+    if (p.measure) {
+      __syncthreads();
+      for (int spin = 0; spin < 2; ++spin) {
+        const double* G = Gc + (size_t)spin * NP * NP;
+        double* gs = p.g_sum + ((size_t)chain * 2 + spin) * N * N;
+        for (int x = tid; x < N * N; x += L2_THREADS) {
+          const int r = x / N, c = x % N;
+          gs[x] += G[(size_t)r * NP + c];
+        }
+      }
+      for (int j = tid; j < N; j += L2_THREADS) {
+        const double nu = 1.0 - Gc[(size_t)j * NP + j], nd = 1.0 - Gc[(size_t)NP * NP + (size_t)j * NP + j];
+        double* ob = p.obs_sum + (size_t)chain * 3 * N;
+        ob[j] += nu; ob[N + j] += nd; ob[2 * N + j] += nu * nd;
+      }
+      if (tid == 0) p.n_meas[chain] += 1;
+      __syncthreads();
+    }
+  }
+  if (tid == 0 && n_accepted) p.n_acc[chain] += n_accepted;
+}
+
+// ---- host side ------------------------------------------------------------------------------------------------
+struct L2Host { int* piv = nullptr; };
+
+inline int l2_alloc(L2Workspace& w, int n_sites, int np, int n_slices, int n_chains, char* err, size_t errlen) {
+  (void)n_sites; (void)n_slices;
+  const size_t bytes = (size_t)n_chains * 2 * np * np * sizeof(double) + (size_t)n_chains * 2 * np * sizeof(int);
+  if (cudaMalloc(&w.T, bytes) != cudaSuccess) {
+    snprintf(err, errlen, "cudaMalloc of the %zu-byte GEMM workspace failed", bytes);
+    return 4;
+  }
+  // two CTAs per SM (about 113 KiB each) up to NP = 384, one above
+  const size_t budget = (np <= 384) ? 110 * 1024 : 220 * 1024;
+  int kd = 1;
+  while (kd < 64 && l2_smem_bytes(np, kd + 1) <= budget) ++kd;
+  w.kd = kd;
+  w.smem = l2_smem_bytes(np, kd);
+  return 0;
 }
 inline void l2_free(L2Workspace& w) { if (w.T) cudaFree(w.T); w.T = nullptr; }
 
-inline int launch_l2(L2Workspace&, const SweepParams&, uint32_t, cudaStream_t, long long*, char* err, size_t errlen) {
-  snprintf(err, errlen, "large-lattice path not built yet");
-  return 3;
+inline int launch_l2(L2Workspace& w, const SweepParams& p, int np, uint32_t flags, cudaStream_t s, long long* launches, char* err,
+                     size_t errlen) {
+  L2Params lp;
+  lp.p = p; lp.T = w.T; lp.NP = np; lp.KD = w.kd;
+  lp.piv = reinterpret_cast<int*>(w.T + (size_t)p.n_chains * 2 * np * np);
+  const bool exact = !(flags & 0x2u), phys = (flags & 0x1u) != 0;
+  auto go = [&](auto kernel) -> int {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.smem);
+    if (e == cudaSuccess) {
+      kernel<<<p.n_chains, L2_THREADS, w.smem, s>>>(lp);
+      e = cudaGetLastError();
+    }
+    if (e != cudaSuccess) { snprintf(err, errlen, "sweep_l2_kernel launch failed: %s", cudaGetErrorString(e)); return 2; }
+    *launches += 1;
+    return 0;
+  };
+  if (exact && !phys) return go(sweep_l2_kernel<true, false>);
+  if (!exact && !phys) return go(sweep_l2_kernel<false, false>);
+  if (exact && phys) return go(sweep_l2_kernel<true, true>);
+  return go(sweep_l2_kernel<false, true>);
 }
 
 }  // namespace lqmc

@@ -1,0 +1,123 @@
+"""GPU parity of the large-lattice path (N > 64: G in HBM/L2, delayed rank-k updates, tiled GEMM wrap)
+against the oracle and the 16x16 golden slices recorded from the reference (lqmc.py:301-347)."""
+import numpy as np
+import pytest
+
+from oracle import sweep_oracle as so
+
+pytestmark = pytest.mark.gpu
+RTOL_G = 1e-10
+
+
+def _engine(exp_k, lamb, lt, **kw):
+    from latticeqmc_b200 import SweepEngine
+    return SweepEngine(exp_k, lamb, lt, **kw)
+
+
+def _close(a, b, rtol=RTOL_G):
+    return np.max(np.abs(a - b)) <= rtol * max(np.max(np.abs(b)), 1e-300)
+
+
+def test_cfg4_reference_slices(golden):
+    """BASELINE configs[3] (16x16, U=4, beta=8, L=80): from the reference's sweep-start G, the proposals
+    of slice 79 (every one accepted: 256 flips, i.e. 21 delayed-update flushes at depth 12) must give the
+    reference's accept sequence and - EXACT mode - the reference's G bit for bit; then wrap and slice 78."""
+    g = golden("cfg4_16x16_slices")
+    n, lt = g["field0"].shape
+    lamb = float(g["lamb"])
+    with _engine(g["exp_k"], lamb, lt, trace=True) as eng:
+        assert eng.info()["family"] == "l2"
+        eng.set_field(g["field0"][None])
+        eng.set_g(np.stack([g["g0_up"], g["g0_dn"]])[None])
+        eng.slice(79, g["uniforms"][0][None])
+        acc, ratio = eng.get_trace()
+        assert np.array_equal(acc[0, 0, 0], g["accs"][0])
+        assert np.array_equal(ratio[0, 0, 0], g["ratios"][0])
+        out = eng.get_g()[0]
+        assert np.array_equal(out[0], g["post79_up"]) and np.array_equal(out[1], g["post79_dn"])
+        h79 = eng.get_field()[0]
+        eng.wrap(79)
+        w = eng.get_g()[0]
+        wu, wd = so.wrap(g["post79_up"], g["post79_dn"], h79, 79, g["exp_k"], lamb)
+        assert _close(w[0], wu) and _close(w[1], wd)
+        # teacher-force the oracle's wrapped G so that slice 78 can be compared bit for bit as well
+        eng.set_g(np.stack([wu, wd])[None])
+        eng.slice(78, g["uniforms"][1][None])
+        acc, ratio = eng.get_trace()
+        r78, a78 = so.slice_proposals(wu, wd, h79, 78, lamb, g["uniforms"][1])
+        assert np.array_equal(acc[0, 0, 0], a78) and np.array_equal(ratio[0, 0, 0], r78)
+        out = eng.get_g()[0]
+        assert np.array_equal(out[0], wu) and np.array_equal(out[1], wd)
+        assert np.array_equal(eng.get_field()[0], h79)
+        # and against the reference's own snapshot (its wrap went through this container's BLAS)
+        assert np.array_equal(acc[0, 0, 0], g["accs"][1])
+        assert _close(out[0], g["post78_up"], 1e-9) and _close(out[1], g["post78_dn"], 1e-9)
+
+
+@pytest.mark.parametrize("case", [("square", 9, 4.0, 1.0, 10), ("square", 12, 4.0, 1.0, 8), ("ring", 100, 2.0, 0.8, 8),
+                                   ("square", 16, 4.0, 0.8, 8)])
+def test_recompute_large(case):
+    """Sweep-start G (get_m + inv, lqmc.py:156-185,303-307) on well-conditioned products; N = 81, 144, 100
+    need padding to the 128-wide tile, 256 does not."""
+    kind, size, u, beta, lt = case
+    ham = so.ideal_square_kinetic(size, 1.0, u / 2) if kind == "square" else so.ideal_ring_kinetic(size, 1.0, u / 2)
+    n = ham.shape[0]
+    dtau, lamb, exp_k = so.set_beta_constants(ham, u, beta, lt)
+    fields = np.stack([so.initial_field(n, lt, seed=200 + c) for c in range(2)])
+    with _engine(exp_k, lamb, lt, n_chains=2) as eng:
+        eng.set_field(fields)
+        eng.recompute(0)
+        gg = eng.get_g()
+    for c in range(2):
+        ref = so.sweep_start_g(fields[c], exp_k, lamb)
+        cond = np.linalg.cond(so.get_m(fields[c], exp_k, lamb, 0, +1))
+        tol = max(RTOL_G, 50 * cond * 2.2e-16)
+        assert _close(gg[c, 0], ref[0], tol) and _close(gg[c, 1], ref[1], tol), (case, c, cond)
+
+
+@pytest.mark.parametrize("arith", ["exact", "fma"])
+def test_free_running_sweep_10x10(arith):
+    """N = 100 (padded to 128), U=4, beta=1, L=10: two full free-running sweeps of 3 chains, one kernel
+    launch, against the oracle: identical accept/reject sequence, G within 1e-10, accumulators equal."""
+    ham = so.ideal_square_kinetic(10, 1.0, 2.0)
+    n, lt = 100, 10
+    dtau, lamb, exp_k = so.set_beta_constants(ham, 4.0, 1.0, lt)
+    fields = np.stack([so.initial_field(n, lt, seed=300 + c) for c in range(3)])
+    uni = np.random.RandomState(17).rand(3, 2, lt, n)
+    with _engine(exp_k, lamb, lt, n_chains=3, trace=True, arith=arith) as eng:
+        eng.set_field(fields)
+        eng.sweep(2, uni, measure=True)
+        acc, ratio = eng.get_trace()
+        gg, ff, m = eng.get_g(), eng.get_field(), eng.get_measurements()
+    for c in range(3):
+        h = fields[c].copy()
+        tot = np.zeros((2, n, n))
+        for s in range(2):
+            gu, gd, r, a = so.update_step(h, exp_k, lamb, uni[c, s])
+            assert np.array_equal(a, acc[c, s]), (c, s)
+            tot += np.stack([gu, gd])
+        assert np.array_equal(h, ff[c])
+        assert _close(gg[c, 0], gu, 1e-9) and _close(gg[c, 1], gd, 1e-9)
+        assert _close(m["g_sum"][c], tot, 1e-9)
+        assert m["n_accepted"][c] == acc[c].sum() and m["n_meas"][c] == 2
+
+
+def test_delayed_updates_equal_undelayed_bitwise():
+    """EXACT mode: a slice run through the delayed rank-k path equals the oracle's one-flip-at-a-time
+    rank-1 updates bit for bit (same roundings per element), here with ~60% acceptance and N = 144."""
+    ham = so.ideal_square_kinetic(12, 1.0, 2.0)
+    n, lt = 144, 8
+    dtau, lamb, exp_k = so.set_beta_constants(ham, 4.0, 1.0, lt)
+    h = so.initial_field(n, lt, seed=5)
+    gu, gd = so.sweep_start_g(h, exp_k, lamb)
+    u = np.random.RandomState(3).rand(n)
+    with _engine(exp_k, lamb, lt, trace=True) as eng:
+        eng.set_field(h[None])
+        eng.set_g(np.stack([gu, gd])[None])
+        eng.slice(lt - 1, u[None])
+        acc, ratio = eng.get_trace()
+        out = eng.get_g()[0]
+    ratios, accs = so.slice_proposals(gu, gd, h, lt - 1, lamb, u)
+    assert 0.2 < accs.mean() < 0.95
+    assert np.array_equal(acc[0, 0, 0], accs) and np.array_equal(ratio[0, 0, 0], ratios)
+    assert np.array_equal(out[0], gu) and np.array_equal(out[1], gd)
