@@ -64,9 +64,9 @@ struct L2Smem {
     U = reinterpret_cast<double*>(base);
     W = U + (size_t)2 * KD * NP;
     pa = U;
-    pb = pa + 2 * L2_BK * L2_BM;
+    pb = pa + 2 * L2_BK * (L2_BM + 4);
     double* tail = W + (size_t)2 * KD * NP;
-    const size_t gemm_end = (size_t)2 * L2_BK * (L2_BM + L2_BN);
+    const size_t gemm_end = (size_t)2 * L2_BK * (L2_BM + L2_BN + 8);
     if ((size_t)4 * KD * NP < gemm_end) tail = U + gemm_end;
     d = tail;
     u = d + 4 * NP;
@@ -79,7 +79,7 @@ struct L2Smem {
 
 inline size_t l2_smem_bytes(int NP, int KD) {
   size_t vec = (size_t)4 * KD * NP;
-  const size_t gemm = (size_t)2 * L2_BK * (L2_BM + L2_BN);
+  const size_t gemm = (size_t)2 * L2_BK * (L2_BM + L2_BN + 8);
   if (vec < gemm) vec = gemm;
   return (vec + 5 * (size_t)NP + 16) * sizeof(double) + 16 * sizeof(int) + 2 * (size_t)NP + 16;
 }
@@ -95,105 +95,97 @@ struct L2Epilogue {
   bool add_identity = false;
 };
 
+// FP64 tensor-core MMA, D(8x8) += A(8x4) * B(4x8).  Fragment layout (PTX ISA, mma.m8n8k4 .f64):
+//   a : A[row = lane/4][k = lane%4]      b : B[k = lane%4][col = lane/4]
+//   c0, c1 : C[row = lane/4][col = 2*(lane%4) + {0,1}]
+// On sm_100a DMMA issues to the same FP64 pipe as DFMA (same peak); what it buys is operand traffic: a lane
+// loads 1 double per 8 multiply-adds instead of 1 per <= 2.7 for a 4x8 register-tiled DFMA loop, which is the
+// difference between a shared-memory-bound and an FP64-pipe-bound GEMM (profiles/r01_cfg4_summary.md).
+__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+
+constexpr int L2_LDA = L2_BM + 4;    // panel row strides = 4 mod 16 doubles: the 4 k-rows a fragment load touches
+constexpr int L2_LDB = L2_BN + 4;    // fall into disjoint bank groups (conflict-free LDS.64)
+
 __device__ __forceinline__ void l2_issue_panel(const double* __restrict__ At, const double* __restrict__ B, int NP, int i0, int j0,
                                                int k0, double* pa, double* pb, int tid) {
   // A panel: BK rows of BM doubles (512 B each); B panel: BK rows of BN doubles (1 KiB each); 16-byte chunks
   for (int c = tid; c < L2_BK * (L2_BM / 2); c += L2_THREADS) {
     const int r = c / (L2_BM / 2), x = c % (L2_BM / 2);
-    __pipeline_memcpy_async(pa + r * L2_BM + 2 * x, At + (size_t)(k0 + r) * NP + i0 + 2 * x, 16);
+    __pipeline_memcpy_async(pa + r * L2_LDA + 2 * x, At + (size_t)(k0 + r) * NP + i0 + 2 * x, 16);
   }
   for (int c = tid; c < L2_BK * (L2_BN / 2); c += L2_THREADS) {
     const int r = c / (L2_BN / 2), x = c % (L2_BN / 2);
-    __pipeline_memcpy_async(pb + r * L2_BN + 2 * x, B + (size_t)(k0 + r) * NP + j0 + 2 * x, 16);
+    __pipeline_memcpy_async(pb + r * L2_LDB + 2 * x, B + (size_t)(k0 + r) * NP + j0 + 2 * x, 16);
   }
   __pipeline_commit();
 }
 
 __device__ void l2_gemm(const double* __restrict__ At, const double* __restrict__ B, double* __restrict__ Cout, int NP, int spin,
                         const L2Epilogue& ep, const SweepParams& p, L2Smem& sm) {
-  const int tid = threadIdx.x;
-  const int ty = tid % L2_GY, tx = tid / L2_GY;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp >> 2, wn = warp & 3;            // 2 x 4 warps, 32 x 32 warp tiles
+  const int lr = lane >> 2, lk = lane & 3;
   const int nk = NP / L2_BK;
   for (int i0 = 0; i0 < NP; i0 += L2_BM) {
     for (int j0 = 0; j0 < NP; j0 += L2_BN) {
-      double acc[4][8];
+      double acc[4][4][2];
 #pragma unroll
       for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int b = 0; b < 8; ++b) acc[a][b] = 0.0;
+        for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
       __syncthreads();                       // previous users of the panels are done
       l2_issue_panel(At, B, NP, i0, j0, 0, sm.pa, sm.pb, tid);
       for (int kp = 0; kp < nk; ++kp) {
         const int st = kp & 1;
         if (kp + 1 < nk) {
-          l2_issue_panel(At, B, NP, i0, j0, (kp + 1) * L2_BK, sm.pa + (st ^ 1) * L2_BK * L2_BM, sm.pb + (st ^ 1) * L2_BK * L2_BN, tid);
+          l2_issue_panel(At, B, NP, i0, j0, (kp + 1) * L2_BK, sm.pa + (st ^ 1) * L2_BK * L2_LDA, sm.pb + (st ^ 1) * L2_BK * L2_LDB, tid);
           __pipeline_wait_prior(1);
         } else {
           __pipeline_wait_prior(0);
         }
         __syncthreads();
-        const double* ap = sm.pa + st * L2_BK * L2_BM + 2 * ty;
-        const double* bp = sm.pb + st * L2_BK * L2_BN + 2 * tx;
-#pragma unroll 4
-        for (int k = 0; k < L2_BK; ++k) {
-          double a[4], b[8];
+        const double* ap = sm.pa + st * L2_BK * L2_LDA + lk * L2_LDA + 32 * wm + lr;
+        const double* bp = sm.pb + st * L2_BK * L2_LDB + lk * L2_LDB + 32 * wn + lr;
 #pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            const double2 v = *reinterpret_cast<const double2*>(ap + k * L2_BM + 2 * L2_GY * q);
-            a[2 * q] = v.x; a[2 * q + 1] = v.y;
-          }
+        for (int k4 = 0; k4 < L2_BK / 4; ++k4) {
+          double a[4], b[4];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const double2 w = *reinterpret_cast<const double2*>(bp + k * L2_BN + 2 * L2_GX * q);
-            b[2 * q] = w.x; b[2 * q + 1] = w.y;
-          }
+          for (int m = 0; m < 4; ++m) a[m] = ap[4 * k4 * L2_LDA + 8 * m];
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
+          for (int n = 0; n < 4; ++n) b[n] = bp[4 * k4 * L2_LDB + 8 * n];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+          for (int m = 0; m < 4; ++m)
+#pragma unroll
+            for (int n = 0; n < 4; ++n) dmma884(acc[m][n], a[m], b[n]);
         }
         __syncthreads();                     // stage st may be refilled two iterations from now
       }
-      // epilogue
-      double rs[4], cs[8];
+      // epilogue: element (row, col) = acc[m][n][s]
 #pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        const int row = i0 + 2 * ty + 2 * L2_GY * (a >> 1) + (a & 1);
-        rs[a] = ep.hrow ? (ep.row_inv ? hs_vinv(ep.hrow[row], spin, p) : hs_v(ep.hrow[row], spin, p)) : 1.0;
-      }
+      for (int m = 0; m < 4; ++m) {
+        const int row = i0 + 32 * wm + 8 * m + lr;
+        const double rs = ep.hrow ? (ep.row_inv ? hs_vinv(ep.hrow[row], spin, p) : hs_v(ep.hrow[row], spin, p)) : 1.0;
 #pragma unroll
-      for (int b = 0; b < 8; ++b) {
-        const int col = j0 + 2 * tx + 2 * L2_GX * (b >> 1) + (b & 1);
-        cs[b] = ep.hcol ? (ep.col_inv ? hs_vinv(ep.hcol[col], spin, p) : hs_v(ep.hcol[col], spin, p)) : 1.0;
-      }
+        for (int n = 0; n < 4; ++n) {
 #pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        const int row = i0 + 2 * ty + 2 * L2_GY * (a >> 1) + (a & 1);
-#pragma unroll
-        for (int b = 0; b < 8; ++b) {
-          const int col = j0 + 2 * tx + 2 * L2_GX * (b >> 1) + (b & 1);
-          double v = acc[a][b];
-          if (ep.hrow) v *= rs[a];
-          if (ep.hcol) v *= cs[b];
-          if (ep.add_identity && row == col) v += 1.0;
-          acc[a][b] = v;
-        }
-      }
-      if (!ep.transposed_out) {
-#pragma unroll
-        for (int a = 0; a < 4; ++a) {
-          const int row = i0 + 2 * ty + 2 * L2_GY * (a >> 1) + (a & 1);
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            *reinterpret_cast<double2*>(Cout + (size_t)row * NP + j0 + 2 * tx + 2 * L2_GX * q) = make_double2(acc[a][2 * q], acc[a][2 * q + 1]);
-        }
-      } else {
-#pragma unroll
-        for (int b = 0; b < 8; ++b) {
-          const int col = j0 + 2 * tx + 2 * L2_GX * (b >> 1) + (b & 1);
-#pragma unroll
-          for (int q = 0; q < 2; ++q)
-            *reinterpret_cast<double2*>(Cout + (size_t)col * NP + i0 + 2 * ty + 2 * L2_GY * q) = make_double2(acc[2 * q][b], acc[2 * q + 1][b]);
+          for (int s2 = 0; s2 < 2; ++s2) {
+            const int col = j0 + 32 * wn + 8 * n + 2 * lk + s2;
+            double v = acc[m][n][s2];
+            if (ep.hrow) v *= rs;
+            if (ep.hcol) v *= (ep.col_inv ? hs_vinv(ep.hcol[col], spin, p) : hs_v(ep.hcol[col], spin, p));
+            if (ep.add_identity && row == col) v += 1.0;
+            acc[m][n][s2] = v;
+          }
+          const int col0 = j0 + 32 * wn + 8 * n + 2 * lk;
+          if (!ep.transposed_out) {
+            *reinterpret_cast<double2*>(Cout + (size_t)row * NP + col0) = make_double2(acc[m][n][0], acc[m][n][1]);
+          } else {
+            Cout[(size_t)col0 * NP + row] = acc[m][n][0];
+            Cout[(size_t)(col0 + 1) * NP + row] = acc[m][n][1];
+          }
         }
       }
     }

@@ -97,8 +97,9 @@ def test_free_running_sweep_10x10(arith):
             assert np.array_equal(a, acc[c, s]), (c, s)
             tot += np.stack([gu, gd])
         assert np.array_equal(h, ff[c])
-        assert _close(gg[c, 0], gu, 1e-9) and _close(gg[c, 1], gd, 1e-9)
-        assert _close(m["g_sum"][c], tot, 1e-9)
+        tol = 1e-9 if arith == "exact" else 1e-6     # contracted FMAs perturb at 1e-16; the recurrence amplifies
+        assert _close(gg[c, 0], gu, tol) and _close(gg[c, 1], gd, tol)
+        assert _close(m["g_sum"][c], tot, tol)
         assert m["n_accepted"][c] == acc[c].sum() and m["n_meas"][c] == 2
 
 
