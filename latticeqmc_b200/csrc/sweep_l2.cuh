@@ -40,6 +40,7 @@ struct L2Workspace {
 constexpr int L2_THREADS = 256;
 constexpr int L2_BM = 64, L2_BN = 128, L2_BK = 16;     // block tile and k-panel depth
 constexpr int L2_GY = 16, L2_GX = 16;                  // thread grid inside a block tile: 4 x 8 per thread
+constexpr int L2_STAGES = 3;                           // operand-panel ring depth
 constexpr int L2_MAXQ = 4;                             // indices per thread in the vector phases (NP <= 1024)
 
 inline int l2_padded_size(int n_sites) {
@@ -58,20 +59,23 @@ struct L2Smem {
   int8_t* h;      // [NP]
   int8_t* hn;     // [NP]
   // GEMM phase (aliases U / W)
-  double* pa;     // [2 stage][BK][BM]
-  double* pb;     // [2 stage][BK][BN]
+  double* pa;     // [L2_STAGES][BK][BM + 4]
+  double* pb;     // [L2_STAGES][BK][BN + 4]
+  uint64_t* full; // [L2_STAGES] mbarriers: "panel landed"
+  uint32_t pipe_iter = 0;   // panels consumed so far by this CTA (uniform across threads): stage and phase parity
   __device__ L2Smem(unsigned char* base, int NP, int KD) {
     U = reinterpret_cast<double*>(base);
     W = U + (size_t)2 * KD * NP;
     pa = U;
-    pb = pa + 2 * L2_BK * (L2_BM + 4);
+    pb = pa + L2_STAGES * L2_BK * (L2_BM + 4);
     double* tail = W + (size_t)2 * KD * NP;
-    const size_t gemm_end = (size_t)2 * L2_BK * (L2_BM + L2_BN + 8);
+    const size_t gemm_end = (size_t)L2_STAGES * L2_BK * (L2_BM + L2_BN + 8);
     if ((size_t)4 * KD * NP < gemm_end) tail = U + gemm_end;
     d = tail;
     u = d + 4 * NP;
     red_v = u + NP;
-    red_i = reinterpret_cast<int*>(red_v + 16);
+    full = reinterpret_cast<uint64_t*>(red_v + 16);
+    red_i = reinterpret_cast<int*>(full + 4);
     h = reinterpret_cast<int8_t*>(red_i + 16);
     hn = h + NP;
   }
@@ -79,9 +83,9 @@ struct L2Smem {
 
 inline size_t l2_smem_bytes(int NP, int KD) {
   size_t vec = (size_t)4 * KD * NP;
-  const size_t gemm = (size_t)2 * L2_BK * (L2_BM + L2_BN + 8);
+  const size_t gemm = (size_t)L2_STAGES * L2_BK * (L2_BM + L2_BN + 8);
   if (vec < gemm) vec = gemm;
-  return (vec + 5 * (size_t)NP + 16) * sizeof(double) + 16 * sizeof(int) + 2 * (size_t)NP + 16;
+  return (vec + 5 * (size_t)NP + 16 + 4) * sizeof(double) + 16 * sizeof(int) + 2 * (size_t)NP + 16;
 }
 
 // ---- tiled GEMM:  C = A * B  with A given k-major (At[k*NP + i] = A[i][k]) and B row-major ------------------
@@ -109,18 +113,46 @@ __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
 constexpr int L2_LDA = L2_BM + 4;    // panel row strides = 4 mod 16 doubles: the 4 k-rows a fragment load touches
 constexpr int L2_LDB = L2_BN + 4;    // fall into disjoint bank groups (conflict-free LDS.64)
 
+// ---- TMA bulk-copy plumbing (cp.async.bulk + mbarrier complete_tx; SASS: UBLKCP / SYNCS) --------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// One operand panel = BK k-rows of the k-major left operand (BM doubles each) + BK rows of the right operand
+// (BN doubles each).  Warp 0 issues it: lane r copies A row r and B row r as two bulk transfers that
+// complete on the stage's mbarrier.
 __device__ __forceinline__ void l2_issue_panel(const double* __restrict__ At, const double* __restrict__ B, int NP, int i0, int j0,
-                                               int k0, double* pa, double* pb, int tid) {
-  // A panel: BK rows of BM doubles (512 B each); B panel: BK rows of BN doubles (1 KiB each); 16-byte chunks
-  for (int c = tid; c < L2_BK * (L2_BM / 2); c += L2_THREADS) {
-    const int r = c / (L2_BM / 2), x = c % (L2_BM / 2);
-    __pipeline_memcpy_async(pa + r * L2_LDA + 2 * x, At + (size_t)(k0 + r) * NP + i0 + 2 * x, 16);
+                                               int k0, L2Smem& sm, int stage, int lane) {
+  uint64_t* bar = sm.full + stage;
+  if (lane == 0) mbar_expect_tx(bar, L2_BK * (L2_BM + L2_BN) * (uint32_t)sizeof(double));
+  __syncwarp();
+  if (lane < L2_BK) {
+    bulk_g2s(sm.pa + (stage * L2_BK + lane) * L2_LDA, At + (size_t)(k0 + lane) * NP + i0, L2_BM * sizeof(double), bar);
+    bulk_g2s(sm.pb + (stage * L2_BK + lane) * L2_LDB, B + (size_t)(k0 + lane) * NP + j0, L2_BN * sizeof(double), bar);
   }
-  for (int c = tid; c < L2_BK * (L2_BN / 2); c += L2_THREADS) {
-    const int r = c / (L2_BN / 2), x = c % (L2_BN / 2);
-    __pipeline_memcpy_async(pb + r * L2_LDB + 2 * x, B + (size_t)(k0 + r) * NP + j0 + 2 * x, 16);
-  }
-  __pipeline_commit();
 }
 
 __device__ void l2_gemm(const double* __restrict__ At, const double* __restrict__ B, double* __restrict__ Cout, int NP, int spin,
@@ -129,6 +161,10 @@ __device__ void l2_gemm(const double* __restrict__ At, const double* __restrict_
   const int wm = warp >> 2, wn = warp & 3;            // 2 x 4 warps, 32 x 32 warp tiles
   const int lr = lane >> 2, lk = lane & 3;
   const int nk = NP / L2_BK;
+  // operands may have been written by this CTA's ordinary stores (previous epilogue, flush) and the panel
+  // region by ordinary shared stores (U / W): order them before the async-proxy copies
+  fence_proxy_async();
+  __syncthreads();
   for (int i0 = 0; i0 < NP; i0 += L2_BM) {
     for (int j0 = 0; j0 < NP; j0 += L2_BN) {
       double acc[4][4][2];
@@ -136,17 +172,16 @@ __device__ void l2_gemm(const double* __restrict__ At, const double* __restrict_
       for (int a = 0; a < 4; ++a)
 #pragma unroll
         for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
-      __syncthreads();                       // previous users of the panels are done
-      l2_issue_panel(At, B, NP, i0, j0, 0, sm.pa, sm.pb, tid);
+      const uint32_t it0 = sm.pipe_iter;
+      if (warp == 0) {
+#pragma unroll
+        for (int s0 = 0; s0 < L2_STAGES; ++s0)
+          if (s0 < nk) l2_issue_panel(At, B, NP, i0, j0, s0 * L2_BK, sm, (it0 + s0) % L2_STAGES, lane);
+      }
       for (int kp = 0; kp < nk; ++kp) {
-        const int st = kp & 1;
-        if (kp + 1 < nk) {
-          l2_issue_panel(At, B, NP, i0, j0, (kp + 1) * L2_BK, sm.pa + (st ^ 1) * L2_BK * L2_LDA, sm.pb + (st ^ 1) * L2_BK * L2_LDB, tid);
-          __pipeline_wait_prior(1);
-        } else {
-          __pipeline_wait_prior(0);
-        }
-        __syncthreads();
+        const uint32_t it = it0 + kp;
+        const int st = it % L2_STAGES;
+        mbar_wait(sm.full + st, (it / L2_STAGES) & 1u);
         const double* ap = sm.pa + st * L2_BK * L2_LDA + lk * L2_LDA + 32 * wm + lr;
         const double* bp = sm.pb + st * L2_BK * L2_LDB + lk * L2_LDB + 32 * wn + lr;
 #pragma unroll
@@ -161,8 +196,10 @@ __device__ void l2_gemm(const double* __restrict__ At, const double* __restrict_
 #pragma unroll
             for (int n = 0; n < 4; ++n) dmma884(acc[m][n], a[m], b[n]);
         }
-        __syncthreads();                     // stage st may be refilled two iterations from now
+        __syncthreads();                     // every warp is done with stage st: refill it
+        if (warp == 0 && kp + L2_STAGES < nk) l2_issue_panel(At, B, NP, i0, j0, (kp + L2_STAGES) * L2_BK, sm, st, lane);
       }
+      sm.pipe_iter = it0 + nk;
       // epilogue: element (row, col) = acc[m][n][s]
 #pragma unroll
       for (int m = 0; m < 4; ++m) {
@@ -361,23 +398,37 @@ __device__ void l2_propose_slice(double* __restrict__ Gc, int NP, int KD, L2Smem
   if (nd > 0) l2_flush<EXACT>(Gc, NP, nd, sm, KD);
 }
 
-// ---- Gauss-Jordan inverse in global memory (both spins, in place), partial pivoting ----------------------------
-// np.linalg.inv of the sweep-start matrix (lqmc.py:306-307).  One rank-1 pass over the matrix per pivot; rows are
-// swapped physically, columns are un-permuted at the end.  rowk / fcol live in the (idle) U / W buffers.
-__device__ void l2_gj_inverse(double* __restrict__ Gc, int NP, L2Smem& sm, int* piv_global) {
+// ---- Gauss-Jordan inverse in memory (both spins in lockstep, in place), partial pivoting, delayed updates ----------
+// np.linalg.inv of the sweep-start matrix (lqmc.py:306-307).  A Gauss-Jordan step is a rank-1 update of the whole
+// matrix, so it is delayed exactly like the flips: the pivot column and pivot row of the *current* matrix are rebuilt
+// from M0 and the pending (U, W) pairs, the step is appended, and M0 <- M0 - U W^T is applied once per KD pivots
+// (KD x less memory traffic than one full pass per pivot).  The pivot row and pivot column are written to M0 in
+// final form and detached from the pending updates (their U / W entries are zeroed), so they carry no
+// cancellation error.  Same pivot rule as LAPACK's getrf (first entry of largest magnitude); rows are swapped
+// physically, columns are un-permuted at the end.
+__device__ void l2_gj_inverse(double* __restrict__ Gc, int NP, int KD, L2Smem& sm, int* piv_global) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int ty = tid % L2_GY, tx = tid / L2_GY;
-  for (int spin = 0; spin < 2; ++spin) {
-    double* M = Gc + (size_t)spin * NP * NP;
-    double* rowk = sm.U;          // [NP]
-    double* fcol = sm.U + NP;     // [NP]
-    int* piv = piv_global + spin * NP;
-    for (int k = 0; k < NP; ++k) {
-      // pivot search over rows >= k of column k
+  constexpr int HALF = L2_THREADS / 2, WPS = HALF / 32;     // threads / warps per spin in the pivot search
+  double* colk = sm.d;                                       // [2][NP] (the diagonal cache is idle here)
+  int nd = 0;
+  for (int k = 0; k < NP; ++k) {
+    // 1. column k of the current matrices
+    for (int x = tid; x < 2 * NP; x += L2_THREADS) {
+      const int spin = x / NP, r = x % NP;
+      const double* U = sm.U + (size_t)spin * KD * NP;
+      const double* W = sm.W + (size_t)spin * KD * NP;
+      double v = Gc[(size_t)spin * NP * NP + (size_t)r * NP + k];
+      for (int m = 0; m < nd; ++m) v = fma(-U[(size_t)m * NP + r], W[(size_t)m * NP + k], v);
+      colk[x] = v;
+    }
+    __syncthreads();
+    // 2. pivot search, one half of the CTA per spin
+    {
+      const int spin = tid / HALF, t = tid % HALF;
       double pv = 0.0, av = -1.0;
       int idx = NP;
-      for (int r = k + tid; r < NP; r += L2_THREADS) {
-        const double v = M[(size_t)r * NP + k];
+      for (int r = k + t; r < NP; r += HALF) {
+        const double v = colk[spin * NP + r];
         const double a = fabs(v);
         if (a > av) { av = a; pv = v; idx = r; }
       }
@@ -389,72 +440,80 @@ __device__ void l2_gj_inverse(double* __restrict__ Gc, int NP, L2Smem& sm, int* 
         if (oa > av || (oa == av && oi < idx)) { av = oa; pv = op; idx = oi; }
       }
       if (lane == 0) { sm.red_v[warp] = pv; sm.red_i[warp] = idx; }
-      const double akk = M[(size_t)k * NP + k];
-      __syncthreads();
-      pv = sm.red_v[0]; idx = sm.red_i[0];
-#pragma unroll
-      for (int w = 1; w < L2_THREADS / 32; ++w) {
-        const double ov = sm.red_v[w];
-        const int oi = sm.red_i[w];
-        if (oi < NP && (idx >= NP || fabs(ov) > fabs(pv) || (fabs(ov) == fabs(pv) && oi < idx))) { pv = ov; idx = oi; }
-      }
-      if (idx >= NP) idx = k;
-      if (tid == 0) piv[k] = idx;
-      // multipliers (column k before it is rewritten) and the swapped, scaled pivot row
-      for (int r = tid; r < NP; r += L2_THREADS) {
-        double f = (r == idx && idx != k) ? akk : M[(size_t)r * NP + k];
-        if (r == k) f = 0.0;
-        fcol[r] = f;
-      }
-      __syncthreads();
-      for (int c = tid; c < NP; c += L2_THREADS) {
-        const double ak = M[(size_t)k * NP + c];
-        const double ap = M[(size_t)idx * NP + c];
-        const double x = ((c == k) ? 1.0 : ap) / pv;
-        rowk[c] = x;
-        M[(size_t)k * NP + c] = x;
-        if (idx != k) M[(size_t)idx * NP + c] = ak;
-      }
-      __syncthreads();
-      // M[r][c] <- (c == k ? 0 : M[r][c]) - f[r] * rowk[c]   for r != k
-      for (int i0 = 0; i0 < NP; i0 += L2_BM) {
-        for (int j0 = 0; j0 < NP; j0 += L2_BN) {
-#pragma unroll
-          for (int a = 0; a < 4; ++a) {
-            const int row = i0 + 2 * ty + 2 * L2_GY * (a >> 1) + (a & 1);
-            if (row == k) continue;
-            const double f = fcol[row];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int col = j0 + 2 * tx + 2 * L2_GX * q;
-              double2* ptr = reinterpret_cast<double2*>(M + (size_t)row * NP + col);
-              double2 v = *ptr;
-              const double2 rk = *reinterpret_cast<const double2*>(rowk + col);
-              if (col == k) v.x = 0.0;
-              if (col + 1 == k) v.y = 0.0;
-              v.x = fma(-f, rk.x, v.x);
-              v.y = fma(-f, rk.y, v.y);
-              *ptr = v;
-            }
-          }
-        }
-      }
-      __syncthreads();
-    }
-    // undo the row interchanges on the columns, last pivot first
-    for (int r = tid; r < NP; r += L2_THREADS) {
-      double* rp = M + (size_t)r * NP;
-      for (int k = NP - 1; k >= 0; --k) {
-        const int pk = piv[k];
-        if (pk != k) { const double tmp = rp[k]; rp[k] = rp[pk]; rp[pk] = tmp; }
-      }
     }
     __syncthreads();
+    int pidx[2];
+    double ppv[2];
+#pragma unroll
+    for (int spin = 0; spin < 2; ++spin) {
+      double pv = sm.red_v[spin * WPS];
+      int idx = sm.red_i[spin * WPS];
+#pragma unroll
+      for (int w = 1; w < WPS; ++w) {
+        const double ov = sm.red_v[spin * WPS + w];
+        const int oi = sm.red_i[spin * WPS + w];
+        if (oi < NP && (idx >= NP || fabs(ov) > fabs(pv) || (fabs(ov) == fabs(pv) && oi < idx))) { pv = ov; idx = oi; }
+      }
+      if (idx >= NP) { idx = k; pv = colk[spin * NP + k]; }
+      pidx[spin] = idx; ppv[spin] = pv;
+    }
+    if (tid < 2) piv_global[tid * NP + k] = pidx[tid];
+    // 3. current pivot row (row p before the swap), scaled with the 1-injection; physical swap in M0
+    for (int x = tid; x < 2 * NP; x += L2_THREADS) {
+      const int spin = x / NP, c = x % NP;
+      const int pi = pidx[spin];
+      const double* U = sm.U + (size_t)spin * KD * NP;
+      const double* W = sm.W + (size_t)spin * KD * NP;
+      double* M = Gc + (size_t)spin * NP * NP;
+      const double oldk = M[(size_t)k * NP + c];
+      double v = (pi == k) ? oldk : M[(size_t)pi * NP + c];
+      for (int m = 0; m < nd; ++m) v = fma(-U[(size_t)m * NP + pi], W[(size_t)m * NP + c], v);
+      const double rk = ((c == k) ? 1.0 : v) / ppv[spin];
+      M[(size_t)k * NP + c] = rk;                                   // row k in final form
+      if (pi != k) M[(size_t)pi * NP + c] = (c == k) ? 0.0 : oldk;      // old row k moves to row p (its column-k entry is eliminated)
+      sm.W[((size_t)spin * KD + nd) * NP + c] = rk;
+    }
+    __syncthreads();
+    // 4. multipliers, detach row k / column k from the pending updates, eliminate column k in M0
+    for (int x = tid; x < 2 * NP; x += L2_THREADS) {
+      const int spin = x / NP, r = x % NP;
+      const int pi = pidx[spin];
+      double f;
+      if (r == k) f = 0.0;
+      else if (r == pi) f = colk[spin * NP + k];
+      else f = colk[x];
+      sm.U[((size_t)spin * KD + nd) * NP + r] = f;
+      if (r != k && r != pi) Gc[(size_t)spin * NP * NP + (size_t)r * NP + k] = 0.0;
+    }
+    for (int x = tid; x < 2 * nd; x += L2_THREADS) {
+      const int spin = x / nd, m = x % nd;
+      const int pi = pidx[spin];
+      double* U = sm.U + ((size_t)spin * KD + m) * NP;
+      double* W = sm.W + ((size_t)spin * KD + m) * NP;
+      if (pi != k) U[pi] = U[k];
+      U[k] = 0.0;
+      W[k] = 0.0;
+    }
+    ++nd;
+    __syncthreads();
+    if (nd == KD) { l2_flush<false>(Gc, NP, nd, sm, KD); nd = 0; }
   }
+  if (nd > 0) l2_flush<false>(Gc, NP, nd, sm, KD);
+  // undo the row interchanges on the columns, last pivot first
+  for (int x = tid; x < 2 * NP; x += L2_THREADS) {
+    const int spin = x / NP, r = x % NP;
+    double* rp = Gc + (size_t)spin * NP * NP + (size_t)r * NP;
+    const int* piv = piv_global + spin * NP;
+    for (int k = NP - 1; k >= 0; --k) {
+      const int pk = piv[k];
+      if (pk != k) { const double tmp = rp[k]; rp[k] = rp[pk]; rp[pk] = tmp; }
+    }
+  }
+  __syncthreads();
 }
 
 // ---- sweep-start G = inv(I + prod B) in memory ----------------------------------------------------------------
-__device__ void l2_recompute(double* __restrict__ Gc, double* __restrict__ Tc, int NP, const int8_t* field, int l0,
+__device__ void l2_recompute(double* __restrict__ Gc, double* __restrict__ Tc, int NP, int KD, const int8_t* field, int l0,
                              const SweepParams& p, L2Smem& sm, int* piv_global) {
   const int L = p.n_slices;
   const int tid = threadIdx.x;
@@ -489,7 +548,7 @@ __device__ void l2_recompute(double* __restrict__ Gc, double* __restrict__ Tc, i
       double* t = cur; cur = oth; oth = t;
     }
   }
-  l2_gj_inverse(Gc, NP, sm, piv_global);
+  l2_gj_inverse(Gc, NP, KD, sm, piv_global);
 }
 
 // ---- wrap from slice l to l-1 ------------------------------------------------------------------------------
@@ -529,9 +588,14 @@ __global__ void __launch_bounds__(L2_THREADS, 2) sweep_l2_kernel(const L2Params 
   int* piv = lp.piv + (size_t)chain * 2 * NP;
   const int n_steps = p.step_hi - p.step_lo;
   int n_accepted = 0;
+  if (tid == 0) {
+    for (int s0 = 0; s0 < L2_STAGES; ++s0) mbar_init(sm.full + s0, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
 
   for (int sweep = 0; sweep < p.n_sweeps; ++sweep) {
-    if (p.do_recompute) l2_recompute(Gc, Tc, NP, field, p.recompute_l0, p, sm, piv);
+    if (p.do_recompute) l2_recompute(Gc, Tc, NP, KD, field, p.recompute_l0, p, sm, piv);
     for (int step = p.step_lo; step < p.step_hi; ++step) {
       const int l = L - 1 - step;
       const long long base = (((long long)chain * p.n_sweeps + sweep) * n_steps + (step - p.step_lo)) * N;
