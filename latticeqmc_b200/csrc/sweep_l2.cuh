@@ -40,6 +40,9 @@ struct L2Workspace {
 constexpr int L2_THREADS = 256;
 constexpr int L2_BM = 64, L2_BN = 128, L2_BK = 16;     // block tile and k-panel depth
 constexpr int L2_GY = 16, L2_GX = 16;                  // thread grid inside a block tile: 4 x 8 per thread
+#ifndef LQMC_L2_STAGING_TMA
+#define LQMC_L2_STAGING_TMA 0                          // 1: cp.async.bulk rows + mbarrier ring; 0: LDGSTS (cp.async) ring
+#endif
 constexpr int L2_STAGES = 3;                           // operand-panel ring depth
 constexpr int L2_MAXQ = 4;                             // indices per thread in the vector phases (NP <= 1024)
 
@@ -139,19 +142,44 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+__device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 // One operand panel = BK k-rows of the k-major left operand (BM doubles each) + BK rows of the right operand
-// (BN doubles each).  Warp 0 issues it: lane r copies A row r and B row r as two bulk transfers that
-// complete on the stage's mbarrier.
-__device__ __forceinline__ void l2_issue_panel(const double* __restrict__ At, const double* __restrict__ B, int NP, int i0, int j0,
-                                               int k0, L2Smem& sm, int stage, int lane) {
-  uint64_t* bar = sm.full + stage;
-  if (lane == 0) mbar_expect_tx(bar, L2_BK * (L2_BM + L2_BN) * (uint32_t)sizeof(double));
+// (BN doubles each).  Warp 0 issues it: lane r < BK copies A row r and B row r as two bulk transfers that complete
+// on the stage's mbarrier.  All addresses are per-lane registers set up once per block tile.
+struct L2PanelIssue {
+  const double* srcA;   // At + lane*NP + i0     (+ k0*NP per panel)
+  const double* srcB;   // B  + lane*NP + j0
+  uint32_t dstA, dstB;  // shared addresses of row `lane` in stage 0
+  uint32_t bar;         // shared address of full[0]
+};
+__device__ __forceinline__ void l2_issue_panel(const L2PanelIssue& pi, int NP, int k0, int stage, int lane) {
+  const uint32_t bar = pi.bar + 8u * stage;
+  if (lane == 0)
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(L2_BK * (L2_BM + L2_BN) * sizeof(double))) : "memory");
   __syncwarp();
   if (lane < L2_BK) {
-    bulk_g2s(sm.pa + (stage * L2_BK + lane) * L2_LDA, At + (size_t)(k0 + lane) * NP + i0, L2_BM * sizeof(double), bar);
-    bulk_g2s(sm.pb + (stage * L2_BK + lane) * L2_LDB, B + (size_t)(k0 + lane) * NP + j0, L2_BN * sizeof(double), bar);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     pi.dstA + (uint32_t)(stage * L2_BK * L2_LDA * sizeof(double))),
+                 "l"(pi.srcA + (size_t)k0 * NP), "r"((uint32_t)(L2_BM * sizeof(double))), "r"(bar)
+                 : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     pi.dstB + (uint32_t)(stage * L2_BK * L2_LDB * sizeof(double))),
+                 "l"(pi.srcB + (size_t)k0 * NP), "r"((uint32_t)(L2_BN * sizeof(double))), "r"(bar)
+                 : "memory");
   }
 }
 
@@ -161,6 +189,9 @@ __device__ void l2_gemm(const double* __restrict__ At, const double* __restrict_
   const int wm = warp >> 2, wn = warp & 3;            // 2 x 4 warps, 32 x 32 warp tiles
   const int lr = lane >> 2, lk = lane & 3;
   const int nk = NP / L2_BK;
+  const double* pa = sm.pa;
+  const double* pb = sm.pb;
+  const uint32_t pa_u32 = smem_u32(sm.pa), pb_u32 = smem_u32(sm.pb), bar_u32 = smem_u32(sm.full);
   // operands may have been written by this CTA's ordinary stores (previous epilogue, flush) and the panel
   // region by ordinary shared stores (U / W): order them before the async-proxy copies
   fence_proxy_async();
@@ -172,18 +203,25 @@ __device__ void l2_gemm(const double* __restrict__ At, const double* __restrict_
       for (int a = 0; a < 4; ++a)
 #pragma unroll
         for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+#if LQMC_L2_STAGING_TMA
       const uint32_t it0 = sm.pipe_iter;
+      L2PanelIssue pi;
+      pi.srcA = At + (size_t)lane * NP + i0;
+      pi.srcB = B + (size_t)lane * NP + j0;
+      pi.dstA = pa_u32 + (uint32_t)(lane * L2_LDA * sizeof(double));
+      pi.dstB = pb_u32 + (uint32_t)(lane * L2_LDB * sizeof(double));
+      pi.bar = bar_u32;
       if (warp == 0) {
 #pragma unroll
         for (int s0 = 0; s0 < L2_STAGES; ++s0)
-          if (s0 < nk) l2_issue_panel(At, B, NP, i0, j0, s0 * L2_BK, sm, (it0 + s0) % L2_STAGES, lane);
+          if (s0 < nk) l2_issue_panel(pi, NP, s0 * L2_BK, (it0 + s0) % L2_STAGES, lane);
       }
       for (int kp = 0; kp < nk; ++kp) {
         const uint32_t it = it0 + kp;
         const int st = it % L2_STAGES;
-        mbar_wait(sm.full + st, (it / L2_STAGES) & 1u);
-        const double* ap = sm.pa + st * L2_BK * L2_LDA + lk * L2_LDA + 32 * wm + lr;
-        const double* bp = sm.pb + st * L2_BK * L2_LDB + lk * L2_LDB + 32 * wn + lr;
+        mbar_wait_u32(bar_u32 + 8u * st, (it / L2_STAGES) & 1u);
+        const double* ap = pa + st * L2_BK * L2_LDA + lk * L2_LDA + 32 * wm + lr;
+        const double* bp = pb + st * L2_BK * L2_LDB + lk * L2_LDB + 32 * wn + lr;
 #pragma unroll
         for (int k4 = 0; k4 < L2_BK / 4; ++k4) {
           double a[4], b[4];
@@ -197,9 +235,53 @@ __device__ void l2_gemm(const double* __restrict__ At, const double* __restrict_
             for (int n = 0; n < 4; ++n) dmma884(acc[m][n], a[m], b[n]);
         }
         __syncthreads();                     // every warp is done with stage st: refill it
-        if (warp == 0 && kp + L2_STAGES < nk) l2_issue_panel(At, B, NP, i0, j0, (kp + L2_STAGES) * L2_BK, sm, st, lane);
+        if (warp == 0 && kp + L2_STAGES < nk) l2_issue_panel(pi, NP, (kp + L2_STAGES) * L2_BK, st, lane);
       }
       sm.pipe_iter = it0 + nk;
+#else
+      // LDGSTS ring: every thread copies 2 (A) + 4 (B) 16-byte chunks per panel; addresses set up once per tile
+      const double* srcA = At + (size_t)(tid >> 5) * NP + i0 + 2 * (tid & 31);          // rows tid/32 (+8), chunk tid%32
+      const double* srcB = B + (size_t)(tid >> 6) * NP + j0 + 2 * (tid & 63);           // rows tid/64 (+4 q), chunk tid%64
+      double* dstA = sm.pa + (tid >> 5) * L2_LDA + 2 * (tid & 31);
+      double* dstB = sm.pb + (tid >> 6) * L2_LDB + 2 * (tid & 63);
+      auto issue = [&](int kpanel, int stage) {
+        const size_t koff = (size_t)kpanel * L2_BK * NP;
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+          __pipeline_memcpy_async(dstA + stage * L2_BK * L2_LDA + q * 8 * L2_LDA, srcA + koff + (size_t)q * 8 * NP, 16);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          __pipeline_memcpy_async(dstB + stage * L2_BK * L2_LDB + q * 4 * L2_LDB, srcB + koff + (size_t)q * 4 * NP, 16);
+      };
+#pragma unroll
+      for (int s0 = 0; s0 < L2_STAGES - 1; ++s0) {
+        if (s0 < nk) issue(s0, s0);
+        __pipeline_commit();
+      }
+      for (int kp = 0; kp < nk; ++kp) {
+        const int st = kp % L2_STAGES;
+        __pipeline_wait_prior(L2_STAGES - 2);        // this thread's copies of panel kp have landed
+        __syncthreads();                             // everyone's have; and every warp is done with panel kp-1
+        if (kp + L2_STAGES - 1 < nk) issue(kp + L2_STAGES - 1, (kp + L2_STAGES - 1) % L2_STAGES);
+        __pipeline_commit();
+        const double* ap = pa + st * L2_BK * L2_LDA + lk * L2_LDA + 32 * wm + lr;
+        const double* bp = pb + st * L2_BK * L2_LDB + lk * L2_LDB + 32 * wn + lr;
+#pragma unroll
+        for (int k4 = 0; k4 < L2_BK / 4; ++k4) {
+          double a[4], b[4];
+#pragma unroll
+          for (int m = 0; m < 4; ++m) a[m] = ap[4 * k4 * L2_LDA + 8 * m];
+#pragma unroll
+          for (int n = 0; n < 4; ++n) b[n] = bp[4 * k4 * L2_LDB + 8 * n];
+#pragma unroll
+          for (int m = 0; m < 4; ++m)
+#pragma unroll
+            for (int n = 0; n < 4; ++n) dmma884(acc[m][n], a[m], b[n]);
+        }
+      }
+      __pipeline_wait_prior(0);
+      __syncthreads();                               // panels free for the next tile
+#endif
       // epilogue: element (row, col) = acc[m][n][s]
 #pragma unroll
       for (int m = 0; m < 4; ++m) {
@@ -231,52 +313,74 @@ __device__ void l2_gemm(const double* __restrict__ At, const double* __restrict_
 }
 
 // ---- G0 <- G0 - sum_m U_m W_m^T for both spins (the delayed block update) -----------------------------------
+// A streaming pass over G (read + write 16 N^2 bytes for both spins): HBM-bound once the chains' matrices exceed
+// L2.  Block tile 32 rows x 128 columns: warp w owns rows 4w..4w+3, lane l the column pairs {2l, 2l+1} and
+// {64+2l, 64+2l+1}, so every global access of a warp is one fully coalesced 512-byte row segment, the U
+// fragment is a warp-wide broadcast and the W fragment a conflict-free 512-byte read.  The next tile's loads
+// are kept in flight while the nd updates are applied to the current one.
 template <bool EXACT>
 __device__ void l2_flush(double* __restrict__ Gc, int NP, int nd, L2Smem& sm, int KD) {
-  const int tid = threadIdx.x;
-  const int ty = tid % L2_GY, tx = tid / L2_GY;
-  for (int spin = 0; spin < 2; ++spin) {
-    double* G = Gc + (size_t)spin * NP * NP;
-    const double* U = sm.U + (size_t)spin * KD * NP;
-    const double* W = sm.W + (size_t)spin * KD * NP;
-    for (int i0 = 0; i0 < NP; i0 += L2_BM) {
-      for (int j0 = 0; j0 < NP; j0 += L2_BN) {
-        double g[4][8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n_tiles = 2 * (NP / 32) * (NP / 128);
+  double* const thread_base = Gc + (size_t)(4 * warp) * NP + 2 * lane;
+  // tile walk (spin, i0, j0) kept as running offsets: no integer division in the loop (the XU pipe is 1/4 rate)
+  struct Walk { int spin, i0, j0; };
+  auto advance = [&](Walk& w) {
+    w.j0 += 128;
+    if (w.j0 == NP) { w.j0 = 0; w.i0 += 32; if (w.i0 == NP) { w.i0 = 0; w.spin += 1; } }
+  };
+  auto tile_ptr_w = [&](const Walk& w) -> double* { return thread_base + ((size_t)w.spin * NP + w.i0) * NP + w.j0; };
+  auto load_tile4 = [&](const double* base, double (&g)[4][4]) {
 #pragma unroll
-        for (int a = 0; a < 4; ++a) {
-          const int row = i0 + 2 * ty + 2 * L2_GY * (a >> 1) + (a & 1);
+    for (int a = 0; a < 4; ++a)
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const double2 v = *reinterpret_cast<const double2*>(G + (size_t)row * NP + j0 + 2 * tx + 2 * L2_GX * q);
-            g[a][2 * q] = v.x; g[a][2 * q + 1] = v.y;
-          }
-        }
-        for (int m = 0; m < nd; ++m) {
-          double e[4], c[8];
-#pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            const double2 v = *reinterpret_cast<const double2*>(U + (size_t)m * NP + i0 + 2 * ty + 2 * L2_GY * q);
-            e[2 * q] = v.x; e[2 * q + 1] = v.y;
-          }
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const double2 w = *reinterpret_cast<const double2*>(W + (size_t)m * NP + j0 + 2 * tx + 2 * L2_GX * q);
-            c[2 * q] = w.x; c[2 * q + 1] = w.y;
-          }
-#pragma unroll
-          for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int b = 0; b < 8; ++b) g[a][b] = rank1<EXACT>(g[a][b], e[a], c[b]);
-        }
-#pragma unroll
-        for (int a = 0; a < 4; ++a) {
-          const int row = i0 + 2 * ty + 2 * L2_GY * (a >> 1) + (a & 1);
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            *reinterpret_cast<double2*>(G + (size_t)row * NP + j0 + 2 * tx + 2 * L2_GX * q) = make_double2(g[a][2 * q], g[a][2 * q + 1]);
-        }
+      for (int q = 0; q < 2; ++q) {
+        const double2 v = *reinterpret_cast<const double2*>(base + (size_t)a * NP + 64 * q);
+        g[a][2 * q] = v.x; g[a][2 * q + 1] = v.y;
       }
+  };
+  Walk wc{0, 0, 0}, wn{0, 0, 0};
+  double nxt[4][4];
+  load_tile4(tile_ptr_w(wn), nxt);
+  for (int t = 0; t < n_tiles; ++t) {
+    double g[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) g[a][b] = nxt[a][b];
+    double* base = tile_ptr_w(wc);
+    advance(wn);
+    if (t + 1 < n_tiles) load_tile4(tile_ptr_w(wn), nxt);
+    const double* U = sm.U + (size_t)wc.spin * KD * NP + wc.i0 + 4 * warp;
+    const double* W = sm.W + (size_t)wc.spin * KD * NP + wc.j0 + 2 * lane;
+    advance(wc);
+    // fragments of update m+1 are fetched while update m is applied (shared-memory latency off the critical path)
+    double e[4], c[4];
+    auto load_frag = [&](int m, double (&ef)[4], double (&cf)[4]) {
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const double2 v = *reinterpret_cast<const double2*>(U + (size_t)m * NP + 2 * q);
+        ef[2 * q] = v.x; ef[2 * q + 1] = v.y;
+        const double2 w = *reinterpret_cast<const double2*>(W + (size_t)m * NP + 64 * q);
+        cf[2 * q] = w.x; cf[2 * q + 1] = w.y;
+      }
+    };
+    load_frag(0, e, c);
+    for (int m = 0; m < nd; ++m) {
+      double en[4], cn[4];
+      load_frag((m + 1 < nd) ? m + 1 : m, en, cn);
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) g[a][b] = rank1<EXACT>(g[a][b], e[a], c[b]);
+#pragma unroll
+      for (int a = 0; a < 4; ++a) { e[a] = en[a]; c[a] = cn[a]; }
     }
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int q = 0; q < 2; ++q)
+        *reinterpret_cast<double2*>(base + (size_t)a * NP + 64 * q) = make_double2(g[a][2 * q], g[a][2 * q + 1]);
   }
   __syncthreads();
 }
@@ -288,13 +392,14 @@ __device__ void l2_propose_slice(double* __restrict__ Gc, int NP, int KD, L2Smem
   const int tid = threadIdx.x, lane = tid & 31;
   const int N = p.n_sites;
   // diagonal of both spins
-  for (int x = tid; x < 2 * NP; x += L2_THREADS) {
-    const int spin = x / NP, j = x % NP;
-    sm.d[x] = Gc[(size_t)spin * NP * NP + (size_t)j * NP + j];
-  }
+  for (int spin = 0; spin < 2; ++spin)
+    for (int j = tid; j < NP; j += L2_THREADS) sm.d[spin * NP + j] = Gc[(size_t)spin * NP * NP + (size_t)j * NP + j];
   __syncthreads();
   int nd = 0;
   int i0 = 0;
+#ifdef LQMC_PHASE_CLOCKS
+  long long tk_scan = 0, tk_build = 0, tk_flush = 0, tk0 = clock64();
+#endif
   int cur = 0;                  // diagonal buffer the scan reads; a flip writes the other one (slower warps may still be scanning)
   while (i0 < N) {
     const double* dcur = sm.d + cur * 2 * NP;
@@ -322,25 +427,34 @@ __device__ void l2_propose_slice(double* __restrict__ Gc, int NP, int KD, L2Smem
       p.tr_acc[trace_base + i] = (lane == first) ? 1 : 0;
     }
     if (!ballot) { i0 += 32; continue; }
+#ifdef LQMC_PHASE_CLOCKS
+    { const long long tk1 = clock64(); tk_scan += tk1 - tk0; tk0 = tk1; }
+#endif
     const int is = i0 + first;
     gu = __shfl_sync(0xffffffffu, gu, first);
     gd = __shfl_sync(0xffffffffu, gd, first);
     const int hs = __shfl_sync(0xffffffffu, (int)h, first);
     const double fu = (hs > 0) ? p.f_p2 : p.f_m2;
     const double fd = (hs > 0) ? p.f_m2 : p.f_p2;
-    // rebuild row `is` and column `is` of the current G: thread handles entries j = tid + 256 q of both spins
+    // rebuild row `is` and column `is` of the current G: thread handles entries j = tid + 256 q of both spins.
+    // The (strided) global loads of both spins are issued together, ahead of any use.
+    double row2[2][L2_MAXQ], col2[2][L2_MAXQ];
 #pragma unroll
     for (int spin = 0; spin < 2; ++spin) {
       const double* G = Gc + (size_t)spin * NP * NP;
-      const double* U = sm.U + (size_t)spin * KD * NP;
-      const double* W = sm.W + (size_t)spin * KD * NP;
-      const double gs = spin ? gd : gu;
-      double row[L2_MAXQ], col[L2_MAXQ];
 #pragma unroll
       for (int q = 0; q < L2_MAXQ; ++q) {
         const int j = tid + L2_THREADS * q;
-        if (j < NP) { row[q] = G[(size_t)is * NP + j]; col[q] = G[(size_t)j * NP + is]; }
+        if (j < NP) { row2[spin][q] = G[(size_t)is * NP + j]; col2[spin][q] = G[(size_t)j * NP + is]; }
       }
+    }
+#pragma unroll
+    for (int spin = 0; spin < 2; ++spin) {
+      const double* U = sm.U + (size_t)spin * KD * NP;
+      const double* W = sm.W + (size_t)spin * KD * NP;
+      const double gs = spin ? gd : gu;
+      double (&row)[L2_MAXQ] = row2[spin];
+      double (&col)[L2_MAXQ] = col2[spin];
       for (int m = 0; m < nd; ++m) {
         const double ui = U[(size_t)m * NP + is], wi = W[(size_t)m * NP + is];
 #pragma unroll
@@ -392,10 +506,20 @@ __device__ void l2_propose_slice(double* __restrict__ Gc, int NP, int KD, L2Smem
     cur ^= 1;
     __syncthreads();
     if (tid == 0) sm.h[is] = (int8_t)(-hs);     // after the barrier: no warp is still scanning site `is`
+#ifdef LQMC_PHASE_CLOCKS
+    { const long long tk1 = clock64(); tk_build += tk1 - tk0; tk0 = tk1; }
+#endif
     if (nd == KD) { l2_flush<EXACT>(Gc, NP, nd, sm, KD); nd = 0; }
+#ifdef LQMC_PHASE_CLOCKS
+    { const long long tk1 = clock64(); tk_flush += tk1 - tk0; tk0 = tk1; }
+#endif
     i0 = is + 1;
   }
   if (nd > 0) l2_flush<EXACT>(Gc, NP, nd, sm, KD);
+#ifdef LQMC_PHASE_CLOCKS
+  { const long long tk1 = clock64(); tk_flush += tk1 - tk0;
+    if (tid == 0) { double* ob = p.obs_sum + (size_t)blockIdx.x * 3 * N; ob[0] = (double)tk_scan; ob[1] = (double)tk_build; ob[2] = (double)tk_flush; ob[3] = (double)n_accepted; } }
+#endif
 }
 
 // ---- Gauss-Jordan inverse in memory (both spins in lockstep, in place), partial pivoting, delayed updates ----------
@@ -413,13 +537,14 @@ __device__ void l2_gj_inverse(double* __restrict__ Gc, int NP, int KD, L2Smem& s
   int nd = 0;
   for (int k = 0; k < NP; ++k) {
     // 1. column k of the current matrices
-    for (int x = tid; x < 2 * NP; x += L2_THREADS) {
-      const int spin = x / NP, r = x % NP;
+    for (int spin = 0; spin < 2; ++spin) {
       const double* U = sm.U + (size_t)spin * KD * NP;
       const double* W = sm.W + (size_t)spin * KD * NP;
-      double v = Gc[(size_t)spin * NP * NP + (size_t)r * NP + k];
-      for (int m = 0; m < nd; ++m) v = fma(-U[(size_t)m * NP + r], W[(size_t)m * NP + k], v);
-      colk[x] = v;
+      for (int r = tid; r < NP; r += L2_THREADS) {
+        double v = Gc[(size_t)spin * NP * NP + (size_t)r * NP + k];
+        for (int m = 0; m < nd; ++m) v = fma(-U[(size_t)m * NP + r], W[(size_t)m * NP + k], v);
+        colk[spin * NP + r] = v;
+      }
     }
     __syncthreads();
     // 2. pivot search, one half of the CTA per spin
@@ -459,8 +584,8 @@ __device__ void l2_gj_inverse(double* __restrict__ Gc, int NP, int KD, L2Smem& s
     }
     if (tid < 2) piv_global[tid * NP + k] = pidx[tid];
     // 3. current pivot row (row p before the swap), scaled with the 1-injection; physical swap in M0
-    for (int x = tid; x < 2 * NP; x += L2_THREADS) {
-      const int spin = x / NP, c = x % NP;
+    for (int spin = 0; spin < 2; ++spin)
+    for (int c = tid; c < NP; c += L2_THREADS) {
       const int pi = pidx[spin];
       const double* U = sm.U + (size_t)spin * KD * NP;
       const double* W = sm.W + (size_t)spin * KD * NP;
@@ -475,18 +600,18 @@ __device__ void l2_gj_inverse(double* __restrict__ Gc, int NP, int KD, L2Smem& s
     }
     __syncthreads();
     // 4. multipliers, detach row k / column k from the pending updates, eliminate column k in M0
-    for (int x = tid; x < 2 * NP; x += L2_THREADS) {
-      const int spin = x / NP, r = x % NP;
+    for (int spin = 0; spin < 2; ++spin)
+    for (int r = tid; r < NP; r += L2_THREADS) {
       const int pi = pidx[spin];
       double f;
       if (r == k) f = 0.0;
       else if (r == pi) f = colk[spin * NP + k];
-      else f = colk[x];
+      else f = colk[spin * NP + r];
       sm.U[((size_t)spin * KD + nd) * NP + r] = f;
       if (r != k && r != pi) Gc[(size_t)spin * NP * NP + (size_t)r * NP + k] = 0.0;
     }
-    for (int x = tid; x < 2 * nd; x += L2_THREADS) {
-      const int spin = x / nd, m = x % nd;
+    for (int spin = 0; spin < 2; ++spin)
+    for (int m = tid; m < nd; m += L2_THREADS) {
       const int pi = pidx[spin];
       double* U = sm.U + ((size_t)spin * KD + m) * NP;
       double* W = sm.W + ((size_t)spin * KD + m) * NP;
@@ -500,8 +625,8 @@ __device__ void l2_gj_inverse(double* __restrict__ Gc, int NP, int KD, L2Smem& s
   }
   if (nd > 0) l2_flush<false>(Gc, NP, nd, sm, KD);
   // undo the row interchanges on the columns, last pivot first
-  for (int x = tid; x < 2 * NP; x += L2_THREADS) {
-    const int spin = x / NP, r = x % NP;
+  for (int spin = 0; spin < 2; ++spin)
+  for (int r = tid; r < NP; r += L2_THREADS) {
     double* rp = Gc + (size_t)spin * NP * NP + (size_t)r * NP;
     const int* piv = piv_global + spin * NP;
     for (int k = NP - 1; k >= 0; --k) {
@@ -526,15 +651,14 @@ __device__ void l2_recompute(double* __restrict__ Gc, double* __restrict__ Tc, i
     int l = (l0 - 1 + L) % L;
     const int8_t* hl = field + (size_t)l * NP;
     if (L == 1) {
-      for (int x = tid; x < NP * NP; x += L2_THREADS) {
-        const int r = x / NP, c = x % NP;
-        G[x] = p.E[x] * hs_v(hl[c], spin, p) + (r == c ? 1.0 : 0.0);
-      }
+      for (int r = 0; r < NP; ++r)
+        for (int c = tid; c < NP; c += L2_THREADS)
+          G[(size_t)r * NP + c] = p.E[(size_t)r * NP + c] * hs_v(hl[c], spin, p) + (r == c ? 1.0 : 0.0);
     } else {
       // first factor, stored k-major (transposed): cur[c][r] = E[r][c] * v_c
-      for (int x = tid; x < NP * NP; x += L2_THREADS) {
-        const int c = x / NP, r = x % NP;
-        cur[x] = p.Et[x] * hs_v(hl[c], spin, p);
+      for (int c = 0; c < NP; ++c) {
+        const double v = hs_v(hl[c], spin, p);
+        for (int r = tid; r < NP; r += L2_THREADS) cur[(size_t)c * NP + r] = p.Et[(size_t)c * NP + r] * v;
       }
     }
     __syncthreads();
@@ -624,10 +748,8 @@ __global__ void __launch_bounds__(L2_THREADS, 2) sweep_l2_kernel(const L2Params 
       for (int spin = 0; spin < 2; ++spin) {
         const double* G = Gc + (size_t)spin * NP * NP;
         double* gs = p.g_sum + ((size_t)chain * 2 + spin) * N * N;
-        for (int x = tid; x < N * N; x += L2_THREADS) {
-          const int r = x / N, c = x % N;
-          gs[x] += G[(size_t)r * NP + c];
-        }
+        for (int r = 0; r < N; ++r)
+          for (int c = tid; c < N; c += L2_THREADS) gs[(size_t)r * N + c] += G[(size_t)r * NP + c];
       }
       for (int j = tid; j < N; j += L2_THREADS) {
         const double nu = 1.0 - Gc[(size_t)j * NP + j], nd = 1.0 - Gc[(size_t)NP * NP + (size_t)j * NP + j];
