@@ -338,7 +338,7 @@ def run_ours(args):
                           achieved=achieved, peak=peaks["fp64_tflops"], unit="TFLOP/s", frac=achieved / peaks["fp64_tflops"],
                           traffic=load_traffic(args.workload), peak_source=peaks["source"],
                           kernel="sweep_reg_kernel" if info["family"] == "reg" else "sweep_l2_kernel",
-                          flops_per_launch=flops),
+                          flops_per_launch=flops, hbm=hbm_leg(args.workload, kernel_ms, peaks)),
             e2e=dict(value=e2e_value, unit=UNIT,
                      h2d_bytes_per_step=int(world * (fields.nbytes + pin_uni.numel() * 8)),
                      d2h_bytes_per_step=int(world * (fields.nbytes + chains * 2 * n * n * 8)),
@@ -375,6 +375,15 @@ def load_peaks():
     return out
 
 
+def hbm_leg(workload, kernel_ms, peaks):
+    """Secondary roofline: measured DRAM bytes of the launch (ncu, profiles/traffic.json) over the live event time."""
+    t = load_traffic(workload)
+    if not t:
+        return None
+    gbs = t / (kernel_ms * 1e-3) * 1e-9
+    return dict(achieved=gbs, peak=peaks["hbm_gbs"], unit="GB/s", frac=gbs / peaks["hbm_gbs"])
+
+
 def load_traffic(workload):
     """dram bytes per launch from the committed ncu capture of this workload, if any."""
     try:
@@ -389,7 +398,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("LQMC_BENCH_WORKLOAD", "cfg2"), choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=os.environ.get("LQMC_BENCH_WORKLOAD", "cfg4"), choices=sorted(WORKLOADS),
+                    help="default cfg4 = the 16x16, beta=8 configuration north_star quotes the metric on")
     ap.add_argument("--chains", type=int, default=0, help="chains per GPU (default: the workload's)")
     ap.add_argument("--arith", default="exact", choices=["exact", "fma"])
     ap.add_argument("--seed", type=int, default=20260101)

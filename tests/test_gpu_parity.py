@@ -314,3 +314,46 @@ def test_shared_reciprocal_division_is_ieee():
     from latticeqmc_b200.engine import selftest_division
     assert selftest_division(1 << 28, seed=12345) == 0
     assert selftest_division(1 << 26, seed=777) == 0
+
+
+def test_parallel_manager_equals_reference_processes(golden):
+    """`measure(..., cores=C)` / ParallelProcessManager: chain c seeded like reference process c
+    (np.random.seed(pid); config.initialize(); run_lqmc(), multiprocessing.py:45-52), sweeps split
+    sweeps/procs with the remainder on chain 0 (:260-263), unweighted mean over chains (:265-267).
+    Checked against the oracle run the way a reference process would run."""
+    import lqmc
+    model = lqmc.HubbardModel(u=4, t=1)
+    model.build_square(2)
+    n, lt, warm, sweeps, procs = 4, 20, 3, 7, 3
+    seeds = [101, 202, 303]
+    mgr = lqmc.ParallelProcessManager(model, 2.0, lt, warmup=warm, procs=procs, seeds=seeds)
+    mgr.set_jobs(sweeps)
+    mgr.run()
+    gf_up, gf_dn = mgr.get_result()
+    dtau, lamb, exp_k = so.set_beta_constants(model.ham_kinetic(), 4, 2.0, lt)
+    split = [3, 2, 2]
+    total = np.zeros((2, n, n))
+    for c in range(procs):
+        state = np.random.get_state()
+        np.random.seed(seeds[c])
+        h = (2 * np.random.randint(0, 2, size=(n, lt)) - 1).astype(np.int8)
+        for _ in range(warm):
+            so.update_step(h, exp_k, lamb, None)
+        total += so.measure_loop(h, exp_k, lamb, split[c], None)
+        np.random.set_state(state)
+    ref = total / procs
+    assert _close(gf_up, ref[0], 1e-9) and _close(gf_dn, ref[1], 1e-9)
+    assert mgr.observables["docc"].shape == (procs, n)
+
+
+def test_measure_single_core_matches_run(golden):
+    """`lqmc.measure(model, beta, L, warmup, sweeps, cores=1)` = LatticeQMC(...).run() (lqmc/__init__.py:46-47)."""
+    import lqmc
+    g = golden("cfg1_2x2_free")
+    model = lqmc.HubbardModel(u=4, t=1)
+    model.build_square(2)
+    np.random.seed(11)
+    gf_up, gf_dn = lqmc.measure(model, 2.0, 20, 4, 6, cores=1, log_lvl=None)
+    ref_up = g["gf_up"][4:10].sum(0) / 6
+    ref_dn = g["gf_dn"][4:10].sum(0) / 6
+    assert _close(gf_up, ref_up, 1e-9) and _close(gf_dn, ref_dn, 1e-9)

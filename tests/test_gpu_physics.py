@@ -1,0 +1,65 @@
+"""Physics mode (textbook DQMC) on the GPU: against the physics oracle on the same
+uniforms, and against exact diagonalisation within statistical error (BASELINE.json north_star, second
+correctness gate)."""
+import numpy as np
+import pytest
+from scipy.linalg import expm
+
+from oracle import ed
+from oracle import sweep_oracle as so
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(u, beta, lt, mu=0.0):
+    ham = so.ideal_square_kinetic(2, 1.0, mu)          # diag = -mu; mu = 0 <=> true half filling (H6)
+    dtau, lamb, exp_k = so.set_beta_constants(ham, u, beta, lt)
+    return ham, lamb, exp_k, expm(dtau * ham)
+
+
+def test_physics_sweep_matches_oracle():
+    from latticeqmc_b200 import SweepEngine
+    ham, lamb, exp_k, exp_k_inv = _setup(4.0, 2.0, 20)
+    n, lt = 4, 20
+    fields = np.stack([so.initial_field(n, lt, 40 + c) for c in range(3)])
+    uni = np.random.RandomState(5).rand(3, 2, lt, n)
+    with SweepEngine(exp_k, lamb, lt, n_chains=3, exp_k_inv=exp_k_inv, mode="physics", trace=True) as eng:
+        eng.set_field(fields)
+        eng.sweep(2, uni)
+        acc, ratio = eng.get_trace()
+        gg = eng.get_g()
+    for c in range(3):
+        h = fields[c].copy()
+        for s in range(2):
+            gu, gd, r, a = so.physics_sweep(h, exp_k, exp_k_inv, lamb, uni[c, s])
+            assert np.array_equal(a, acc[c, s])
+            assert np.allclose(r, ratio[c, s], rtol=1e-8, atol=1e-10)
+            assert np.all(r > 0)                                  # a true determinant ratio at half filling
+        assert np.allclose(gg[c, 0], gu, atol=1e-9) and np.allclose(gg[c, 1], gd, atol=1e-9)
+
+
+def test_physics_mode_agrees_with_exact_diagonalisation():
+    """2x2, U=4, t=1, beta=2, dtau=0.1, half filling: 512 chains x 150 measured sweeps.  ED: n = 0.5/0.5,
+    <n_up n_dn> = 0.0873, local moment 0.8254.  Tolerance = Trotter error O(U t dtau^2) + statistics."""
+    from latticeqmc_b200 import SweepEngine
+    ham, lamb, exp_k, exp_k_inv = _setup(4.0, 2.0, 20)
+    hop = ham.copy()
+    np.fill_diagonal(hop, 0.0)
+    exact = ed.thermal_observables(hop, 4.0, 2.0, 2.0)
+    n, lt, chains = 4, 20, 512
+    fields = np.stack([so.initial_field(n, lt, 900 + c) for c in range(chains)])
+    with SweepEngine(exp_k, lamb, lt, n_chains=chains, exp_k_inv=exp_k_inv, mode="physics", arith="fma") as eng:
+        eng.set_field(fields)
+        eng.sweep(50, None, seed=77)
+        eng.sweep(150, None, seed=77, measure=True)
+        m = eng.get_measurements()
+    per_chain = m["obs_sum"].mean(axis=2) / m["n_meas"][:, None]           # (chains, 3)
+    mean = per_chain.mean(0)
+    err = per_chain.std(0, ddof=1) / np.sqrt(chains)
+    n_up, n_dn, docc = mean
+    assert err.max() < 5e-3
+    assert abs(n_up - exact["n_up"]) < 0.01 + 4 * err[0]
+    assert abs(n_dn - exact["n_dn"]) < 0.01 + 4 * err[1]
+    assert abs(docc - exact["docc"]) < 0.01 + 4 * err[2]
+    moment = n_up + n_dn - 2 * docc
+    assert abs(moment - exact["moment"]) < 0.02 + 8 * err.max()
