@@ -37,6 +37,7 @@ WORKLOADS = {
     "cfg2": ("square", 8, 4.0, 4.0, 40, 256, "8x8 square Hubbard, U=4, beta=4, dtau=0.1, 256 chains on 1 B200"),
     "cfg3": ("ring", 64, 8.0, 8.0, 80, 1024, "1D periodic chain N=64, U=8, beta=8, 1024 chains"),
     "cfg4": ("square", 16, 4.0, 8.0, 80, 296, "16x16 square Hubbard, U=4, beta=8, dtau=0.1, delayed rank-k updates"),
+    "cfg5": ("square", 24, 6.0, 10.0, 100, 148, "24x24 square Hubbard (N=576), U=6, beta=10, dtau=0.1"),
 }
 METRIC = "HS spin-flip updates/sec"
 UNIT = "proposals/s"
