@@ -70,6 +70,17 @@ int lqmc_get_g(lqmc_engine* e, double* g);
  * Parity mode uses l0 = 0 as the reference does; physics mode passes the slice the sweep is at. */
 int lqmc_recompute(lqmc_engine* e, int l0);
 
+/* Numerically stabilised G(l0) = inv(I + B_{l0-1} ... B_0 B_{L-1} ... B_{l0}) in the get_m convention
+ * (lqmc.py:156-185): the product is accumulated `chunk` factors at a time as U D V with a column-norm
+ * pre-pivoted Householder QR after every chunk, and G = (D_b^-1 U^T + D_s V)^-1 D_b^-1 U^T.  The reference has
+ * no counterpart (it inverts the raw product, lqmc.py:303-307, cond ~1e21 at beta >= 8: SURVEY.md H8); this is
+ * what physics mode uses.  Works in either mode as an inspection call (it only reads the field, writes G). */
+int lqmc_recompute_stable(lqmc_engine* e, int l0, int chunk);
+
+/* Physics mode only: rebuild G with lqmc_recompute_stable every `stab_every` slices inside lqmc_sweep
+ * (0 = off: one unstabilised sweep-start product, like the reference).  LQMC_ERR_INVALID in parity mode. */
+int lqmc_set_stabilization(lqmc_engine* e, int stab_every);
+
 /* The N proposals of time slice l (lqmc.py:311-335): ratio, Metropolis test `u <= ratio`,
  * Sherman-Morrison rank-1 update of both G, field flip.  uniforms: host f64 [chain][site], or NULL for
  * the device Philox stream of (seed, chain) at the engine's current sweep counter. */

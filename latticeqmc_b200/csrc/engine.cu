@@ -15,6 +15,7 @@
 #include "../../include/lqmc_b200.h"
 #include "sweep_reg.cuh"
 #include "sweep_l2.cuh"
+#include "stab.cuh"
 
 namespace {
 
@@ -61,6 +62,21 @@ struct lqmc_engine {
   long long launches = 0;
   int8_t* hostField = nullptr;     // pinned staging for the layout conversions
   double* hostG = nullptr;
+  // stabilised recompute (stab.cuh), allocated on first use
+  int stab_every = 0;
+  struct Stab {
+    bool ready = false;
+    int NPs = 0, nfrag = 4, kd = 1;
+    double* X[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // [2C][NPs^2] work matrices
+    double* dvec = nullptr;       // [2C][NPs]
+    double* tfac = nullptr;       // [2C][NPs * ST_NB]
+    int* perm = nullptr;          // [2C][NPs]
+    int* piv = nullptr;           // [2C][NPs]
+    double* E = nullptr; double* Et = nullptr;   // exp(-dtau K) padded to NPs (own copies when NPs != NP)
+    bool own_E = false;
+    size_t smem_gemm = 0, smem_qr = 0, smem_inv = 0;
+  } st;
+  std::vector<double> hE;          // host copy of exp_k (N x N)
 };
 
 namespace {
@@ -112,24 +128,41 @@ int launch_reg(lqmc_engine* e, const lqmc::SweepParams& p, cudaStream_t s) {
 }
 
 // One entry for every phase combination: n_sweeps x [recompute?] + steps [step_lo, step_hi) x [propose?][wrap?]
-int run(lqmc_engine* e, int n_sweeps, int step_lo, int step_hi, bool recompute, bool propose, bool wrap, bool measure,
-        int l0, const double* d_uniforms, uint64_t seed, cudaStream_t s) {
+struct RunSpec {
+  int n_sweeps = 1, step_lo = 0, step_hi = 0;
+  bool recompute = false, propose = false, wrap = false, measure = false, skip_last_wrap = false;
+  int l0 = 0;
+  const double* d_uniforms = nullptr;
+  uint64_t seed = 0;
+  long long sweep0 = -1;                 // -1: the engine's sweep counter
+  int buf_sweeps = -1, buf_steps = -1, buf_sweep0 = 0, buf_step0 = -1;   // -1: this launch's own extent
+  bool keep_trace_extent = false;        // the caller sized the trace buffers for a segmented sweep
+};
+
+int run(lqmc_engine* e, const RunSpec& r, cudaStream_t s) {
   CU(cudaSetDevice(e->device));
   lqmc::SweepParams p;
   memset(&p, 0, sizeof(p));
   p.n_sites = e->N; p.n_slices = e->L; p.n_chains = e->C;
   p.E = e->dE; p.Et = e->dEt; p.Ei = e->dEi; p.Eit = e->dEit;
   p.field = e->dField; p.G = e->dG;
-  p.uniforms = d_uniforms; p.seed = seed;
-  p.sweep0 = e->sweep_counter; p.chain0 = e->chain0;
+  p.uniforms = r.d_uniforms; p.seed = r.seed;
+  p.sweep0 = r.sweep0 >= 0 ? r.sweep0 : e->sweep_counter; p.chain0 = e->chain0;
   p.g_sum = e->dGsum; p.obs_sum = e->dObs; p.n_meas = e->dNmeas; p.n_acc = e->dNacc;
-  p.n_sweeps = n_sweeps; p.step_lo = step_lo; p.step_hi = step_hi;
-  p.do_recompute = recompute; p.do_propose = propose; p.do_wrap = wrap; p.measure = measure; p.recompute_l0 = l0;
+  p.n_sweeps = r.n_sweeps; p.step_lo = r.step_lo; p.step_hi = r.step_hi;
+  p.do_recompute = r.recompute; p.do_propose = r.propose; p.do_wrap = r.wrap; p.measure = r.measure; p.recompute_l0 = r.l0;
+  p.skip_last_wrap = r.skip_last_wrap;
+  p.buf_sweeps = r.buf_sweeps >= 0 ? r.buf_sweeps : r.n_sweeps;
+  p.buf_steps = r.buf_steps >= 0 ? r.buf_steps : (r.step_hi - r.step_lo);
+  p.buf_sweep0 = r.buf_sweep0;
+  p.buf_step0 = r.buf_step0 >= 0 ? r.buf_step0 : r.step_lo;
   p.exp_pl = e->hs[0]; p.exp_ml = e->hs[1]; p.f_p2 = e->hs[2]; p.f_m2 = e->hs[3];
-  if (propose) {
-    const size_t count = (size_t)e->C * n_sweeps * (step_hi - step_lo) * e->N;
-    int rc = ensure_trace(e, count);
-    if (rc) return rc;
+  if (r.propose) {
+    if (!r.keep_trace_extent) {
+      const size_t count = (size_t)e->C * r.n_sweeps * (r.step_hi - r.step_lo) * e->N;
+      int rc = ensure_trace(e, count);
+      if (rc) return rc;
+    }
     if (e->flags & LQMC_TRACE) { p.tr_ratio = e->dTrRatio; p.tr_acc = e->dTrAcc; }
   }
   int rc;
@@ -145,6 +178,163 @@ int run(lqmc_engine* e, int n_sweeps, int step_lo, int step_hi, bool recompute, 
     if (rc) return rc;
   }
   return rc;
+}
+
+// ---- stabilised recompute: host orchestration of the stab.cuh kernels ---------------------------------------------
+template <class K>
+int set_smem(K kernel, size_t bytes) {
+  CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return LQMC_OK;
+}
+
+int stab_init(lqmc_engine* e) {
+  auto& st = e->st;
+  if (st.ready) return LQMC_OK;
+  CU(cudaSetDevice(e->device));
+  st.NPs = lqmc::st_padded_size(e->N);
+  st.nfrag = (st.NPs == 64) ? 2 : 4;
+  const size_t nm = (size_t)2 * e->C, mat = (size_t)st.NPs * st.NPs;
+  for (int i = 0; i < 5; ++i)
+    if (cudaMalloc(&st.X[i], nm * mat * sizeof(double)) != cudaSuccess)
+      return fail(LQMC_ERR_NOMEM, "cudaMalloc of the stabilisation workspace failed (%zu bytes x 5)", nm * mat * sizeof(double));
+  if (cudaMalloc(&st.dvec, nm * st.NPs * sizeof(double)) != cudaSuccess ||
+      cudaMalloc(&st.tfac, nm * st.NPs * lqmc::ST_NB * sizeof(double)) != cudaSuccess ||
+      cudaMalloc(&st.perm, nm * st.NPs * sizeof(int)) != cudaSuccess || cudaMalloc(&st.piv, nm * st.NPs * sizeof(int)) != cudaSuccess)
+    return fail(LQMC_ERR_NOMEM, "cudaMalloc of the stabilisation vectors failed");
+  if (st.NPs == e->NP) {
+    st.E = e->dE; st.Et = e->dEt; st.own_E = false;
+  } else {
+    std::vector<double> m(mat, 0.0), mt(mat, 0.0);
+    for (int i = 0; i < st.NPs; ++i)
+      for (int j = 0; j < st.NPs; ++j) {
+        const double v = (i < e->N && j < e->N) ? e->hE[(size_t)i * e->N + j] : (i == j ? 1.0 : 0.0);
+        m[(size_t)i * st.NPs + j] = v;
+        mt[(size_t)j * st.NPs + i] = v;
+      }
+    if (cudaMalloc(&st.E, mat * sizeof(double)) != cudaSuccess || cudaMalloc(&st.Et, mat * sizeof(double)) != cudaSuccess)
+      return fail(LQMC_ERR_NOMEM, "cudaMalloc of the padded exp_k failed");
+    st.own_E = true;
+    CU(cudaMemcpy(st.E, m.data(), mat * sizeof(double), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(st.Et, mt.data(), mat * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  st.smem_gemm = (size_t)lqmc::ST_STAGES * lqmc::ST_BK * (lqmc::ST_LDA + 32 * st.nfrag + 4) * sizeof(double);
+  st.smem_qr = lqmc::StQrSmem<lqmc::ST_NB>::bytes(st.NPs);
+  int rc = 0;
+  if (st.nfrag == 4) {
+    int kd = 1;
+    while (kd < 32 && lqmc::l2_smem_bytes(st.NPs, kd + 1, 1) <= 110 * 1024) ++kd;
+    st.kd = kd;
+    st.smem_inv = lqmc::l2_smem_bytes(st.NPs, kd, 1);
+    rc |= set_smem(lqmc::st_chain_kernel<4>, st.smem_gemm);
+    rc |= set_smem(lqmc::st_v_kernel<4>, st.smem_gemm);
+    rc |= set_smem(lqmc::st_final_kernel<4>, st.smem_gemm);
+    rc |= set_smem(lqmc::st_inverse_l2_kernel, st.smem_inv);
+  } else {
+    st.smem_inv = lqmc::RegCfg<64, 16, 8>::smem_bytes;
+    rc |= set_smem(lqmc::st_chain_kernel<2>, st.smem_gemm);
+    rc |= set_smem(lqmc::st_v_kernel<2>, st.smem_gemm);
+    rc |= set_smem(lqmc::st_final_kernel<2>, st.smem_gemm);
+    rc |= set_smem(lqmc::st_inverse_small_kernel, st.smem_inv);
+  }
+  rc |= set_smem(lqmc::st_qr_kernel<lqmc::ST_NB>, st.smem_qr);
+  if (rc) return rc;
+  st.ready = true;
+  return LQMC_OK;
+}
+
+void stab_free(lqmc_engine* e) {
+  auto& st = e->st;
+  for (int i = 0; i < 5; ++i) if (st.X[i]) cudaFree(st.X[i]);
+  if (st.dvec) cudaFree(st.dvec);
+  if (st.tfac) cudaFree(st.tfac);
+  if (st.perm) cudaFree(st.perm);
+  if (st.piv) cudaFree(st.piv);
+  if (st.own_E) { if (st.E) cudaFree(st.E); if (st.Et) cudaFree(st.Et); }
+  st = lqmc_engine::Stab();
+}
+
+lqmc::HsConsts hs_consts(const lqmc_engine* e) { return lqmc::HsConsts{e->hs[0], e->hs[1]}; }
+
+// (U, D, V) <- UDV decomposition of  [B_{s_last} ... B_{s_first}] * U D V   (normal)  or of the transposed chain.
+// Usrc / Dsrc / Vold may be nullptr (identity).  Uses X[0], X[1] as scratch; outputs must not alias them or Vold.
+int stab_absorb(lqmc_engine* e, const double* Usrc, size_t u_stride, const double* Dsrc, size_t d_stride, const double* Vold,
+                size_t vold_stride, int s_start, int s_step, int count, bool transposed, double* Uout, size_t uo_stride,
+                double* Dout, size_t do_stride, double* Vout, size_t vo_stride, cudaStream_t s) {
+  auto& st = e->st;
+  const int grid = 2 * e->C;
+  lqmc::StChainArgs ca;
+  ca.src = Usrc; ca.src_stride = u_stride; ca.dcol = Dsrc; ca.dcol_stride = d_stride;
+  ca.buf0 = st.X[0]; ca.buf1 = st.X[1];
+  ca.field = e->dField; ca.Eop = transposed ? st.E : st.Et;
+  ca.N = e->N; ca.NPs = st.NPs; ca.NPf = e->NP; ca.L = e->L;
+  ca.s_start = s_start; ca.s_step = s_step; ca.count = count; ca.transposed = transposed ? 1 : 0;
+  ca.hc = hs_consts(e);
+  if (st.nfrag == 4) lqmc::st_chain_kernel<4><<<grid, lqmc::ST_THREADS, st.smem_gemm, s>>>(ca);
+  else lqmc::st_chain_kernel<2><<<grid, lqmc::ST_THREADS, st.smem_gemm, s>>>(ca);
+  double* Mres = st.X[count & 1];
+  double* Moth = st.X[(count + 1) & 1];
+  lqmc::StQrArgs qa;
+  qa.M = Mres; qa.A = Moth; qa.Q = Uout; qa.q_stride = uo_stride; qa.dvec = Dout; qa.d_stride = do_stride;
+  qa.tfac = st.tfac; qa.perm = st.perm; qa.N = e->N; qa.NPs = st.NPs;
+  lqmc::st_qr_kernel<lqmc::ST_NB><<<grid, lqmc::ST_THREADS, st.smem_qr, s>>>(qa);
+  lqmc::StVArgs va;
+  va.R = Moth; va.dvec = Dout; va.d_stride = do_stride; va.perm = st.perm; va.Vold = Vold; va.vold_stride = vold_stride;
+  va.At = Mres; va.Vnew = Vout; va.vnew_stride = vo_stride; va.N = e->N; va.NPs = st.NPs; va.hc = hs_consts(e);
+  if (st.nfrag == 4) lqmc::st_v_kernel<4><<<grid, lqmc::ST_THREADS, st.smem_gemm, s>>>(va);
+  else lqmc::st_v_kernel<2><<<grid, lqmc::ST_THREADS, st.smem_gemm, s>>>(va);
+  CU(cudaGetLastError());
+  e->launches += 3;
+  return LQMC_OK;
+}
+
+int stab_invert(lqmc_engine* e, double* M, cudaStream_t s) {
+  auto& st = e->st;
+  lqmc::StInvArgs ia;
+  ia.M = M; ia.piv = st.piv; ia.NPs = st.NPs; ia.KD = st.kd;
+  if (st.nfrag == 4) lqmc::st_inverse_l2_kernel<<<2 * e->C, lqmc::L2_THREADS, st.smem_inv, s>>>(ia);
+  else lqmc::st_inverse_small_kernel<<<2 * e->C, 128, st.smem_inv, s>>>(ia);
+  CU(cudaGetLastError());
+  e->launches += 1;
+  return LQMC_OK;
+}
+
+// G(l0) = inv(I + B_{l0-1} ... B_0 B_{L-1} ... B_{l0}) from scratch, `chunk` factors per QR (one-sided UDV)
+int stab_recompute_scratch(lqmc_engine* e, int l0, int chunk, cudaStream_t s) {
+  int rc = stab_init(e);
+  if (rc) return rc;
+  auto& st = e->st;
+  const size_t mat = (size_t)st.NPs * st.NPs;
+  double* XU = st.X[2];
+  double* Vcur = st.X[3];
+  double* Vnext = st.X[4];
+  bool first = true;
+  int sl = l0, remaining = e->L;
+  while (remaining > 0) {
+    const int cnt = remaining < chunk ? remaining : chunk;
+    rc = stab_absorb(e, first ? nullptr : XU, mat, first ? nullptr : st.dvec, st.NPs, first ? nullptr : Vcur, mat, sl, +1, cnt, false,
+                     XU, mat, st.dvec, st.NPs, Vnext, mat, s);
+    if (rc) return rc;
+    double* t = Vcur; Vcur = Vnext; Vnext = t;
+    first = false;
+    sl = (sl + cnt) % e->L;
+    remaining -= cnt;
+  }
+  const int grid = 2 * e->C;
+  lqmc::StFormsArgs fa;
+  fa.U = XU; fa.u_stride = mat; fa.V = Vcur; fa.v_stride = mat; fa.dvec = st.dvec; fa.d_stride = st.NPs;
+  fa.lhsT = st.X[0]; fa.rhs = st.X[1]; fa.NPs = st.NPs;
+  lqmc::st_forms_kernel<<<grid, lqmc::ST_THREADS, 0, s>>>(fa);
+  e->launches += 1;
+  rc = stab_invert(e, st.X[0], s);
+  if (rc) return rc;
+  lqmc::StFinalArgs ga;
+  ga.At = st.X[1]; ga.B = st.X[0]; ga.rvec = nullptr; ga.rvec_stride = 0; ga.scratch = Vnext; ga.G = e->dG;
+  ga.N = e->N; ga.NPs = st.NPs; ga.NPg = e->NP; ga.transposed_out = 1; ga.hc = hs_consts(e);
+  if (st.nfrag == 4) lqmc::st_final_kernel<4><<<grid, lqmc::ST_THREADS, st.smem_gemm, s>>>(ga);
+  else lqmc::st_final_kernel<2><<<grid, lqmc::ST_THREADS, st.smem_gemm, s>>>(ga);
+  CU(cudaGetLastError());
+  e->launches += 1;
+  return LQMC_OK;
 }
 
 }  // namespace
@@ -168,6 +358,7 @@ int lqmc_create(lqmc_engine** out, int device, int n_sites, int n_slices, int n_
   if (!e) return fail(LQMC_ERR_NOMEM, "out of host memory");
   e->device = device; e->N = n_sites; e->L = n_slices; e->C = n_chains; e->flags = flags; e->lamb = lamb;
   memcpy(e->hs, hs_consts, sizeof(e->hs));
+  e->hE.assign(exp_k, exp_k + (size_t)n_sites * n_sites);
   if (n_sites <= 64) {
     e->family_reg = true;
     e->NP = n_sites <= 16 ? 16 : (n_sites <= 32 ? 32 : 64);
@@ -225,6 +416,7 @@ void lqmc_destroy(lqmc_engine* e) {
   for (void* p : ptrs)
     if (p) cudaFree(p);
   lqmc::l2_free(e->l2);
+  stab_free(e);
   if (e->hostField) cudaFreeHost(e->hostField);
   if (e->hostG) cudaFreeHost(e->hostG);
   if (e->stream) cudaStreamDestroy(e->stream);
@@ -289,9 +481,32 @@ int lqmc_get_g(lqmc_engine* e, double* g) {
 int lqmc_recompute(lqmc_engine* e, int l0) {
   if (!e) return fail(LQMC_ERR_INVALID, "engine is NULL");
   if (l0 < 0 || l0 >= e->L) return fail(LQMC_ERR_INVALID, "l0 = %d outside [0, %d)", l0, e->L);
-  int rc = run(e, 1, 0, 0, true, false, false, false, l0, nullptr, 0, e->stream);
+  RunSpec r;
+  r.recompute = true; r.l0 = l0;
+  int rc = run(e, r, e->stream);
   if (rc) return rc;
   CU(cudaStreamSynchronize(e->stream));
+  return LQMC_OK;
+}
+
+int lqmc_recompute_stable(lqmc_engine* e, int l0, int chunk) {
+  if (!e) return fail(LQMC_ERR_INVALID, "engine is NULL");
+  if (l0 < 0 || l0 >= e->L) return fail(LQMC_ERR_INVALID, "l0 = %d outside [0, %d)", l0, e->L);
+  if (chunk < 1) return fail(LQMC_ERR_INVALID, "chunk = %d must be >= 1", chunk);
+  CU(cudaSetDevice(e->device));
+  int rc = stab_recompute_scratch(e, l0, chunk, e->stream);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(e->stream));
+  return LQMC_OK;
+}
+
+int lqmc_set_stabilization(lqmc_engine* e, int stab_every) {
+  if (!e) return fail(LQMC_ERR_INVALID, "engine is NULL");
+  if (stab_every < 0) return fail(LQMC_ERR_INVALID, "stab_every = %d is negative", stab_every);
+  if (stab_every > 0 && !(e->flags & LQMC_MODE_PHYSICS))
+    return fail(LQMC_ERR_INVALID, "stabilisation belongs to physics mode: the reference recurrence recomputes G exactly once per "
+                                  "sweep, unstabilised (lqmc.py:303-307)");
+  e->stab_every = stab_every;
   return LQMC_OK;
 }
 
@@ -305,7 +520,9 @@ int lqmc_slice(lqmc_engine* e, int l, const double* uniforms, uint64_t seed) {
     if (rc) return rc;
     d_u = e->dUni;
   }
-  int rc = run(e, 1, step, step + 1, false, true, false, false, 0, d_u, seed, e->stream);
+  RunSpec r;
+  r.step_lo = step; r.step_hi = step + 1; r.propose = true; r.d_uniforms = d_u; r.seed = seed;
+  int rc = run(e, r, e->stream);
   if (rc) return rc;
   CU(cudaStreamSynchronize(e->stream));
   return LQMC_OK;
@@ -315,7 +532,9 @@ int lqmc_wrap(lqmc_engine* e, int l) {
   if (!e) return fail(LQMC_ERR_INVALID, "engine is NULL");
   if (l < 1 || l >= e->L) return fail(LQMC_ERR_INVALID, "wrap needs 1 <= l < %d, got %d", e->L, l);
   const int step = e->L - 1 - l;
-  int rc = run(e, 1, step, step + 1, false, false, true, false, 0, nullptr, 0, e->stream);
+  RunSpec r;
+  r.step_lo = step; r.step_hi = step + 1; r.wrap = true;
+  int rc = run(e, r, e->stream);
   if (rc) return rc;
   CU(cudaStreamSynchronize(e->stream));
   return LQMC_OK;
@@ -327,7 +546,32 @@ int lqmc_sweep_async(lqmc_engine* e, int n_sweeps, const double* d_uniforms, uin
   if (n_sweeps == 0) return LQMC_OK;
   cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
   const bool phys = (e->flags & LQMC_MODE_PHYSICS) != 0;
-  int rc = run(e, n_sweeps, 0, e->L, true, true, true, measure != 0, phys ? e->L - 1 : 0, d_uniforms, seed, s);
+  if (phys && e->stab_every > 0) {
+    // stabilised schedule: G is rebuilt from the field (QR/UDV) at the top of every segment of stab_every slices and
+    // propagated by wraps inside it; one sweep = ceil(L / stab_every) x (stabilisation kernels + one sweep-kernel launch)
+    CU(cudaSetDevice(e->device));
+    int rc = ensure_trace(e, (size_t)e->C * n_sweeps * e->L * e->N);
+    if (rc) return rc;
+    for (int sw = 0; sw < n_sweeps; ++sw)
+      for (int lo = 0; lo < e->L; lo += e->stab_every) {
+        const int hi = (lo + e->stab_every < e->L) ? lo + e->stab_every : e->L;
+        rc = stab_recompute_scratch(e, e->L - 1 - lo, e->stab_every, s);
+        if (rc) return rc;
+        RunSpec r;
+        r.step_lo = lo; r.step_hi = hi; r.propose = true; r.wrap = true; r.skip_last_wrap = true;
+        r.measure = (measure != 0) && hi == e->L;
+        r.d_uniforms = d_uniforms; r.seed = seed; r.sweep0 = e->sweep_counter + sw;
+        r.buf_sweeps = n_sweeps; r.buf_steps = e->L; r.buf_sweep0 = sw; r.buf_step0 = 0; r.keep_trace_extent = true;
+        rc = run(e, r, s);
+        if (rc) return rc;
+      }
+    e->sweep_counter += n_sweeps;
+    return LQMC_OK;
+  }
+  RunSpec r;
+  r.n_sweeps = n_sweeps; r.step_lo = 0; r.step_hi = e->L; r.recompute = true; r.propose = true; r.wrap = true;
+  r.measure = measure != 0; r.l0 = phys ? e->L - 1 : 0; r.d_uniforms = d_uniforms; r.seed = seed;
+  int rc = run(e, r, s);
   if (rc) return rc;
   e->sweep_counter += n_sweeps;
   return LQMC_OK;

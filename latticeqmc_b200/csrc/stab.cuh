@@ -1,0 +1,592 @@
+// Numerically stabilised Green's function for the HS-field sweep: batched Householder-QR / UDV kernels.
+//
+// The reference recomputes G = inv(I + B_{L-1} ... B_0) once per sweep as a plain matrix product followed by
+// np.linalg.inv (/root/reference/lqmc/lqmc.py:156-185,303-307).  At beta >= 8 that product has a condition number
+// of 1e21..1e24 and the result is roundoff.  Physics mode replaces it by the standard DQMC
+// stabilisation: the product is accumulated `chunk` factors at a time as
+//        A = U D V,      U orthogonal, D positive diagonal (graded), V well conditioned
+// with a column-norm pre-pivoted Householder QR after every chunk, and
+//        G = (D_b^-1 U^T + D_s V)^-1 D_b^-1 U^T,       D = D_b D_s split at 1.
+//
+// One CTA (256 threads) per (chain, spin) matrix; everything lives in HBM / L2 except the QR panel.
+//   st_chain_kernel   M = B_s ... B_s' (U D): `count` GEMMs (DMMA m8n8k4, operand ring as in sweep_l2.cuh) with the
+//                     diagonal exp(V_l) as a row scale and D as a column scale in the epilogues
+//   st_qr_kernel      column norms -> permutation -> blocked Householder QR (panel of NB columns factored in shared
+//                     memory, compact-WY trailing update streamed over the rest) -> D = |diag R| -> explicit Q
+//   st_v_kernel       V <- (D^-1 R) P^T V, one GEMM whose right operand rows are gathered through the permutation
+//   st_forms / st_inverse / st_final     the G formula above
+// The two-sided variant (st_combine_*) joins a stack of left products with the running right product so that a
+// stabilisation point costs O(1) QR factorizations instead of O(L / chunk).
+#pragma once
+#include "sweep_l2.cuh"
+
+namespace lqmc {
+
+constexpr int ST_THREADS = 256;
+constexpr int ST_BM = 64, ST_BK = 16, ST_STAGES = 3;
+constexpr int ST_LDA = ST_BM + 4;
+constexpr int ST_NB = 16;                 // QR panel width
+constexpr int ST_CB = 256;                // columns per trailing-update block (2 per thread, thread pairs split the reflectors)
+
+struct HsConsts { double exp_pl, exp_ml; };
+
+// exp(-sigma lamb h) (inv = false) or its inverse, sigma = +1 for spin index 0   [get_exp_v, lqmc.py:149-154]
+__device__ __forceinline__ double st_hs(int8_t h, int spin, bool inv, const HsConsts& c) {
+  const bool minus = ((h > 0) != (spin != 0));
+  return (minus != inv) ? c.exp_ml : c.exp_pl;
+}
+
+inline int st_padded_size(int n_sites) { return n_sites <= 64 ? 64 : (n_sites + 127) / 128 * 128; }
+
+// ---- GEMM  C = A * B,  A given k-major, B row-major (rows optionally gathered through bperm) ----------------------
+struct StEpilogue {
+  const int8_t* hrow = nullptr;   // row scale exp(-+sigma lamb h[row]) for row < nvalid
+  bool row_inv = false;
+  const double* rvec = nullptr;   // row scale by a vector
+  const double* cvec = nullptr;   // column scale by a vector
+  bool transposed_out = false;
+  int nvalid = 0;
+};
+
+template <int NFRAG>
+__device__ void st_gemm(const double* __restrict__ At, const double* __restrict__ B, const int* __restrict__ bperm,
+                        double* __restrict__ Cout, int NP, int spin, const StEpilogue& ep, const HsConsts& hc, double* pa,
+                        double* pb) {
+  constexpr int BN = 32 * NFRAG, LDB = BN + 4;
+  constexpr int BSH = (NFRAG == 4) ? 6 : 5, BQ = (NFRAG == 4) ? 4 : 2, BSTEP = (NFRAG == 4) ? 4 : 8;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp >> 2, wn = warp & 3;
+  const int lr = lane >> 2, lk = lane & 3;
+  const int nk = NP / ST_BK;
+  const int brow = tid >> BSH, bchunk = tid & ((1 << BSH) - 1);
+  __syncthreads();
+  for (int i0 = 0; i0 < NP; i0 += ST_BM) {
+    for (int j0 = 0; j0 < NP; j0 += BN) {
+      double acc[4][NFRAG][2];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < NFRAG; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+      const double* srcA = At + (size_t)(tid >> 5) * NP + i0 + 2 * (tid & 31);
+      double* dstA = pa + (tid >> 5) * ST_LDA + 2 * (tid & 31);
+      double* dstB = pb + brow * LDB + 2 * bchunk;
+      auto issue = [&](int kpanel, int stage) {
+        const int k0 = kpanel * ST_BK;
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+          __pipeline_memcpy_async(dstA + stage * ST_BK * ST_LDA + q * 8 * ST_LDA, srcA + (size_t)(k0 + q * 8) * NP, 16);
+#pragma unroll
+        for (int q = 0; q < BQ; ++q) {
+          const int krow = k0 + brow + q * BSTEP;
+          const int srow = bperm ? bperm[krow] : krow;
+          __pipeline_memcpy_async(dstB + stage * ST_BK * LDB + q * BSTEP * LDB, B + (size_t)srow * NP + j0 + 2 * bchunk, 16);
+        }
+      };
+#pragma unroll
+      for (int s0 = 0; s0 < ST_STAGES - 1; ++s0) {
+        if (s0 < nk) issue(s0, s0);
+        __pipeline_commit();
+      }
+      for (int kp = 0; kp < nk; ++kp) {
+        const int st = kp % ST_STAGES;
+        __pipeline_wait_prior(ST_STAGES - 2);
+        __syncthreads();
+        if (kp + ST_STAGES - 1 < nk) issue(kp + ST_STAGES - 1, (kp + ST_STAGES - 1) % ST_STAGES);
+        __pipeline_commit();
+        const double* ap = pa + st * ST_BK * ST_LDA + lk * ST_LDA + 32 * wm + lr;
+        const double* bp = pb + st * ST_BK * LDB + lk * LDB + 8 * NFRAG * wn + lr;
+#pragma unroll
+        for (int k4 = 0; k4 < ST_BK / 4; ++k4) {
+          double a[4], b[NFRAG];
+#pragma unroll
+          for (int m = 0; m < 4; ++m) a[m] = ap[4 * k4 * ST_LDA + 8 * m];
+#pragma unroll
+          for (int n = 0; n < NFRAG; ++n) b[n] = bp[4 * k4 * LDB + 8 * n];
+#pragma unroll
+          for (int m = 0; m < 4; ++m)
+#pragma unroll
+            for (int n = 0; n < NFRAG; ++n) dmma884(acc[m][n], a[m], b[n]);
+        }
+      }
+      __pipeline_wait_prior(0);
+      __syncthreads();
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const int row = i0 + 32 * wm + 8 * m + lr;
+        double rs = 1.0;
+        if (ep.hrow && row < ep.nvalid) rs = st_hs(ep.hrow[row], spin, ep.row_inv, hc);
+        if (ep.rvec) rs *= ep.rvec[row];
+#pragma unroll
+        for (int n = 0; n < NFRAG; ++n) {
+          const int col0 = j0 + 8 * NFRAG * wn + 8 * n + 2 * lk;
+          double v0 = acc[m][n][0] * rs, v1 = acc[m][n][1] * rs;
+          if (ep.cvec) { v0 *= ep.cvec[col0]; v1 *= ep.cvec[col0 + 1]; }
+          if (!ep.transposed_out) {
+            *reinterpret_cast<double2*>(Cout + (size_t)row * NP + col0) = make_double2(v0, v1);
+          } else {
+            Cout[(size_t)col0 * NP + row] = v0;
+            Cout[(size_t)(col0 + 1) * NP + row] = v1;
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// out[j][i] = f(in[i][j], i, j) over the full padded matrix, through 32 x 33 shared tiles (both sides coalesced)
+template <class F>
+__device__ void st_transpose_map(const double* __restrict__ in, double* __restrict__ out, int NP, double* tile, F f) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i0 = 0; i0 < NP; i0 += 32)
+    for (int j0 = 0; j0 < NP; j0 += 32) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) tile[(warp + 8 * q) * 33 + lane] = in[(size_t)(i0 + warp + 8 * q) * NP + j0 + lane];
+      __syncthreads();
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int j = j0 + warp + 8 * q, i = i0 + lane;
+        out[(size_t)j * NP + i] = f(tile[lane * 33 + warp + 8 * q], i, j);
+      }
+      __syncthreads();
+    }
+}
+
+__device__ __forceinline__ double st_warp_sum(double v) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  return v;
+}
+
+// ---- st_chain_kernel ---------------------------------------------------------------------------------------------
+// normal     : X <- B_{s_last} ... B_{s_first} * src * diag(dcol),   B_s = E diag(v_s)      (left products)
+// transposed : X <- B_{s_last}^T ... B_{s_first}^T * src * diag(dcol),  B_s^T = diag(v_s) E^T  (right products, transposed)
+// slices s_i = (s_start + i s_step) mod L.  The result is in buf[count & 1].
+struct StChainArgs {
+  const double* src; size_t src_stride;      // nullptr: identity
+  const double* dcol; size_t dcol_stride;    // nullptr: no column scale
+  double* buf0; double* buf1;                // [2C][NPs^2]
+  const int8_t* field;                       // [chain][L][NPf]
+  const double* Eop;                         // k-major left operand: E^T stored row-major (normal) / E row-major (transposed)
+  int N, NPs, NPf, L;
+  int s_start, s_step, count, transposed;
+  HsConsts hc;
+};
+
+template <int NFRAG>
+__global__ void __launch_bounds__(ST_THREADS) st_chain_kernel(const StChainArgs a) {
+  extern __shared__ __align__(16) unsigned char st_smem[];
+  double* pa = reinterpret_cast<double*>(st_smem);
+  double* pb = pa + ST_STAGES * ST_BK * ST_LDA;
+  const int m = blockIdx.x, chain = m >> 1, spin = m & 1;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int NP = a.NPs;
+  const int8_t* field = a.field + (size_t)chain * a.L * a.NPf;
+  double* buf[2] = {a.buf0 + (size_t)m * NP * NP, a.buf1 + (size_t)m * NP * NP};
+  const double* src = a.src ? a.src + (size_t)m * a.src_stride : nullptr;
+  const double* dcol = a.dcol ? a.dcol + (size_t)m * a.dcol_stride : nullptr;
+  auto slice_of = [&](int i) { int s = (a.s_start + i * a.s_step) % a.L; return s < 0 ? s + a.L : s; };
+  {
+    const int8_t* h0 = field + (size_t)slice_of(0) * a.NPf;
+    for (int r = warp; r < NP; r += ST_THREADS / 32) {
+      const double rs = (!a.transposed && r < a.N) ? st_hs(h0[r], spin, false, a.hc) : 1.0;
+      for (int c = lane; c < NP; c += 32) {
+        const double x = src ? src[(size_t)r * NP + c] : (r == c ? 1.0 : 0.0);
+        buf[0][(size_t)r * NP + c] = x * rs;
+      }
+    }
+  }
+  for (int i = 0; i < a.count; ++i) {
+    StEpilogue ep;
+    ep.nvalid = a.N;
+    const bool last = (i == a.count - 1);
+    if (!a.transposed) {
+      if (!last) ep.hrow = field + (size_t)slice_of(i + 1) * a.NPf;
+    } else {
+      ep.hrow = field + (size_t)slice_of(i) * a.NPf;
+    }
+    if (last) ep.cvec = dcol;
+    st_gemm<NFRAG>(a.Eop, buf[i & 1], nullptr, buf[(i + 1) & 1], NP, spin, ep, a.hc, pa, pb);
+  }
+}
+
+// ---- blocked Householder QR ----------------------------------------------------------------------------------------
+// Compact-WY block reflector applied from the left to A[row0 : row0+m, c0 : c1):
+//     A <- (I - V Top V^T) A,     Top = T^T (TRANS_T, the factorization's Q^T A) or T (forming Q)
+// V (m x NB, unit lower trapezoid, explicit) and T (NB x NB upper triangular) are in shared memory.  Thread pairs
+// (tid, tid + 128) share two columns {c, c + 128} of the block and split the reflector index range.
+template <int NB, bool TRANS_T>
+__device__ void st_apply_reflector(double* __restrict__ Amat, int ld, int row0, int m, int c0, int c1,
+                                   const double* __restrict__ Vs, const double* __restrict__ Ts, double* __restrict__ Wt) {
+  constexpr int LDV = NB + 2, NA = NB / 2;
+  const int tid = threadIdx.x, cl = tid & 127, half = tid >> 7;
+  const int a0 = half * NA;
+  double* const abase = Amat + (size_t)row0 * ld;
+  for (int cb = c0; cb < c1; cb += ST_CB) {
+    const int ca = cb + cl, cb2 = ca + 128;
+    const bool va = ca < c1, vb = cb2 < c1;
+    // W = V^T A_blk
+    double acc0[NA], acc1[NA];
+#pragma unroll
+    for (int q = 0; q < NA; ++q) acc0[q] = acc1[q] = 0.0;
+#pragma unroll 4
+    for (int r = 0; r < m; ++r) {
+      const double x0 = va ? abase[(size_t)r * ld + ca] : 0.0;
+      const double x1 = vb ? abase[(size_t)r * ld + cb2] : 0.0;
+      const double* vr = Vs + r * LDV + a0;
+#pragma unroll
+      for (int q = 0; q < NA; q += 2) {
+        const double2 v = *reinterpret_cast<const double2*>(vr + q);
+        acc0[q] = fma(v.x, x0, acc0[q]); acc0[q + 1] = fma(v.y, x0, acc0[q + 1]);
+        acc1[q] = fma(v.x, x1, acc1[q]); acc1[q + 1] = fma(v.y, x1, acc1[q + 1]);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < NA; ++q) { Wt[(a0 + q) * ST_CB + cl] = acc0[q]; Wt[(a0 + q) * ST_CB + 128 + cl] = acc1[q]; }
+    __syncthreads();
+    // W2 = Top W  (this thread's reflector range, its two columns)
+#pragma unroll
+    for (int q = 0; q < NA; ++q) acc0[q] = acc1[q] = 0.0;
+    for (int b = 0; b < NB; ++b) {
+      const double y0 = Wt[b * ST_CB + cl], y1 = Wt[b * ST_CB + 128 + cl];
+#pragma unroll
+      for (int q = 0; q < NA; ++q) {
+        const double t = TRANS_T ? Ts[b * NB + a0 + q] : Ts[(a0 + q) * NB + b];
+        acc0[q] = fma(t, y0, acc0[q]);
+        acc1[q] = fma(t, y1, acc1[q]);
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < NA; ++q) { Wt[(a0 + q) * ST_CB + cl] = acc0[q]; Wt[(a0 + q) * ST_CB + 128 + cl] = acc1[q]; }
+    __syncthreads();
+    // A_blk <- A_blk - V W2 : the pair splits the rows
+    double f0[NB], f1[NB];
+#pragma unroll
+    for (int q = 0; q < NB; ++q) { f0[q] = Wt[q * ST_CB + cl]; f1[q] = Wt[q * ST_CB + 128 + cl]; }
+#pragma unroll 2
+    for (int r = half; r < m; r += 2) {
+      double x0 = va ? abase[(size_t)r * ld + ca] : 0.0;
+      double x1 = vb ? abase[(size_t)r * ld + cb2] : 0.0;
+      const double* vr = Vs + r * LDV;
+#pragma unroll
+      for (int q = 0; q < NB; q += 2) {
+        const double2 v = *reinterpret_cast<const double2*>(vr + q);
+        x0 = fma(-v.x, f0[q], x0); x0 = fma(-v.y, f0[q + 1], x0);
+        x1 = fma(-v.x, f1[q], x1); x1 = fma(-v.y, f1[q + 1], x1);
+      }
+      if (va) abase[(size_t)r * ld + ca] = x0;
+      if (vb) abase[(size_t)r * ld + cb2] = x1;
+    }
+    __syncthreads();
+  }
+}
+
+template <int NB>
+struct StQrSmem {
+  static constexpr int LDV = NB + 2;
+  double* P;      // [rows][LDV] panel / reflectors
+  double* Ts;     // [NB][NB]
+  double* Gm;     // [NB][NB]
+  double* taus;   // [NB]
+  double* dots;   // [NB]
+  double* Wt;     // [NB][ST_CB]
+  __device__ StQrSmem(unsigned char* base, int rows) {
+    P = reinterpret_cast<double*>(base);
+    Ts = P + (size_t)rows * LDV;
+    Gm = Ts + NB * NB;
+    taus = Gm + NB * NB;
+    dots = taus + NB;
+    Wt = dots + NB;
+  }
+  static size_t bytes(int rows) { return ((size_t)rows * (NB + 2) + 2 * NB * NB + 2 * NB + (size_t)NB * ST_CB) * sizeof(double); }
+};
+
+// T factor of the panel's block reflector from the explicit V in sm.P (m rows, w valid columns) and sm.taus
+template <int NB>
+__device__ void st_form_t(StQrSmem<NB>& sm, int m, int w) {
+  constexpr int LDV = NB + 2;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int q = tid; q < NB * NB; q += ST_THREADS) { sm.Ts[q] = 0.0; sm.Gm[q] = 0.0; }
+  __syncthreads();
+  for (int q = warp; q < NB * NB; q += ST_THREADS / 32) {
+    const int a = q / NB, b = q % NB;
+    if (a < b && b < w) {
+      double s = 0.0;
+      for (int r = lane; r < m; r += 32) s = fma(sm.P[r * LDV + a], sm.P[r * LDV + b], s);
+      s = st_warp_sum(s);
+      if (lane == 0) sm.Gm[a * NB + b] = s;
+    }
+  }
+  __syncthreads();
+  if (warp == 0) {
+    for (int j = 0; j < w; ++j) {
+      if (lane < j) {
+        double s = 0.0;
+        for (int l = lane; l < j; ++l) s = fma(sm.Ts[lane * NB + l], sm.Gm[l * NB + j], s);
+        sm.Ts[lane * NB + j] = -sm.taus[j] * s;
+      }
+      if (lane == j) sm.Ts[j * NB + j] = sm.taus[j];
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+}
+
+struct StQrArgs {
+  const double* M;     // [2C][NPs^2] matrix to factor
+  double* A;           // [2C][NPs^2] work: column-permuted copy, then R (upper) + reflectors (lower)
+  double* Q; size_t q_stride;
+  double* dvec; size_t d_stride;
+  double* tfac;        // [2C][NPs * NB]
+  int* perm;           // [2C][NPs]
+  int N, NPs;
+};
+
+template <int NB>
+__global__ void __launch_bounds__(ST_THREADS) st_qr_kernel(const StQrArgs a) {
+  constexpr int LDV = NB + 2;
+  extern __shared__ __align__(16) unsigned char st_smem[];
+  const int N = a.N, NP = a.NPs;
+  StQrSmem<NB> sm(st_smem, NP);
+  const int m_idx = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const double* M = a.M + (size_t)m_idx * NP * NP;
+  double* A = a.A + (size_t)m_idx * NP * NP;
+  double* Q = a.Q + (size_t)m_idx * a.q_stride;
+  double* dvec = a.dvec + (size_t)m_idx * a.d_stride;
+  double* tfac = a.tfac + (size_t)m_idx * NP * NB;
+  int* perm = a.perm + (size_t)m_idx * NP;
+
+  // 1. column norms and the descending-norm permutation (ties: lower index first)
+  double* norms = sm.P;
+  for (int c = tid; c < N; c += ST_THREADS) {
+    double s = 0.0;
+    for (int r = 0; r < N; ++r) { const double v = M[(size_t)r * NP + c]; s = fma(v, v, s); }
+    norms[c] = s;
+  }
+  __syncthreads();
+  for (int c = tid; c < NP; c += ST_THREADS) {
+    if (c < N) {
+      const double nc = norms[c];
+      int rank = 0;
+      for (int o = 0; o < N; ++o) { const double no = norms[o]; rank += (no > nc || (no == nc && o < c)) ? 1 : 0; }
+      perm[rank] = c;
+    } else {
+      perm[c] = c;
+    }
+  }
+  __syncthreads();
+  // 2. A = M[:, perm]
+  for (int r = warp; r < N; r += ST_THREADS / 32)
+    for (int j = lane; j < N; j += 32) A[(size_t)r * NP + j] = M[(size_t)r * NP + perm[j]];
+  __syncthreads();
+
+  // 3. panels
+  for (int j0 = 0; j0 < N; j0 += NB) {
+    const int w = min(NB, N - j0), m = N - j0;
+    for (int r = warp; r < m; r += ST_THREADS / 32)
+      if (lane < NB) sm.P[r * LDV + lane] = (lane < w) ? A[(size_t)(j0 + r) * NP + j0 + lane] : 0.0;
+    if (tid < NB) sm.taus[tid] = 0.0;
+    __syncthreads();
+    double scale_prev = 0.0, beta_prev = 0.0, tau_prev = 0.0;
+    for (int j = 0; j < w; ++j) {
+      // finish column j-1 (nobody reads it any more): scale the reflector, store beta and tau
+      if (j > 0) {
+        for (int r = j + tid; r < m; r += ST_THREADS) sm.P[r * LDV + j - 1] *= scale_prev;
+        if (tid == 0) { sm.P[(j - 1) * LDV + j - 1] = beta_prev; sm.taus[j - 1] = tau_prev; }
+      }
+      // dots[c] = sum_{r > j} P[r][j] P[r][c]  for c = j .. w-1
+      for (int c = j + warp; c < w; c += ST_THREADS / 32) {
+        double s = 0.0;
+        for (int r = j + 1 + lane; r < m; r += 32) s = fma(sm.P[r * LDV + j], sm.P[r * LDV + c], s);
+        s = st_warp_sum(s);
+        if (lane == 0) sm.dots[c] = s;
+      }
+      __syncthreads();
+      const double alpha = sm.P[j * LDV + j], sigma = sm.dots[j];
+      double tau = 0.0, beta = alpha, scale = 0.0;
+      if (sigma != 0.0) {
+        const double nrm = sqrt(fma(alpha, alpha, sigma));
+        beta = (alpha >= 0.0) ? -nrm : nrm;
+        tau = (beta - alpha) / beta;
+        scale = 1.0 / (alpha - beta);
+        for (int c = j + 1 + warp; c < w; c += ST_THREADS / 32) {
+          const double wv = fma(scale, sm.dots[c], sm.P[j * LDV + c]);
+          const double tw = tau * wv, tws = tw * scale;
+          for (int r = j + 1 + lane; r < m; r += 32) sm.P[r * LDV + c] = fma(-tws, sm.P[r * LDV + j], sm.P[r * LDV + c]);
+          __syncwarp();
+          if (lane == 0) sm.P[j * LDV + c] -= tw;
+        }
+      }
+      scale_prev = scale; beta_prev = beta; tau_prev = tau;
+      __syncthreads();
+    }
+    {
+      const int j = w;
+      for (int r = j + tid; r < m; r += ST_THREADS) sm.P[r * LDV + j - 1] *= scale_prev;
+      if (tid == 0) { sm.P[(j - 1) * LDV + j - 1] = beta_prev; sm.taus[j - 1] = tau_prev; }
+    }
+    __syncthreads();
+    // write the factored panel back (R on and above the diagonal, reflectors below) and make V explicit
+    for (int r = warp; r < m; r += ST_THREADS / 32)
+      if (lane < w) A[(size_t)(j0 + r) * NP + j0 + lane] = sm.P[r * LDV + lane];
+    __syncthreads();
+    for (int q = tid; q < NB * NB; q += ST_THREADS) {
+      const int r = q / NB, c = q % NB;
+      if (r < m && c >= r) sm.P[r * LDV + c] = (c == r && c < w) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    st_form_t<NB>(sm, m, w);
+    for (int q = tid; q < NB * NB; q += ST_THREADS) tfac[(size_t)j0 * NB + q] = sm.Ts[q];
+    if (j0 + w < N) st_apply_reflector<NB, true>(A, NP, j0, m, j0 + w, N, sm.P, sm.Ts, sm.Wt);
+    __syncthreads();
+  }
+
+  // 4. D = |diag R|
+  for (int j = tid; j < NP; j += ST_THREADS) {
+    double d = 1.0;
+    if (j < N) { d = fabs(A[(size_t)j * NP + j]); if (!(d > 0.0)) d = 1e-300; }
+    dvec[j] = d;
+  }
+  // 5. explicit Q = H_1 ... H_N
+  for (int r = warp; r < NP; r += ST_THREADS / 32)
+    for (int c = lane; c < NP; c += 32) Q[(size_t)r * NP + c] = (r == c) ? 1.0 : 0.0;
+  __syncthreads();
+  const int n_panels = (N + NB - 1) / NB;
+  for (int pb = n_panels - 1; pb >= 0; --pb) {
+    const int j0 = pb * NB, w = min(NB, N - j0), m = N - j0;
+    for (int r = warp; r < m; r += ST_THREADS / 32)
+      if (lane < NB) {
+        double v = 0.0;
+        if (lane < w) v = (r > lane) ? A[(size_t)(j0 + r) * NP + j0 + lane] : (r == lane ? 1.0 : 0.0);
+        sm.P[r * LDV + lane] = v;
+      }
+    for (int q = tid; q < NB * NB; q += ST_THREADS) sm.Ts[q] = tfac[(size_t)j0 * NB + q];
+    __syncthreads();
+    st_apply_reflector<NB, false>(Q, NP, j0, m, j0, N, sm.P, sm.Ts, sm.Wt);
+  }
+}
+
+// ---- V <- (D^-1 R) P^T V ---------------------------------------------------------------------------------------------
+struct StVArgs {
+  const double* R;       // [2C][NPs^2] factored matrix (upper triangle = R)
+  const double* dvec; size_t d_stride;
+  const int* perm;       // [2C][NPs]
+  const double* Vold; size_t vold_stride;     // nullptr: identity
+  double* At;            // [2C][NPs^2] scratch for the k-major left operand
+  double* Vnew; size_t vnew_stride;
+  int N, NPs;
+  HsConsts hc;
+};
+
+template <int NFRAG>
+__global__ void __launch_bounds__(ST_THREADS) st_v_kernel(const StVArgs a) {
+  extern __shared__ __align__(16) unsigned char st_smem[];
+  double* pa = reinterpret_cast<double*>(st_smem);
+  double* pb = pa + ST_STAGES * ST_BK * ST_LDA;
+  const int m = blockIdx.x, NP = a.NPs, N = a.N;
+  const double* R = a.R + (size_t)m * NP * NP;
+  const double* dvec = a.dvec + (size_t)m * a.d_stride;
+  const int* perm = a.perm + (size_t)m * NP;
+  double* At = a.At + (size_t)m * NP * NP;
+  double* Vnew = a.Vnew + (size_t)m * a.vnew_stride;
+  // At[k][i] = R[i][k] / D[i]  (i <= k < N), identity elsewhere
+  st_transpose_map(R, At, NP, pa, [&](double x, int i, int k) {
+    if (k < N && i <= k) return x / dvec[i];
+    return (i == k) ? 1.0 : 0.0;
+  });
+  if (a.Vold) {
+    StEpilogue ep;
+    st_gemm<NFRAG>(At, a.Vold + (size_t)m * a.vold_stride, perm, Vnew, NP, m & 1, ep, a.hc, pa, pb);
+  } else {
+    // V_old = I: V_new[i][perm[k]] = At[k][i]
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int k = warp; k < NP; k += ST_THREADS / 32) {
+      const int pk = perm[k];
+      for (int i = lane; i < NP; i += 32) Vnew[(size_t)i * NP + pk] = At[(size_t)k * NP + i];
+    }
+  }
+}
+
+// ---- one-sided G = (D_b^-1 U^T + D_s V)^-1 D_b^-1 U^T ---------------------------------------------------------------
+// st_forms:   lhsT[i][j] = U[i][j] / db[j] + V[j][i] ds[j]   (the transposed left-hand side, row-major)
+//             rhs[k][i]  = U[i][k] / db[k]                   (= D_b^-1 U^T row-major = k-major left operand of the last GEMM)
+// then  W = inv(lhsT)  and  G^T = (U D_b^-1) W.
+struct StFormsArgs {
+  const double* U; size_t u_stride;
+  const double* V; size_t v_stride;
+  const double* dvec; size_t d_stride;
+  double* lhsT; double* rhs;      // [2C][NPs^2]
+  int NPs;
+};
+
+__global__ void __launch_bounds__(ST_THREADS) st_forms_kernel(const StFormsArgs a) {
+  __shared__ double tile[32 * 33];
+  const int m = blockIdx.x, NP = a.NPs;
+  const double* U = a.U + (size_t)m * a.u_stride;
+  const double* V = a.V + (size_t)m * a.v_stride;
+  const double* d = a.dvec + (size_t)m * a.d_stride;
+  double* lhsT = a.lhsT + (size_t)m * NP * NP;
+  double* rhs = a.rhs + (size_t)m * NP * NP;
+  // rhs[k][i] = U[i][k] / max(d[k], 1)
+  st_transpose_map(U, rhs, NP, tile, [&](double x, int i, int k) { return x / fmax(d[k], 1.0); });
+  // lhsT[i][j] = V[j][i] * min(d[j], 1)   (+ U[i][j] / max(d[j], 1) below)
+  st_transpose_map(V, lhsT, NP, tile, [&](double x, int j, int i) { return x * fmin(d[j], 1.0); });
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = warp; i < NP; i += ST_THREADS / 32)
+    for (int j = lane; j < NP; j += 32) lhsT[(size_t)i * NP + j] += U[(size_t)i * NP + j] / fmax(d[j], 1.0);
+}
+
+// in-place inverse of one matrix per CTA, large sizes: delayed Gauss-Jordan of sweep_l2.cuh on a single matrix
+struct StInvArgs { double* M; int* piv; int NPs, KD; };
+
+__global__ void __launch_bounds__(L2_THREADS) st_inverse_l2_kernel(const StInvArgs a) {
+  extern __shared__ __align__(16) unsigned char st_smem[];
+  L2Smem sm(st_smem, a.NPs, a.KD, 1);
+  l2_gj_inverse<1>(a.M + (size_t)blockIdx.x * a.NPs * a.NPs, a.NPs, a.KD, sm, a.piv + (size_t)blockIdx.x * a.NPs);
+}
+
+// small sizes (NPs = 64): shared-memory Gauss-Jordan of sweep_reg.cuh, 128 threads
+__global__ void __launch_bounds__(128) st_inverse_small_kernel(const StInvArgs a) {
+  using C = RegCfg<64, 16, 8>;
+  extern __shared__ __align__(16) unsigned char st_smem[];
+  RegSmem<C> sm(st_smem);
+  double* M = a.M + (size_t)blockIdx.x * 64 * 64;
+  const int t = threadIdx.x;
+  for (int q = t; q < 64 * 64; q += 128) sm.stage[(q >> 6) * C::S + (q & 63)] = M[q];
+  __syncthreads();
+  gj_inverse<C>(sm.stage, sm, 0, t);
+  for (int q = t; q < 64 * 64; q += 128) M[q] = sm.stage[(q >> 6) * C::S + (q & 63)];
+}
+
+// G^T = rhs^T-as-k-major * W, written transposed into a scratch matrix, then copied into the sweep kernels' G
+struct StFinalArgs {
+  const double* At;      // [2C][NPs^2] k-major left operand
+  const double* B;       // [2C][NPs^2]
+  const double* rvec; size_t rvec_stride;   // optional row scale of the product (row index of A*B)
+  double* scratch;       // [2C][NPs^2]
+  double* G;             // [chain][2][NPg][NPg]
+  int N, NPs, NPg, transposed_out;
+  HsConsts hc;
+};
+
+template <int NFRAG>
+__global__ void __launch_bounds__(ST_THREADS) st_final_kernel(const StFinalArgs a) {
+  extern __shared__ __align__(16) unsigned char st_smem[];
+  double* pa = reinterpret_cast<double*>(st_smem);
+  double* pb = pa + ST_STAGES * ST_BK * ST_LDA;
+  const int m = blockIdx.x, NP = a.NPs;
+  double* scratch = a.scratch + (size_t)m * NP * NP;
+  StEpilogue ep;
+  ep.transposed_out = a.transposed_out != 0;
+  if (a.rvec) ep.rvec = a.rvec + (size_t)m * a.rvec_stride;
+  st_gemm<NFRAG>(a.At + (size_t)m * NP * NP, a.B + (size_t)m * NP * NP, nullptr, scratch, NP, m & 1, ep, a.hc, pa, pb);
+  double* G = a.G + (size_t)m * a.NPg * a.NPg;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int r = warp; r < a.N; r += ST_THREADS / 32)
+    for (int c = lane; c < a.N; c += 32) G[(size_t)r * a.NPg + c] = scratch[(size_t)r * NP + c];
+}
+
+}  // namespace lqmc

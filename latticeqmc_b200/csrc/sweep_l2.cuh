@@ -66,14 +66,15 @@ struct L2Smem {
   double* pb;     // [L2_STAGES][BK][BN + 4]
   uint64_t* full; // [L2_STAGES] mbarriers: "panel landed"
   uint32_t pipe_iter = 0;   // panels consumed so far by this CTA (uniform across threads): stage and phase parity
-  __device__ L2Smem(unsigned char* base, int NP, int KD) {
+  // ns = matrices the CTA works on at once (2: both spins of a chain; 1: the single-matrix inverse of stab.cuh)
+  __device__ L2Smem(unsigned char* base, int NP, int KD, int ns = 2) {
     U = reinterpret_cast<double*>(base);
-    W = U + (size_t)2 * KD * NP;
+    W = U + (size_t)ns * KD * NP;
     pa = U;
     pb = pa + L2_STAGES * L2_BK * (L2_BM + 4);
-    double* tail = W + (size_t)2 * KD * NP;
+    double* tail = W + (size_t)ns * KD * NP;
     const size_t gemm_end = (size_t)L2_STAGES * L2_BK * (L2_BM + L2_BN + 8);
-    if ((size_t)4 * KD * NP < gemm_end) tail = U + gemm_end;
+    if ((size_t)2 * ns * KD * NP < gemm_end) tail = U + gemm_end;
     d = tail;
     u = d + 4 * NP;
     red_v = u + NP;
@@ -84,8 +85,8 @@ struct L2Smem {
   }
 };
 
-inline size_t l2_smem_bytes(int NP, int KD) {
-  size_t vec = (size_t)4 * KD * NP;
+inline size_t l2_smem_bytes(int NP, int KD, int ns = 2) {
+  size_t vec = (size_t)2 * ns * KD * NP;
   const size_t gemm = (size_t)L2_STAGES * L2_BK * (L2_BM + L2_BN + 8);
   if (vec < gemm) vec = gemm;
   return (vec + 5 * (size_t)NP + 16 + 4) * sizeof(double) + 16 * sizeof(int) + 2 * (size_t)NP + 16;
@@ -318,10 +319,10 @@ __device__ void l2_gemm(const double* __restrict__ At, const double* __restrict_
 // {64+2l, 64+2l+1}, so every global access of a warp is one fully coalesced 512-byte row segment, the U
 // fragment is a warp-wide broadcast and the W fragment a conflict-free 512-byte read.  The next tile's loads
 // are kept in flight while the nd updates are applied to the current one.
-template <bool EXACT>
+template <bool EXACT, int NS = 2>
 __device__ void l2_flush(double* __restrict__ Gc, int NP, int nd, L2Smem& sm, int KD) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int n_tiles = 2 * (NP / 32) * (NP / 128);
+  const int n_tiles = NS * (NP / 32) * (NP / 128);
   double* const thread_base = Gc + (size_t)(4 * warp) * NP + 2 * lane;
   // tile walk (spin, i0, j0) kept as running offsets: no integer division in the loop (the XU pipe is 1/4 rate)
   struct Walk { int spin, i0, j0; };
@@ -530,14 +531,15 @@ __device__ void l2_propose_slice(double* __restrict__ Gc, int NP, int KD, L2Smem
 // final form and detached from the pending updates (their U / W entries are zeroed), so they carry no
 // cancellation error.  Same pivot rule as LAPACK's getrf (first entry of largest magnitude); rows are swapped
 // physically, columns are un-permuted at the end.
+template <int NS = 2>
 __device__ void l2_gj_inverse(double* __restrict__ Gc, int NP, int KD, L2Smem& sm, int* piv_global) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  constexpr int HALF = L2_THREADS / 2, WPS = HALF / 32;     // threads / warps per spin in the pivot search
+  constexpr int HALF = L2_THREADS / NS, WPS = HALF / 32;     // threads / warps per spin in the pivot search
   double* colk = sm.d;                                       // [2][NP] (the diagonal cache is idle here)
   int nd = 0;
   for (int k = 0; k < NP; ++k) {
     // 1. column k of the current matrices
-    for (int spin = 0; spin < 2; ++spin) {
+    for (int spin = 0; spin < NS; ++spin) {
       const double* U = sm.U + (size_t)spin * KD * NP;
       const double* W = sm.W + (size_t)spin * KD * NP;
       for (int r = tid; r < NP; r += L2_THREADS) {
@@ -567,10 +569,10 @@ __device__ void l2_gj_inverse(double* __restrict__ Gc, int NP, int KD, L2Smem& s
       if (lane == 0) { sm.red_v[warp] = pv; sm.red_i[warp] = idx; }
     }
     __syncthreads();
-    int pidx[2];
-    double ppv[2];
+    int pidx[NS];
+    double ppv[NS];
 #pragma unroll
-    for (int spin = 0; spin < 2; ++spin) {
+    for (int spin = 0; spin < NS; ++spin) {
       double pv = sm.red_v[spin * WPS];
       int idx = sm.red_i[spin * WPS];
 #pragma unroll
@@ -582,9 +584,9 @@ __device__ void l2_gj_inverse(double* __restrict__ Gc, int NP, int KD, L2Smem& s
       if (idx >= NP) { idx = k; pv = colk[spin * NP + k]; }
       pidx[spin] = idx; ppv[spin] = pv;
     }
-    if (tid < 2) piv_global[tid * NP + k] = pidx[tid];
+    if (tid < NS) piv_global[tid * NP + k] = pidx[tid];
     // 3. current pivot row (row p before the swap), scaled with the 1-injection; physical swap in M0
-    for (int spin = 0; spin < 2; ++spin)
+    for (int spin = 0; spin < NS; ++spin)
     for (int c = tid; c < NP; c += L2_THREADS) {
       const int pi = pidx[spin];
       const double* U = sm.U + (size_t)spin * KD * NP;
@@ -600,7 +602,7 @@ __device__ void l2_gj_inverse(double* __restrict__ Gc, int NP, int KD, L2Smem& s
     }
     __syncthreads();
     // 4. multipliers, detach row k / column k from the pending updates, eliminate column k in M0
-    for (int spin = 0; spin < 2; ++spin)
+    for (int spin = 0; spin < NS; ++spin)
     for (int r = tid; r < NP; r += L2_THREADS) {
       const int pi = pidx[spin];
       double f;
@@ -610,7 +612,7 @@ __device__ void l2_gj_inverse(double* __restrict__ Gc, int NP, int KD, L2Smem& s
       sm.U[((size_t)spin * KD + nd) * NP + r] = f;
       if (r != k && r != pi) Gc[(size_t)spin * NP * NP + (size_t)r * NP + k] = 0.0;
     }
-    for (int spin = 0; spin < 2; ++spin)
+    for (int spin = 0; spin < NS; ++spin)
     for (int m = tid; m < nd; m += L2_THREADS) {
       const int pi = pidx[spin];
       double* U = sm.U + ((size_t)spin * KD + m) * NP;
@@ -621,11 +623,11 @@ __device__ void l2_gj_inverse(double* __restrict__ Gc, int NP, int KD, L2Smem& s
     }
     ++nd;
     __syncthreads();
-    if (nd == KD) { l2_flush<false>(Gc, NP, nd, sm, KD); nd = 0; }
+    if (nd == KD) { l2_flush<false, NS>(Gc, NP, nd, sm, KD); nd = 0; }
   }
-  if (nd > 0) l2_flush<false>(Gc, NP, nd, sm, KD);
+  if (nd > 0) l2_flush<false, NS>(Gc, NP, nd, sm, KD);
   // undo the row interchanges on the columns, last pivot first
-  for (int spin = 0; spin < 2; ++spin)
+  for (int spin = 0; spin < NS; ++spin)
   for (int r = tid; r < NP; r += L2_THREADS) {
     double* rp = Gc + (size_t)spin * NP * NP + (size_t)r * NP;
     const int* piv = piv_global + spin * NP;
@@ -672,7 +674,7 @@ __device__ void l2_recompute(double* __restrict__ Gc, double* __restrict__ Tc, i
       double* t = cur; cur = oth; oth = t;
     }
   }
-  l2_gj_inverse(Gc, NP, KD, sm, piv_global);
+  l2_gj_inverse<2>(Gc, NP, KD, sm, piv_global);
 }
 
 // ---- wrap from slice l to l-1 ------------------------------------------------------------------------------
@@ -710,7 +712,6 @@ __global__ void __launch_bounds__(L2_THREADS, 2) sweep_l2_kernel(const L2Params 
   double* Gc = p.G + (size_t)chain * 2 * NP * NP;
   double* Tc = lp.T + (size_t)chain * 2 * NP * NP;
   int* piv = lp.piv + (size_t)chain * 2 * NP;
-  const int n_steps = p.step_hi - p.step_lo;
   int n_accepted = 0;
   if (tid == 0) {
     for (int s0 = 0; s0 < L2_STAGES; ++s0) mbar_init(sm.full + s0, 1);
@@ -722,7 +723,7 @@ __global__ void __launch_bounds__(L2_THREADS, 2) sweep_l2_kernel(const L2Params 
     if (p.do_recompute) l2_recompute(Gc, Tc, NP, KD, field, p.recompute_l0, p, sm, piv);
     for (int step = p.step_lo; step < p.step_hi; ++step) {
       const int l = L - 1 - step;
-      const long long base = (((long long)chain * p.n_sweeps + sweep) * n_steps + (step - p.step_lo)) * N;
+      const long long base = (((long long)chain * p.buf_sweeps + p.buf_sweep0 + sweep) * p.buf_steps + (step - p.buf_step0)) * N;
       if (p.do_propose) {
         __syncthreads();
         for (int j = tid; j < NP; j += L2_THREADS) {
@@ -738,7 +739,7 @@ __global__ void __launch_bounds__(L2_THREADS, 2) sweep_l2_kernel(const L2Params 
         __syncthreads();
         for (int j = tid; j < NP; j += L2_THREADS) field[(size_t)l * NP + j] = sm.h[j];
       }
-      if (p.do_wrap && l > 0) {
+      if (p.do_wrap && l > 0 && !(p.skip_last_wrap && step == p.step_hi - 1)) {
         __syncthreads();
         l2_wrap<PHYS>(Gc, Tc, NP, field + (size_t)(l - 1) * NP, p, sm);
       }

@@ -56,6 +56,10 @@ struct SweepParams {
   uint8_t* tr_acc;
   int n_sweeps, step_lo, step_hi;
   int do_recompute, do_propose, do_wrap, measure, recompute_l0;
+  int skip_last_wrap;   // no wrap after step_hi-1 (the caller recomputes G for the next slice: stabilised segments)
+  // indexing of the uniforms / trace buffers [chain][buf_sweeps][buf_steps][N]: this launch's sweep s and step t sit at
+  // sweep index buf_sweep0 + s and step index t - buf_step0 (a segmented sweep is several launches over one buffer)
+  int buf_sweeps, buf_steps, buf_sweep0, buf_step0;
   double exp_pl, exp_ml, f_p2, f_m2;  // exp(+lamb), exp(-lamb), exp(+2 lamb)-1, exp(-2 lamb)-1
 };
 
@@ -508,7 +512,6 @@ __global__ void __launch_bounds__(C::THREADS, (C::THREADS == 256) ? 2 : 4) sweep
   const int N = p.n_sites, L = p.n_slices;
   int8_t* field = p.field + (size_t)chain * L * NP;
   double* Gc = p.G + ((size_t)chain * 2 + spin) * NP * NP;
-  const int n_steps = p.step_hi - p.step_lo;
   double g[TR][TC];
   int n_accepted = 0;
 
@@ -518,7 +521,7 @@ __global__ void __launch_bounds__(C::THREADS, (C::THREADS == 256) ? 2 : 4) sweep
     if (p.do_recompute) recompute_g<C>(g, sm, p, field, p.recompute_l0, spin, t, ty, tx);
     for (int step = p.step_lo; step < p.step_hi; ++step) {
       const int l = L - 1 - step;
-      const long long base = (((long long)chain * p.n_sweeps + sweep) * n_steps + (step - p.step_lo)) * N;
+      const long long base = (((long long)chain * p.buf_sweeps + p.buf_sweep0 + sweep) * p.buf_steps + (step - p.buf_step0)) * N;
       if (p.do_propose) {
         __syncthreads();             // previous users of sm.u / sm.h are done
         if (tid < NP) {
@@ -536,7 +539,7 @@ __global__ void __launch_bounds__(C::THREADS, (C::THREADS == 256) ? 2 : 4) sweep
         __syncthreads();
         if (tid < NP) field[l * NP + tid] = sm.h[tid];
       }
-      if (p.do_wrap && l > 0) {
+      if (p.do_wrap && l > 0 && !(p.skip_last_wrap && step == p.step_hi - 1)) {
         __syncthreads();
         if (tid < NP) sm.hn[tid] = field[(l - 1) * NP + tid];
         // wrap_g's first barrier (after store_tile) also publishes sm.hn

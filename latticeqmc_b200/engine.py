@@ -23,7 +23,7 @@ EXPORTS = (
     "lqmc_recompute", "lqmc_slice", "lqmc_wrap", "lqmc_sweep", "lqmc_sweep_async", "lqmc_sync",
     "lqmc_get_trace", "lqmc_get_measurements", "lqmc_reset_measurements", "lqmc_device_ptr", "lqmc_info",
     "lqmc_set_sweep_counter", "lqmc_set_chain_offset", "lqmc_philox_uniforms", "lqmc_last_error",
-    "lqmc_version", "lqmc_selftest_division",
+    "lqmc_version", "lqmc_selftest_division", "lqmc_recompute_stable", "lqmc_set_stabilization",
 )
 
 
@@ -56,6 +56,8 @@ def load_library(path=None):
     lib.lqmc_set_g.argtypes = [vp, vp]
     lib.lqmc_get_g.argtypes = [vp, vp]
     lib.lqmc_recompute.argtypes = [vp, ctypes.c_int]
+    lib.lqmc_recompute_stable.argtypes = [vp, ctypes.c_int, ctypes.c_int]
+    lib.lqmc_set_stabilization.argtypes = [vp, ctypes.c_int]
     lib.lqmc_slice.argtypes = [vp, ctypes.c_int, vp, ctypes.c_uint64]
     lib.lqmc_wrap.argtypes = [vp, ctypes.c_int]
     lib.lqmc_sweep.argtypes = [vp, ctypes.c_int, vp, ctypes.c_uint64, ctypes.c_int]
@@ -119,7 +121,7 @@ class SweepEngine:
     """
 
     def __init__(self, exp_k, lamb, n_slices, n_chains=1, exp_k_inv=None, device=0, mode="parity",
-                 arith="exact", trace=False, chain_offset=0):
+                 arith="exact", trace=False, chain_offset=0, stab_every=0):
         self._lib = load_library()
         self._h = ctypes.c_void_p()
         exp_k = np.ascontiguousarray(exp_k, dtype=np.float64)
@@ -148,6 +150,9 @@ class SweepEngine:
                                           self.lamb, hs.ctypes.data_as(dp), flags))
         if chain_offset:
             self.set_chain_offset(chain_offset)
+        self.stab_every = 0
+        if stab_every:
+            self.set_stabilization(stab_every)
         self._last_trace_shape = None
 
     # -- plumbing ------------------------------------------------------------------------------
@@ -200,6 +205,15 @@ class SweepEngine:
     # -- phases --------------------------------------------------------------------------------
     def recompute(self, l0=0):
         self._check(self._lib.lqmc_recompute(self._h, int(l0)))
+
+    def recompute_stable(self, l0=0, chunk=8):
+        """QR/UDV-stabilised `G(l0) = inv(get_m(l0))`, `chunk` B factors per factorization."""
+        self._check(self._lib.lqmc_recompute_stable(self._h, int(l0), int(chunk)))
+
+    def set_stabilization(self, stab_every):
+        """Physics mode: rebuild G through `recompute_stable` every `stab_every` slices of a sweep (0 = off)."""
+        self._check(self._lib.lqmc_set_stabilization(self._h, int(stab_every)))
+        self.stab_every = int(stab_every)
 
     def slice(self, l, uniforms=None, seed=0):
         ptr = None

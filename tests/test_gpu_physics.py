@@ -64,3 +64,88 @@ def test_physics_mode_agrees_with_exact_diagonalisation():
     assert abs(docc - exact["docc"]) < 0.01 + 4 * err[2]
     moment = n_up + n_dn - 2 * docc
     assert abs(moment - exact["moment"]) < 0.02 + 8 * err.max()
+
+
+# ---- QR/UDV-stabilised recompute (north_star item 3) ----------------------------------------------------------------
+
+def _kin(kind, size, mu):
+    return so.ideal_square_kinetic(size, 1.0, mu) if kind == "square" else so.ideal_ring_kinetic(size, 1.0, mu)
+
+
+@pytest.mark.parametrize("case", [
+    # kind, size, U, beta, L, mu, l0, chunk
+    ("square", 2, 4.0, 2.0, 20, 0.0, 0, 8),          # N = 4: one ragged QR panel
+    ("square", 4, 4.0, 4.0, 40, 0.0, 7, 10),         # N = 16
+    ("square", 6, 6.0, 6.0, 60, 0.0, 59, 8),         # N = 36 (padded to 64), ill-conditioned product
+    ("ring", 64, 8.0, 8.0, 80, 0.0, 0, 10),          # BASELINE configs[2]: cond(prod B) ~ 1e24
+    ("ring", 64, 8.0, 8.0, 80, 4.0, 41, 10),         # same with the reference's diag(K) = -U/2 (H6)
+    ("square", 10, 4.0, 4.0, 40, 0.0, 3, 8),         # N = 100 (padded to 128)
+    ("square", 12, 4.0, 2.0, 20, 0.0, 19, 5),        # N = 144 (padded to 256)
+    ("square", 16, 4.0, 8.0, 80, 0.0, 0, 8),         # BASELINE configs[3] at true half filling
+])
+def test_stabilised_recompute_matches_oracle(case):
+    """`lqmc_recompute_stable` against the oracle's NumPy QR/UDV (`physics_g_stable`, same pre-pivoted scheme) and,
+    where the product is well conditioned, against the plain inverse."""
+    from latticeqmc_b200 import SweepEngine
+    kind, size, u, beta, lt, mu, l0, chunk = case
+    ham = _kin(kind, size, mu)
+    n = ham.shape[0]
+    dtau, lamb, exp_k = so.set_beta_constants(ham, u, beta, lt)
+    chains = 2
+    fields = np.stack([so.initial_field(n, lt, 700 + c) for c in range(chains)])
+    with SweepEngine(exp_k, lamb, lt, n_chains=chains, exp_k_inv=expm(dtau * ham), mode="physics") as eng:
+        eng.set_field(fields)
+        eng.recompute_stable(l0, chunk)
+        gg = eng.get_g()
+    for c in range(chains):
+        for si, sigma in enumerate((+1, -1)):
+            ref = so.physics_g_stable(fields[c], exp_k, lamb, l0, sigma, chunk)
+            err = np.abs(gg[c, si] - ref).max()
+            assert err < 1e-9, (case, c, sigma, err)
+            # a Green's function: diagonal inside [0, 1] up to roundoff
+            d = np.diag(gg[c, si])
+            assert d.min() > -1e-9 and d.max() < 1 + 1e-9
+    if beta <= 2.0:
+        naive = so.physics_g_naive(fields[0], exp_k, lamb, l0, +1)
+        assert np.abs(gg[0, 0] - naive).max() < 1e-9
+
+
+@pytest.mark.parametrize("case", [("square", 2, 4.0, 2.0, 20, 5, 3), ("square", 4, 4.0, 4.0, 40, 8, 2), ("ring", 64, 8.0, 8.0, 80, 10, 1)])
+def test_stabilised_physics_sweep_matches_oracle(case):
+    """Physics-mode sweeps with `stab_every`: G rebuilt by QR/UDV at the top of every segment, wraps inside.
+    Same decisions as the oracle's `physics_sweep(stab_every=k)` on the same uniforms, G(0) within 1e-8."""
+    from latticeqmc_b200 import SweepEngine
+    kind, size, u, beta, lt, k, chains = case
+    ham = _kin(kind, size, 0.0)
+    n = ham.shape[0]
+    dtau, lamb, exp_k = so.set_beta_constants(ham, u, beta, lt)
+    exp_k_inv = expm(dtau * ham)
+    fields = np.stack([so.initial_field(n, lt, 800 + c) for c in range(chains)])
+    sweeps = 2
+    uni = np.random.RandomState(9).rand(chains, sweeps, lt, n)
+    with SweepEngine(exp_k, lamb, lt, n_chains=chains, exp_k_inv=exp_k_inv, mode="physics", trace=True, stab_every=k) as eng:
+        eng.set_field(fields)
+        eng.sweep(sweeps, uni, measure=True)
+        acc, ratio = eng.get_trace()
+        gg, ff, m = eng.get_g(), eng.get_field(), eng.get_measurements()
+    for c in range(chains):
+        h = fields[c].copy()
+        for s in range(sweeps):
+            gu, gd, r, a = so.physics_sweep(h, exp_k, exp_k_inv, lamb, uni[c, s], stab_every=k)
+            # decisions can only differ where u sits within roundoff of the ratio
+            close_call = np.abs(uni[c, s] - r) < 1e-7
+            assert np.array_equal(a | close_call, acc[c, s] | close_call), (case, c, s)
+            assert np.allclose(r, ratio[c, s], rtol=1e-6, atol=1e-8)
+            assert np.all(r > -1e-9)
+        assert np.array_equal(h, ff[c])
+        assert np.abs(gg[c, 0] - gu).max() < 1e-8 and np.abs(gg[c, 1] - gd).max() < 1e-8
+        assert m["n_meas"][c] == sweeps
+
+
+def test_stabilisation_is_refused_in_parity_mode():
+    from latticeqmc_b200 import SweepEngine
+    ham = so.ideal_square_kinetic(2, 1.0, 2.0)
+    dtau, lamb, exp_k = so.set_beta_constants(ham, 4.0, 2.0, 20)
+    with SweepEngine(exp_k, lamb, 20) as eng:
+        with pytest.raises(ValueError):
+            eng.set_stabilization(5)
