@@ -67,7 +67,10 @@ struct lqmc_engine {
   struct Stab {
     bool ready = false;
     int NPs = 0, nfrag = 4, kd = 1;
-    double* X[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // [2C][NPs^2] work matrices
+    double* X[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // [2C][NPs^2] work matrices
+    // left stack of the two-sided scheme: UDV of C_j C_{j+1} ... C_{nseg-1} for every segment j
+    int stack_k = 0, nseg = 0;
+    double* stU = nullptr; double* stV = nullptr; double* stD = nullptr;   // [nseg][2C][NPs^2], [nseg][2C][NPs]
     double* dvec = nullptr;       // [2C][NPs]
     double* tfac = nullptr;       // [2C][NPs * ST_NB]
     int* perm = nullptr;          // [2C][NPs]
@@ -130,7 +133,7 @@ int launch_reg(lqmc_engine* e, const lqmc::SweepParams& p, cudaStream_t s) {
 // One entry for every phase combination: n_sweeps x [recompute?] + steps [step_lo, step_hi) x [propose?][wrap?]
 struct RunSpec {
   int n_sweeps = 1, step_lo = 0, step_hi = 0;
-  bool recompute = false, propose = false, wrap = false, measure = false, skip_last_wrap = false;
+  bool recompute = false, propose = false, wrap = false, measure = false, skip_last_wrap = false, wrap_first = false;
   int l0 = 0;
   const double* d_uniforms = nullptr;
   uint64_t seed = 0;
@@ -151,7 +154,7 @@ int run(lqmc_engine* e, const RunSpec& r, cudaStream_t s) {
   p.g_sum = e->dGsum; p.obs_sum = e->dObs; p.n_meas = e->dNmeas; p.n_acc = e->dNacc;
   p.n_sweeps = r.n_sweeps; p.step_lo = r.step_lo; p.step_hi = r.step_hi;
   p.do_recompute = r.recompute; p.do_propose = r.propose; p.do_wrap = r.wrap; p.measure = r.measure; p.recompute_l0 = r.l0;
-  p.skip_last_wrap = r.skip_last_wrap;
+  p.skip_last_wrap = r.skip_last_wrap; p.wrap_first = r.wrap_first;
   p.buf_sweeps = r.buf_sweeps >= 0 ? r.buf_sweeps : r.n_sweeps;
   p.buf_steps = r.buf_steps >= 0 ? r.buf_steps : (r.step_hi - r.step_lo);
   p.buf_sweep0 = r.buf_sweep0;
@@ -194,7 +197,7 @@ int stab_init(lqmc_engine* e) {
   st.NPs = lqmc::st_padded_size(e->N);
   st.nfrag = (st.NPs == 64) ? 2 : 4;
   const size_t nm = (size_t)2 * e->C, mat = (size_t)st.NPs * st.NPs;
-  for (int i = 0; i < 5; ++i)
+  for (int i = 0; i < 6; ++i)
     if (cudaMalloc(&st.X[i], nm * mat * sizeof(double)) != cudaSuccess)
       return fail(LQMC_ERR_NOMEM, "cudaMalloc of the stabilisation workspace failed (%zu bytes x 5)", nm * mat * sizeof(double));
   if (cudaMalloc(&st.dvec, nm * st.NPs * sizeof(double)) != cudaSuccess ||
@@ -227,13 +230,13 @@ int stab_init(lqmc_engine* e) {
     st.smem_inv = lqmc::l2_smem_bytes(st.NPs, kd, 1);
     rc |= set_smem(lqmc::st_chain_kernel<4>, st.smem_gemm);
     rc |= set_smem(lqmc::st_v_kernel<4>, st.smem_gemm);
-    rc |= set_smem(lqmc::st_final_kernel<4>, st.smem_gemm);
+    rc |= set_smem(lqmc::st_gemm_kernel<4>, st.smem_gemm);
     rc |= set_smem(lqmc::st_inverse_l2_kernel, st.smem_inv);
   } else {
     st.smem_inv = lqmc::RegCfg<64, 16, 8>::smem_bytes;
     rc |= set_smem(lqmc::st_chain_kernel<2>, st.smem_gemm);
     rc |= set_smem(lqmc::st_v_kernel<2>, st.smem_gemm);
-    rc |= set_smem(lqmc::st_final_kernel<2>, st.smem_gemm);
+    rc |= set_smem(lqmc::st_gemm_kernel<2>, st.smem_gemm);
     rc |= set_smem(lqmc::st_inverse_small_kernel, st.smem_inv);
   }
   rc |= set_smem(lqmc::st_qr_kernel<lqmc::ST_NB>, st.smem_qr);
@@ -244,7 +247,10 @@ int stab_init(lqmc_engine* e) {
 
 void stab_free(lqmc_engine* e) {
   auto& st = e->st;
-  for (int i = 0; i < 5; ++i) if (st.X[i]) cudaFree(st.X[i]);
+  for (int i = 0; i < 6; ++i) if (st.X[i]) cudaFree(st.X[i]);
+  if (st.stU) cudaFree(st.stU);
+  if (st.stV) cudaFree(st.stV);
+  if (st.stD) cudaFree(st.stD);
   if (st.dvec) cudaFree(st.dvec);
   if (st.tfac) cudaFree(st.tfac);
   if (st.perm) cudaFree(st.perm);
@@ -298,6 +304,29 @@ int stab_invert(lqmc_engine* e, double* M, cudaStream_t s) {
   return LQMC_OK;
 }
 
+struct GemmSpec {
+  const double* At = nullptr; const double* B = nullptr; double* out = nullptr;
+  const double* rvec = nullptr; int rmode = 0; const double* cvec = nullptr; int cmode = 0;
+  const double* addend = nullptr;
+  bool transposed_out = false;
+  double* G = nullptr;
+};
+
+int stab_gemm(lqmc_engine* e, const GemmSpec& g, cudaStream_t s) {
+  auto& st = e->st;
+  const size_t mat = (size_t)st.NPs * st.NPs;
+  lqmc::StGemmArgs a;
+  a.At = g.At; a.at_stride = mat; a.B = g.B; a.b_stride = mat; a.out = g.out; a.out_stride = mat;
+  a.rvec = g.rvec; a.rvec_stride = st.NPs; a.rmode = g.rmode; a.cvec = g.cvec; a.cvec_stride = st.NPs; a.cmode = g.cmode;
+  a.addend = g.addend; a.addend_stride = mat; a.G = g.G;
+  a.N = e->N; a.NPs = st.NPs; a.NPg = e->NP; a.transposed_out = g.transposed_out ? 1 : 0; a.hc = hs_consts(e);
+  if (st.nfrag == 4) lqmc::st_gemm_kernel<4><<<2 * e->C, lqmc::ST_THREADS, st.smem_gemm, s>>>(a);
+  else lqmc::st_gemm_kernel<2><<<2 * e->C, lqmc::ST_THREADS, st.smem_gemm, s>>>(a);
+  CU(cudaGetLastError());
+  e->launches += 1;
+  return LQMC_OK;
+}
+
 // G(l0) = inv(I + B_{l0-1} ... B_0 B_{L-1} ... B_{l0}) from scratch, `chunk` factors per QR (one-sided UDV)
 int stab_recompute_scratch(lqmc_engine* e, int l0, int chunk, cudaStream_t s) {
   int rc = stab_init(e);
@@ -327,13 +356,144 @@ int stab_recompute_scratch(lqmc_engine* e, int l0, int chunk, cudaStream_t s) {
   e->launches += 1;
   rc = stab_invert(e, st.X[0], s);
   if (rc) return rc;
-  lqmc::StFinalArgs ga;
-  ga.At = st.X[1]; ga.B = st.X[0]; ga.rvec = nullptr; ga.rvec_stride = 0; ga.scratch = Vnext; ga.G = e->dG;
-  ga.N = e->N; ga.NPs = st.NPs; ga.NPg = e->NP; ga.transposed_out = 1; ga.hc = hs_consts(e);
-  if (st.nfrag == 4) lqmc::st_final_kernel<4><<<grid, lqmc::ST_THREADS, st.smem_gemm, s>>>(ga);
-  else lqmc::st_final_kernel<2><<<grid, lqmc::ST_THREADS, st.smem_gemm, s>>>(ga);
+  GemmSpec g;
+  g.At = st.X[1]; g.B = st.X[0]; g.out = Vnext; g.transposed_out = true; g.G = e->dG;
+  return stab_gemm(e, g, s);
+}
+
+// ---- two-sided scheme: left stack + running right product ------------------------------------------------------------
+// Segment j (j = 0 .. nseg-1) covers slices [lo_j, hi_j], hi_j = L-1 - j k, visited in this order by the sweep.
+// C_j = B_{hi_j} ... B_{lo_j}.  At the top of segment j the sweep needs
+//     G(hi_j + 1) = inv(I + Left_j Right_j),   Left_j = C_j ... C_{nseg-1} (not yet updated),  Right_j = C_0 ... C_{j-1},
+// which the sweep kernel wraps down to G(hi_j).  Left_j = U_L D_L V_L comes from the stack built at the sweep start;
+// Right_j^T = U_R D_R V_R grows by one transposed chunk per segment.  With D = D_b D_s split at 1,
+//     G = U_R D_Rb^-1 [ D_Lb^-1 (U_L^T U_R) D_Rb^-1 + D_Ls (V_L V_R^T) D_Rs ]^-1 D_Lb^-1 U_L^T.
+void seg_bounds(const lqmc_engine* e, int j, int* lo, int* hi) {
+  const int k = e->stab_every;
+  *hi = e->L - 1 - j * k;
+  *lo = (e->L - (j + 1) * k > 0) ? e->L - (j + 1) * k : 0;
+}
+
+int stab_stack_alloc(lqmc_engine* e) {
+  auto& st = e->st;
+  int rc = stab_init(e);
+  if (rc) return rc;
+  const int k = e->stab_every, nseg = (e->L + k - 1) / k;
+  if (st.stack_k == k && st.stU) return LQMC_OK;
+  if (st.stU) { cudaFree(st.stU); cudaFree(st.stV); cudaFree(st.stD); st.stU = st.stV = st.stD = nullptr; }
+  const size_t nm = (size_t)2 * e->C, mat = (size_t)st.NPs * st.NPs;
+  if (cudaMalloc(&st.stU, nseg * nm * mat * sizeof(double)) != cudaSuccess || cudaMalloc(&st.stV, nseg * nm * mat * sizeof(double)) != cudaSuccess ||
+      cudaMalloc(&st.stD, nseg * nm * st.NPs * sizeof(double)) != cudaSuccess)
+    return fail(LQMC_ERR_NOMEM, "cudaMalloc of the UDV stack failed (%d segments x %zu bytes x 2)", nseg, nm * mat * sizeof(double));
+  st.stack_k = k; st.nseg = nseg;
+  return LQMC_OK;
+}
+
+int stab_build_left_stack(lqmc_engine* e, cudaStream_t s) {
+  auto& st = e->st;
+  const size_t nm = (size_t)2 * e->C, mat = (size_t)st.NPs * st.NPs;
+  for (int j = st.nseg - 1; j >= 0; --j) {
+    int lo, hi;
+    seg_bounds(e, j, &lo, &hi);
+    const bool first = (j == st.nseg - 1);
+    const double* Uprev = first ? nullptr : st.stU + (size_t)(j + 1) * nm * mat;
+    const double* Dprev = first ? nullptr : st.stD + (size_t)(j + 1) * nm * st.NPs;
+    const double* Vprev = first ? nullptr : st.stV + (size_t)(j + 1) * nm * mat;
+    int rc = stab_absorb(e, Uprev, mat, Dprev, st.NPs, Vprev, mat, lo, +1, hi - lo + 1, false, st.stU + (size_t)j * nm * mat, mat,
+                         st.stD + (size_t)j * nm * st.NPs, st.NPs, st.stV + (size_t)j * nm * mat, mat, s);
+    if (rc) return rc;
+  }
+  return LQMC_OK;
+}
+
+// state of the running right product: U_R = X[2], D_R = dvec, V_R = X[3] / X[4] (ping-pong)
+struct RightState { double* U; double* V; double* Vother; bool empty; };
+
+int stab_transpose(lqmc_engine* e, const double* in, double* out, const double* vec, int mode, cudaStream_t s) {
+  auto& st = e->st;
+  const size_t mat = (size_t)st.NPs * st.NPs;
+  lqmc::StTransposeArgs ta;
+  ta.in = in; ta.in_stride = mat; ta.out = out; ta.out_stride = mat; ta.vec = vec; ta.vec_stride = st.NPs; ta.mode = mode; ta.NPs = st.NPs;
+  lqmc::st_transpose_kernel<<<2 * e->C, lqmc::ST_THREADS, 0, s>>>(ta);
   CU(cudaGetLastError());
   e->launches += 1;
+  return LQMC_OK;
+}
+
+// G(hi_j + 1) from stack entry j and the right state, into the sweep kernels' G
+int stab_combine(lqmc_engine* e, int j, const RightState& R, cudaStream_t s) {
+  auto& st = e->st;
+  const size_t nm = (size_t)2 * e->C, mat = (size_t)st.NPs * st.NPs;
+  const double* UL = st.stU + (size_t)j * nm * mat;
+  const double* VL = st.stV + (size_t)j * nm * mat;
+  const double* DL = st.stD + (size_t)j * nm * st.NPs;
+  const double* DR = st.dvec;
+  double* inner = st.X[0];
+  double* S1 = st.X[1];
+  double* S2 = st.X[5];
+  int rc;
+  // innerT = D_Rb^-1 (U_R^T U_L) D_Lb^-1
+  GemmSpec g;
+  g.At = R.U; g.B = UL; g.out = inner; g.rvec = DR; g.rmode = lqmc::ST_VEC_INV_BIG; g.cvec = DL; g.cmode = lqmc::ST_VEC_INV_BIG;
+  if ((rc = stab_gemm(e, g, s))) return rc;
+  // innerT += (D_Ls (V_L V_R^T) D_Rs)^T
+  if ((rc = stab_transpose(e, VL, S1, nullptr, 0, s))) return rc;
+  if ((rc = stab_transpose(e, R.V, S2, nullptr, 0, s))) return rc;
+  g = GemmSpec();
+  g.At = S1; g.B = S2; g.out = inner; g.transposed_out = true; g.addend = inner;
+  g.rvec = DL; g.rmode = lqmc::ST_VEC_SMALL; g.cvec = DR; g.cmode = lqmc::ST_VEC_SMALL;
+  if ((rc = stab_gemm(e, g, s))) return rc;
+  // W^T = inv(innerT)
+  if ((rc = stab_invert(e, inner, s))) return rc;
+  // Z = W (D_Lb^-1 U_L^T)
+  if ((rc = stab_transpose(e, UL, S1, DL, lqmc::ST_VEC_INV_BIG, s))) return rc;
+  g = GemmSpec();
+  g.At = inner; g.B = S1; g.out = S2;
+  if ((rc = stab_gemm(e, g, s))) return rc;
+  // G^T = Z^T (D_Rb^-1 U_R^T)
+  if ((rc = stab_transpose(e, R.U, S1, DR, lqmc::ST_VEC_INV_BIG, s))) return rc;
+  g = GemmSpec();
+  g.At = S2; g.B = S1; g.out = inner; g.transposed_out = true; g.G = e->dG;
+  return stab_gemm(e, g, s);
+}
+
+int stab_sweeps(lqmc_engine* e, int n_sweeps, const double* d_uniforms, uint64_t seed, bool measure, cudaStream_t s) {
+  int rc = stab_stack_alloc(e);
+  if (rc) return rc;
+  auto& st = e->st;
+  const size_t mat = (size_t)st.NPs * st.NPs;
+  rc = ensure_trace(e, (size_t)e->C * n_sweeps * e->L * e->N);
+  if (rc) return rc;
+  const int k = e->stab_every;
+  for (int sw = 0; sw < n_sweeps; ++sw) {
+    rc = stab_build_left_stack(e, s);
+    if (rc) return rc;
+    RightState R{st.X[2], st.X[3], st.X[4], true};
+    lqmc::StIdentityArgs ia;
+    ia.M0 = R.U; ia.M1 = R.V; ia.d = st.dvec; ia.NPs = st.NPs;
+    lqmc::st_identity_kernel<<<2 * e->C, lqmc::ST_THREADS, 0, s>>>(ia);
+    e->launches += 1;
+    for (int j = 0; j < st.nseg; ++j) {
+      if (j > 0) {
+        int lo, hi;
+        seg_bounds(e, j - 1, &lo, &hi);
+        rc = stab_absorb(e, R.U, mat, st.dvec, st.NPs, R.V, mat, hi, -1, hi - lo + 1, true, R.U, mat, st.dvec, st.NPs, R.Vother, mat, s);
+        if (rc) return rc;
+        double* t = R.V; R.V = R.Vother; R.Vother = t;
+      }
+      rc = stab_combine(e, j, R, s);
+      if (rc) return rc;
+      RunSpec r;
+      r.step_lo = j * k; r.step_hi = (j + 1) * k < e->L ? (j + 1) * k : e->L;
+      r.propose = true; r.wrap = true; r.skip_last_wrap = true; r.wrap_first = true;
+      r.measure = measure && r.step_hi == e->L;
+      r.d_uniforms = d_uniforms; r.seed = seed; r.sweep0 = e->sweep_counter + sw;
+      r.buf_sweeps = n_sweeps; r.buf_steps = e->L; r.buf_sweep0 = sw; r.buf_step0 = 0; r.keep_trace_extent = true;
+      rc = run(e, r, s);
+      if (rc) return rc;
+    }
+  }
+  e->sweep_counter += n_sweeps;
   return LQMC_OK;
 }
 
@@ -547,26 +707,10 @@ int lqmc_sweep_async(lqmc_engine* e, int n_sweeps, const double* d_uniforms, uin
   cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
   const bool phys = (e->flags & LQMC_MODE_PHYSICS) != 0;
   if (phys && e->stab_every > 0) {
-    // stabilised schedule: G is rebuilt from the field (QR/UDV) at the top of every segment of stab_every slices and
-    // propagated by wraps inside it; one sweep = ceil(L / stab_every) x (stabilisation kernels + one sweep-kernel launch)
+    // stabilised schedule (stab.cuh): G is rebuilt from the field by QR/UDV at the top of every segment of stab_every
+    // slices and propagated by wraps inside it
     CU(cudaSetDevice(e->device));
-    int rc = ensure_trace(e, (size_t)e->C * n_sweeps * e->L * e->N);
-    if (rc) return rc;
-    for (int sw = 0; sw < n_sweeps; ++sw)
-      for (int lo = 0; lo < e->L; lo += e->stab_every) {
-        const int hi = (lo + e->stab_every < e->L) ? lo + e->stab_every : e->L;
-        rc = stab_recompute_scratch(e, e->L - 1 - lo, e->stab_every, s);
-        if (rc) return rc;
-        RunSpec r;
-        r.step_lo = lo; r.step_hi = hi; r.propose = true; r.wrap = true; r.skip_last_wrap = true;
-        r.measure = (measure != 0) && hi == e->L;
-        r.d_uniforms = d_uniforms; r.seed = seed; r.sweep0 = e->sweep_counter + sw;
-        r.buf_sweeps = n_sweeps; r.buf_steps = e->L; r.buf_sweep0 = sw; r.buf_step0 = 0; r.keep_trace_extent = true;
-        rc = run(e, r, s);
-        if (rc) return rc;
-      }
-    e->sweep_counter += n_sweeps;
-    return LQMC_OK;
+    return stab_sweeps(e, n_sweeps, d_uniforms, seed, measure != 0, s);
   }
   RunSpec r;
   r.n_sweeps = n_sweeps; r.step_lo = 0; r.step_hi = e->L; r.recompute = true; r.propose = true; r.wrap = true;

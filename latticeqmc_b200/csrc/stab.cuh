@@ -39,11 +39,21 @@ __device__ __forceinline__ double st_hs(int8_t h, int spin, bool inv, const HsCo
 inline int st_padded_size(int n_sites) { return n_sites <= 64 ? 64 : (n_sites + 127) / 128 * 128; }
 
 // ---- GEMM  C = A * B,  A given k-major, B row-major (rows optionally gathered through bperm) ----------------------
+// how a scale vector enters: the value itself, 1 / max(v, 1)  (D_b^-1)  or  min(v, 1)  (D_s)
+enum { ST_VEC_PLAIN = 0, ST_VEC_INV_BIG = 1, ST_VEC_SMALL = 2 };
+__device__ __forceinline__ double st_vscale(double v, int mode) {
+  if (mode == ST_VEC_INV_BIG) return 1.0 / fmax(v, 1.0);
+  if (mode == ST_VEC_SMALL) return fmin(v, 1.0);
+  return v;
+}
+
 struct StEpilogue {
   const int8_t* hrow = nullptr;   // row scale exp(-+sigma lamb h[row]) for row < nvalid
   bool row_inv = false;
-  const double* rvec = nullptr;   // row scale by a vector
+  const double* rvec = nullptr;   // row scale by a vector (of the product A*B, whatever the store layout)
   const double* cvec = nullptr;   // column scale by a vector
+  int rmode = ST_VEC_PLAIN, cmode = ST_VEC_PLAIN;
+  const double* addend = nullptr; // added element-wise, indexed like the output (may be the output itself)
   bool transposed_out = false;
   int nvalid = 0;
 };
@@ -115,15 +125,17 @@ __device__ void st_gemm(const double* __restrict__ At, const double* __restrict_
         const int row = i0 + 32 * wm + 8 * m + lr;
         double rs = 1.0;
         if (ep.hrow && row < ep.nvalid) rs = st_hs(ep.hrow[row], spin, ep.row_inv, hc);
-        if (ep.rvec) rs *= ep.rvec[row];
+        if (ep.rvec) rs *= st_vscale(ep.rvec[row], ep.rmode);
 #pragma unroll
         for (int n = 0; n < NFRAG; ++n) {
           const int col0 = j0 + 8 * NFRAG * wn + 8 * n + 2 * lk;
           double v0 = acc[m][n][0] * rs, v1 = acc[m][n][1] * rs;
-          if (ep.cvec) { v0 *= ep.cvec[col0]; v1 *= ep.cvec[col0 + 1]; }
+          if (ep.cvec) { v0 *= st_vscale(ep.cvec[col0], ep.cmode); v1 *= st_vscale(ep.cvec[col0 + 1], ep.cmode); }
           if (!ep.transposed_out) {
+            if (ep.addend) { v0 += ep.addend[(size_t)row * NP + col0]; v1 += ep.addend[(size_t)row * NP + col0 + 1]; }
             *reinterpret_cast<double2*>(Cout + (size_t)row * NP + col0) = make_double2(v0, v1);
           } else {
+            if (ep.addend) { v0 += ep.addend[(size_t)col0 * NP + row]; v1 += ep.addend[(size_t)(col0 + 1) * NP + row]; }
             Cout[(size_t)col0 * NP + row] = v0;
             Cout[(size_t)(col0 + 1) * NP + row] = v1;
           }
@@ -561,32 +573,71 @@ __global__ void __launch_bounds__(128) st_inverse_small_kernel(const StInvArgs a
   for (int q = t; q < 64 * 64; q += 128) M[q] = sm.stage[(q >> 6) * C::S + (q & 63)];
 }
 
-// G^T = rhs^T-as-k-major * W, written transposed into a scratch matrix, then copied into the sweep kernels' G
-struct StFinalArgs {
-  const double* At;      // [2C][NPs^2] k-major left operand
-  const double* B;       // [2C][NPs^2]
-  const double* rvec; size_t rvec_stride;   // optional row scale of the product (row index of A*B)
-  double* scratch;       // [2C][NPs^2]
-  double* G;             // [chain][2][NPg][NPg]
+// ---- generic batched GEMM and transpose kernels for the combination formulas -----------------------------------------
+struct StGemmArgs {
+  const double* At; size_t at_stride;       // k-major left operand
+  const double* B; size_t b_stride;
+  double* out; size_t out_stride;
+  const double* rvec; size_t rvec_stride; int rmode;
+  const double* cvec; size_t cvec_stride; int cmode;
+  const double* addend; size_t addend_stride;
+  double* G;             // optional: copy the leading N x N block of the result into [2C][NPg][NPg]
   int N, NPs, NPg, transposed_out;
   HsConsts hc;
 };
 
 template <int NFRAG>
-__global__ void __launch_bounds__(ST_THREADS) st_final_kernel(const StFinalArgs a) {
+__global__ void __launch_bounds__(ST_THREADS) st_gemm_kernel(const StGemmArgs a) {
   extern __shared__ __align__(16) unsigned char st_smem[];
   double* pa = reinterpret_cast<double*>(st_smem);
   double* pb = pa + ST_STAGES * ST_BK * ST_LDA;
   const int m = blockIdx.x, NP = a.NPs;
-  double* scratch = a.scratch + (size_t)m * NP * NP;
+  double* out = a.out + (size_t)m * a.out_stride;
   StEpilogue ep;
   ep.transposed_out = a.transposed_out != 0;
-  if (a.rvec) ep.rvec = a.rvec + (size_t)m * a.rvec_stride;
-  st_gemm<NFRAG>(a.At + (size_t)m * NP * NP, a.B + (size_t)m * NP * NP, nullptr, scratch, NP, m & 1, ep, a.hc, pa, pb);
-  double* G = a.G + (size_t)m * a.NPg * a.NPg;
+  if (a.rvec) { ep.rvec = a.rvec + (size_t)m * a.rvec_stride; ep.rmode = a.rmode; }
+  if (a.cvec) { ep.cvec = a.cvec + (size_t)m * a.cvec_stride; ep.cmode = a.cmode; }
+  if (a.addend) ep.addend = a.addend + (size_t)m * a.addend_stride;
+  st_gemm<NFRAG>(a.At + (size_t)m * a.at_stride, a.B + (size_t)m * a.b_stride, nullptr, out, NP, m & 1, ep, a.hc, pa, pb);
+  if (a.G) {
+    double* G = a.G + (size_t)m * a.NPg * a.NPg;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int r = warp; r < a.N; r += ST_THREADS / 32)
+      for (int c = lane; c < a.N; c += 32) G[(size_t)r * a.NPg + c] = out[(size_t)r * NP + c];
+  }
+}
+
+// out[k][i] = in[i][k] * scale(vec[k])   (vec optional)
+struct StTransposeArgs {
+  const double* in; size_t in_stride;
+  double* out; size_t out_stride;
+  const double* vec; size_t vec_stride; int mode;
+  int NPs;
+};
+
+__global__ void __launch_bounds__(ST_THREADS) st_transpose_kernel(const StTransposeArgs a) {
+  __shared__ double tile[32 * 33];
+  const int m = blockIdx.x;
+  const double* vec = a.vec ? a.vec + (size_t)m * a.vec_stride : nullptr;
+  const int mode = a.mode;
+  st_transpose_map(a.in + (size_t)m * a.in_stride, a.out + (size_t)m * a.out_stride, a.NPs, tile,
+                   [&](double x, int i, int k) { return vec ? x * st_vscale(vec[k], mode) : x; });
+}
+
+// identity matrices / unit vectors for the empty right product
+struct StIdentityArgs { double* M0; double* M1; double* d; int NPs; };
+__global__ void __launch_bounds__(ST_THREADS) st_identity_kernel(const StIdentityArgs a) {
+  const int m = blockIdx.x, NP = a.NPs;
+  double* M0 = a.M0 + (size_t)m * NP * NP;
+  double* M1 = a.M1 ? a.M1 + (size_t)m * NP * NP : nullptr;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int r = warp; r < a.N; r += ST_THREADS / 32)
-    for (int c = lane; c < a.N; c += 32) G[(size_t)r * a.NPg + c] = scratch[(size_t)r * NP + c];
+  for (int r = warp; r < NP; r += ST_THREADS / 32)
+    for (int c = lane; c < NP; c += 32) {
+      const double v = (r == c) ? 1.0 : 0.0;
+      M0[(size_t)r * NP + c] = v;
+      if (M1) M1[(size_t)r * NP + c] = v;
+    }
+  if (a.d) for (int j = threadIdx.x; j < NP; j += ST_THREADS) a.d[(size_t)m * NP + j] = 1.0;
 }
 
 }  // namespace lqmc

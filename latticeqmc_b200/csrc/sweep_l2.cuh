@@ -724,6 +724,10 @@ __global__ void __launch_bounds__(L2_THREADS, 2) sweep_l2_kernel(const L2Params 
     for (int step = p.step_lo; step < p.step_hi; ++step) {
       const int l = L - 1 - step;
       const long long base = (((long long)chain * p.buf_sweeps + p.buf_sweep0 + sweep) * p.buf_steps + (step - p.buf_step0)) * N;
+      if (p.wrap_first && step == p.step_lo) {
+        __syncthreads();
+        l2_wrap<PHYS>(Gc, Tc, NP, field + (size_t)l * NP, p, sm);
+      }
       if (p.do_propose) {
         __syncthreads();
         for (int j = tid; j < NP; j += L2_THREADS) {

@@ -56,6 +56,7 @@ struct SweepParams {
   uint8_t* tr_acc;
   int n_sweeps, step_lo, step_hi;
   int do_recompute, do_propose, do_wrap, measure, recompute_l0;
+  int wrap_first;       // G arrives one slice above step_lo's (stabilised G(l+1)): wrap it down before the first proposals
   int skip_last_wrap;   // no wrap after step_hi-1 (the caller recomputes G for the next slice: stabilised segments)
   // indexing of the uniforms / trace buffers [chain][buf_sweeps][buf_steps][N]: this launch's sweep s and step t sit at
   // sweep index buf_sweep0 + s and step index t - buf_step0 (a segmented sweep is several launches over one buffer)
@@ -522,6 +523,11 @@ __global__ void __launch_bounds__(C::THREADS, (C::THREADS == 256) ? 2 : 4) sweep
     for (int step = p.step_lo; step < p.step_hi; ++step) {
       const int l = L - 1 - step;
       const long long base = (((long long)chain * p.buf_sweeps + p.buf_sweep0 + sweep) * p.buf_steps + (step - p.buf_step0)) * N;
+      if (p.wrap_first && step == p.step_lo) {
+        __syncthreads();
+        if (tid < NP) sm.hn[tid] = field[l * NP + tid];
+        wrap_g<C, PHYS>(g, sm, p, spin, ty, tx);
+      }
       if (p.do_propose) {
         __syncthreads();             // previous users of sm.u / sm.h are done
         if (tid < NP) {

@@ -8,7 +8,7 @@ from latticeqmc_b200 import SweepEngine
 
 cases = [("square", 2, 4.0, 2.0, 20, 0.0, 0, 8), ("square", 4, 4.0, 4.0, 40, 0.0, 7, 10), ("square", 6, 6.0, 6.0, 60, 0.0, 59, 8),
          ("ring", 64, 8.0, 8.0, 80, 0.0, 0, 10), ("square", 10, 4.0, 4.0, 40, 0.0, 3, 8), ("square", 12, 4.0, 2.0, 20, 0.0, 19, 5),
-         ("square", 16, 4.0, 8.0, 80, 0.0, 0, 8)]
+         ("square", 16, 4.0, 8.0, 80, 0.0, 0, 8), ("ring", 64, 8.0, 8.0, 80, 4.0, 41, 10), ("ring", 64, 8.0, 8.0, 80, 4.0, 41, 5)]
 if len(sys.argv) > 1:
     cases = [cases[int(a)] for a in sys.argv[1:]]
 for case in cases:
@@ -29,6 +29,7 @@ for case in cases:
             for si, sigma in enumerate((+1, -1)):
                 ref = so.physics_g_stable(fields[c], exp_k, lamb, l0, sigma, chunk)
                 errs.append(float(np.abs(gg[c, si] - ref).max()))
+        print("  max|G|", float(np.abs(gg).max()), "max|ref|", float(np.abs(ref).max()))
         print(case, "N", n, "errs", ["%.2e" % e for e in errs], "nan", int(np.isnan(gg).sum()), "t %.3fs" % dt, flush=True)
     except Exception as ex:
         print(case, "FAILED", repr(ex), flush=True)
