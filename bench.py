@@ -43,10 +43,10 @@ METRIC = "HS spin-flip updates/sec"
 UNIT = "proposals/s"
 
 
-def build_workload(name):
+def build_workload(name, mu=None):
     from latticeqmc_b200.workloads import kinetic_and_constants
     kind, size, u, beta, lt, chains, text = WORKLOADS[name]
-    ham, dtau, lamb, exp_k, exp_k_inv = kinetic_and_constants(kind, size, u, beta, lt)
+    ham, dtau, lamb, exp_k, exp_k_inv = kinetic_and_constants(kind, size, u, beta, lt, mu=mu)
     return dict(name=name, text=text, ham=ham, n=ham.shape[0], lt=lt, u=u, beta=beta, lamb=lamb, exp_k=exp_k,
                 exp_k_inv=exp_k_inv, chains=chains)
 
@@ -56,6 +56,17 @@ def flops_per_sweep(n, lt, accept):
     DESIGN.md): rank-1 4N^2 per accepted flip (2 spins), wrap 8N^3 per slice but the last,
     sweep-start product 2 spins x L GEMMs x 2N^3 plus the inverse 2 x 2N^3."""
     return accept * n * lt * 4.0 * n * n + (lt - 1) * 8.0 * n ** 3 + 2.0 * (lt * 2.0 * n ** 3 + 2.0 * n ** 3)
+
+
+def flops_per_sweep_physics(n, lt, accept, stab):
+    """ALGORITHMIC FP64 flops of one stabilised physics-mode sweep of one chain: rank-1 updates,
+    one wrap per slice, the left UDV stack (L chain GEMMs + one QR / Q / V-GEMM per segment), the running right
+    product (the same minus the last segment) and one combination (4 GEMMs + inverse) per segment; both spins."""
+    nseg = -(-lt // stab)
+    len_last = lt - (nseg - 1) * stab
+    qr_block = (4.0 / 3 + 4.0 / 3 + 2.0) * n ** 3
+    per_spin = (2 * lt - len_last) * 2.0 * n ** 3 + (2 * nseg - 1) * qr_block + nseg * 10.0 * n ** 3
+    return accept * n * lt * 4.0 * n * n + lt * 8.0 * n ** 3 + 2.0 * per_spin
 
 
 # ------------------------------------------------------------------------------------------------
@@ -244,13 +255,15 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
 
-    w = build_workload(args.workload)
+    physics = args.mode == "physics"
+    w = build_workload(args.workload, mu=0.0 if physics else None)
     n, lt = w["n"], w["lt"]
     chains = args.chains or w["chains"]
     from latticeqmc_b200.workloads import synthetic_fields
     fields = synthetic_fields(n, lt, chains, seed0=rank * chains)
     eng = SweepEngine(w["exp_k"], w["lamb"], lt, n_chains=chains, exp_k_inv=w["exp_k_inv"], device=local,
-                      mode="parity", arith=args.arith, chain_offset=rank * chains)
+                      mode=args.mode, arith=args.arith, chain_offset=rank * chains,
+                      stab_every=args.stab if physics else 0)
     eng.set_field(fields)
     stream = torch.cuda.Stream(dev)          # a real (non-default) stream: its handle goes to the C ABI, events see it
     torch.cuda.set_stream(stream)
@@ -334,7 +347,8 @@ def run_ours(args):
         proposals_per_step = world * chains * n * lt
         value = proposals_per_step * args.steps / (total_ms * 1e-3)
         e2e_value = proposals_per_step * args.steps / e2e_s
-        flops = flops_per_sweep(n, lt, accept) * chains            # per launch (one rank)
+        flops = (flops_per_sweep_physics(n, lt, accept, args.stab) if physics and args.stab
+                 else flops_per_sweep(n, lt, accept)) * chains            # per step (one rank)
         kernel_ms = total_ms / args.steps
         peaks = load_peaks()
         achieved = flops / (kernel_ms * 1e-3) * 1e-12
@@ -343,7 +357,8 @@ def run_ours(args):
             metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
             ms_per_step=kernel_ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
             config=dict(workload=args.workload, description=w["text"], n_sites=n, n_slices=lt, chains_per_gpu=chains,
-                        chains_total=world * chains, mode="parity", arith=args.arith, rng="device philox4x32-10",
+                        chains_total=world * chains, mode=args.mode, stab_every=args.stab if physics else 0,
+                        arith=args.arith, rng="device philox4x32-10",
                         kernel_family=info["family"], l2="flushed between timed steps (256 MiB memset, untimed)",
                         parallelism=f"chains sharded over {world} GPU(s), no collective in the sweep"),
             accept_rate=accept, accepted_flips_per_s=value * accept,
@@ -415,6 +430,9 @@ def main():
                     help="default cfg4 = the 16x16, beta=8 configuration north_star quotes the metric on")
     ap.add_argument("--chains", type=int, default=0, help="chains per GPU (default: the workload's)")
     ap.add_argument("--arith", default="exact", choices=["exact", "fma"])
+    ap.add_argument("--mode", default="parity", choices=["parity", "physics"],
+                    help="parity = the reference recurrence (headline); physics = textbook DQMC at true half filling")
+    ap.add_argument("--stab", type=int, default=0, help="physics mode: QR/UDV stabilisation every this many slices")
     ap.add_argument("--seed", type=int, default=20260101)
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")

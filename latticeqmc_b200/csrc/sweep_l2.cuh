@@ -400,6 +400,7 @@ __device__ void l2_propose_slice(double* __restrict__ Gc, int NP, int KD, L2Smem
   int i0 = 0;
 #ifdef LQMC_PHASE_CLOCKS
   long long tk_scan = 0, tk_build = 0, tk_flush = 0, tk0 = clock64();
+  long long tk_b1 = 0, tk_b2 = 0, tk_b3 = 0;     // build split: global loads landed / pending updates applied / vectors written
 #endif
   int cur = 0;                  // diagonal buffer the scan reads; a flip writes the other one (slower warps may still be scanning)
   while (i0 < N) {
@@ -449,6 +450,11 @@ __device__ void l2_propose_slice(double* __restrict__ Gc, int NP, int KD, L2Smem
         if (j < NP) { row2[spin][q] = G[(size_t)is * NP + j]; col2[spin][q] = G[(size_t)j * NP + is]; }
       }
     }
+#ifdef LQMC_PHASE_CLOCKS
+    { double chk = row2[0][0] + col2[0][0] + row2[1][0] + col2[1][0]; if (chk == 1.2345e300) tk_b1 -= 1;   // wait for the loads
+      const long long tk1 = clock64(); tk_b1 += tk1 - tk0; }
+    long long tkb = clock64();
+#endif
 #pragma unroll
     for (int spin = 0; spin < 2; ++spin) {
       const double* U = sm.U + (size_t)spin * KD * NP;
@@ -467,6 +473,9 @@ __device__ void l2_propose_slice(double* __restrict__ Gc, int NP, int KD, L2Smem
           }
         }
       }
+#ifdef LQMC_PHASE_CLOCKS
+      { double chk = row[0] + col[0]; if (chk == 1.2345e300) tk_b2 -= 1; const long long tk1 = clock64(); tk_b2 += tk1 - tkb; tkb = tk1; }
+#endif
       double* Un = sm.U + ((size_t)spin * KD + nd) * NP;
       double* Wn = sm.W + ((size_t)spin * KD + nd) * NP;
       if (!PHYS) {
@@ -502,6 +511,9 @@ __device__ void l2_propose_slice(double* __restrict__ Gc, int NP, int KD, L2Smem
         }
       }
     }
+#ifdef LQMC_PHASE_CLOCKS
+    { const long long tk1 = clock64(); tk_b3 += tk1 - tkb; }
+#endif
     ++n_accepted;
     ++nd;
     cur ^= 1;
@@ -519,7 +531,7 @@ __device__ void l2_propose_slice(double* __restrict__ Gc, int NP, int KD, L2Smem
   if (nd > 0) l2_flush<EXACT>(Gc, NP, nd, sm, KD);
 #ifdef LQMC_PHASE_CLOCKS
   { const long long tk1 = clock64(); tk_flush += tk1 - tk0;
-    if (tid == 0) { double* ob = p.obs_sum + (size_t)blockIdx.x * 3 * N; ob[0] = (double)tk_scan; ob[1] = (double)tk_build; ob[2] = (double)tk_flush; ob[3] = (double)n_accepted; } }
+    if (tid == 0) { double* ob = p.obs_sum + (size_t)blockIdx.x * 3 * N; ob[0] = (double)tk_scan; ob[1] = (double)tk_build; ob[2] = (double)tk_flush; ob[3] = (double)n_accepted; ob[4] = (double)tk_b1; ob[5] = (double)tk_b2; ob[6] = (double)tk_b3; } }
 #endif
 }
 

@@ -8,9 +8,11 @@ from scipy.linalg import expm
 from .hubbard import HubbardModel
 
 
-def build_model(kind, size, u, t=1.0):
-    """`kind`: 'square' (size x size, periodic in both directions) or 'ring' (size sites)."""
-    model = HubbardModel(u=u, t=t)
+def build_model(kind, size, u, t=1.0, mu=None):
+    """`kind`: 'square' (size x size, periodic in both directions) or 'ring' (size sites).  `mu=None` keeps the
+    reference default mu = U/2 on the diagonal of K (hubbard.py:30,99-100); physics-mode workloads pass mu = 0,
+    which is true half filling in the reference's HS convention."""
+    model = HubbardModel(u=u, t=t, mu=mu)
     if kind == "square":
         model.build_square(size)
     elif kind == "ring":
@@ -20,9 +22,9 @@ def build_model(kind, size, u, t=1.0):
     return model
 
 
-def kinetic_and_constants(kind, size, u, beta, time_steps):
+def kinetic_and_constants(kind, size, u, beta, time_steps, mu=None):
     """`(K, dtau, lamb, exp_k, exp_k_inv)` the way `LatticeQMC.set_beta` derives them (lqmc.py:102-106)."""
-    ham = build_model(kind, size, u).ham_kinetic()
+    ham = build_model(kind, size, u, mu=mu).ham_kinetic()
     dtau = beta / time_steps
     lamb = np.arccosh(np.exp(u * dtau / 2.)) if u else 0
     return ham, dtau, lamb, expm(-1 * dtau * ham), expm(dtau * ham)
