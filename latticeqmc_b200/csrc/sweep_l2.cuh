@@ -27,6 +27,8 @@
 #include <cuda_pipeline_primitives.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
 #include "sweep_reg.cuh"
 
 namespace lqmc {
@@ -34,6 +36,7 @@ namespace lqmc {
 struct L2Workspace {
   double* T = nullptr;      // [chain][2][NP][NP] second matrix buffer (two-GEMM wrap, running product)
   int kd = 0;               // delay depth the shared-memory budget allows
+  bool tmem_ok = false;     // the NP <= 256 tensor-memory slice path fits the shared-memory region
   size_t smem = 0;          // dynamic shared memory per CTA
 };
 
@@ -58,6 +61,7 @@ struct L2Smem {
   double* d;      // [2 buf][2 spin][NP] current diagonal, double-buffered across flips
   double* u;      // [NP]               uniforms of the slice
   double* red_v;  // [16]
+  double* hist;   // [64]  (TMEM path: history of the flipped site, 2 x L2_KDT; [63] doubles as the TMEM base-address slot)
   int* red_i;     // [16]
   int8_t* h;      // [NP]
   int8_t* hn;     // [NP]
@@ -78,7 +82,8 @@ struct L2Smem {
     d = tail;
     u = d + 4 * NP;
     red_v = u + NP;
-    full = reinterpret_cast<uint64_t*>(red_v + 16);
+    hist = red_v + 16;
+    full = reinterpret_cast<uint64_t*>(hist + 64);
     red_i = reinterpret_cast<int*>(full + 4);
     h = reinterpret_cast<int8_t*>(red_i + 16);
     hn = h + NP;
@@ -89,7 +94,7 @@ inline size_t l2_smem_bytes(int NP, int KD, int ns = 2) {
   size_t vec = (size_t)2 * ns * KD * NP;
   const size_t gemm = (size_t)L2_STAGES * L2_BK * (L2_BM + L2_BN + 8);
   if (vec < gemm) vec = gemm;
-  return (vec + 5 * (size_t)NP + 16 + 4) * sizeof(double) + 16 * sizeof(int) + 2 * (size_t)NP + 16;
+  return (vec + 5 * (size_t)NP + 16 + 64 + 4) * sizeof(double) + 16 * sizeof(int) + 2 * (size_t)NP + 16;
 }
 
 // ---- tiled GEMM:  C = A * B  with A given k-major (At[k*NP + i] = A[i][k]) and B row-major ------------------
@@ -184,8 +189,15 @@ __device__ __forceinline__ void l2_issue_panel(const L2PanelIssue& pi, int NP, i
   }
 }
 
-__device__ void l2_gemm(const double* __restrict__ At, const double* __restrict__ B, double* __restrict__ Cout, int NP, int spin,
-                        const L2Epilogue& ep, const SweepParams& p, L2Smem& sm) {
+// Compiled as a subroutine of its own (__noinline__, every argument by value): the register allocation of the GEMM main
+// loop must not depend on what else lives in the sweep kernel - measured: the same source ran 10 % slower inlined next to
+// the tensor-memory slice path.
+struct L2GemmCtx { double* pa; double* pb; uint64_t* full; double exp_pl, exp_ml; };
+__device__ __forceinline__ double hs_v2(int8_t h, int spin, bool inv, double exp_pl, double exp_ml) {
+  return (((h > 0) != (spin != 0)) != inv) ? exp_ml : exp_pl;
+}
+__device__ __noinline__ void l2_gemm_sub(const double* __restrict__ At, const double* __restrict__ B, double* __restrict__ Cout, int NP,
+                                         int spin, const L2Epilogue ep, const L2GemmCtx sm) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp >> 2, wn = warp & 3;            // 2 x 4 warps, 32 x 32 warp tiles
   const int lr = lane >> 2, lk = lane & 3;
@@ -205,7 +217,7 @@ __device__ void l2_gemm(const double* __restrict__ At, const double* __restrict_
 #pragma unroll
         for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
 #if LQMC_L2_STAGING_TMA
-      const uint32_t it0 = sm.pipe_iter;
+      const uint32_t it0 = pipe_iter_unused;
       L2PanelIssue pi;
       pi.srcA = At + (size_t)lane * NP + i0;
       pi.srcB = B + (size_t)lane * NP + j0;
@@ -238,7 +250,7 @@ __device__ void l2_gemm(const double* __restrict__ At, const double* __restrict_
         __syncthreads();                     // every warp is done with stage st: refill it
         if (warp == 0 && kp + L2_STAGES < nk) l2_issue_panel(pi, NP, (kp + L2_STAGES) * L2_BK, st, lane);
       }
-      sm.pipe_iter = it0 + nk;
+      pipe_iter_unused = it0 + nk;
 #else
       // LDGSTS ring: every thread copies 2 (A) + 4 (B) 16-byte chunks per panel; addresses set up once per tile
       const double* srcA = At + (size_t)(tid >> 5) * NP + i0 + 2 * (tid & 31);          // rows tid/32 (+8), chunk tid%32
@@ -287,7 +299,7 @@ __device__ void l2_gemm(const double* __restrict__ At, const double* __restrict_
 #pragma unroll
       for (int m = 0; m < 4; ++m) {
         const int row = i0 + 32 * wm + 8 * m + lr;
-        const double rs = ep.hrow ? (ep.row_inv ? hs_vinv(ep.hrow[row], spin, p) : hs_v(ep.hrow[row], spin, p)) : 1.0;
+        const double rs = ep.hrow ? (hs_v2(ep.hrow[row], spin, ep.row_inv, sm.exp_pl, sm.exp_ml)) : 1.0;
 #pragma unroll
         for (int n = 0; n < 4; ++n) {
 #pragma unroll
@@ -295,7 +307,7 @@ __device__ void l2_gemm(const double* __restrict__ At, const double* __restrict_
             const int col = j0 + 32 * wn + 8 * n + 2 * lk + s2;
             double v = acc[m][n][s2];
             if (ep.hrow) v *= rs;
-            if (ep.hcol) v *= (ep.col_inv ? hs_vinv(ep.hcol[col], spin, p) : hs_v(ep.hcol[col], spin, p));
+            if (ep.hcol) v *= hs_v2(ep.hcol[col], spin, ep.col_inv, sm.exp_pl, sm.exp_ml);
             if (ep.add_identity && row == col) v += 1.0;
             acc[m][n][s2] = v;
           }
@@ -311,6 +323,13 @@ __device__ void l2_gemm(const double* __restrict__ At, const double* __restrict_
     }
   }
   __syncthreads();
+}
+
+__device__ __forceinline__ void l2_gemm(const double* __restrict__ At, const double* __restrict__ B, double* __restrict__ Cout, int NP, int spin,
+                                        const L2Epilogue& ep, const SweepParams& p, L2Smem& sm) {
+  L2GemmCtx c;
+  c.pa = sm.pa; c.pb = sm.pb; c.full = sm.full; c.exp_pl = p.exp_pl; c.exp_ml = p.exp_ml;
+  l2_gemm_sub(At, B, Cout, NP, spin, ep, c);
 }
 
 // ---- G0 <- G0 - sum_m U_m W_m^T for both spins (the delayed block update) -----------------------------------
@@ -387,7 +406,8 @@ __device__ void l2_flush(double* __restrict__ Gc, int NP, int nd, L2Smem& sm, in
 }
 
 // ---- the N proposals of one slice with delayed updates ------------------------------------------------------
-template <bool EXACT, bool PHYS>
+// QMAX = entries per thread in the vector phases: 1 for NP <= 256 (no dead registers for larger lattices), else L2_MAXQ
+template <bool EXACT, bool PHYS, int QMAX>
 __device__ void l2_propose_slice(double* __restrict__ Gc, int NP, int KD, L2Smem& sm, const SweepParams& p, long long trace_base,
                                  int& n_accepted) {
   const int tid = threadIdx.x, lane = tid & 31;
@@ -440,12 +460,12 @@ __device__ void l2_propose_slice(double* __restrict__ Gc, int NP, int KD, L2Smem
     const double fd = (hs > 0) ? p.f_m2 : p.f_p2;
     // rebuild row `is` and column `is` of the current G: thread handles entries j = tid + 256 q of both spins.
     // The (strided) global loads of both spins are issued together, ahead of any use.
-    double row2[2][L2_MAXQ], col2[2][L2_MAXQ];
+    double row2[2][QMAX], col2[2][QMAX];
 #pragma unroll
     for (int spin = 0; spin < 2; ++spin) {
       const double* G = Gc + (size_t)spin * NP * NP;
 #pragma unroll
-      for (int q = 0; q < L2_MAXQ; ++q) {
+      for (int q = 0; q < QMAX; ++q) {
         const int j = tid + L2_THREADS * q;
         if (j < NP) { row2[spin][q] = G[(size_t)is * NP + j]; col2[spin][q] = G[(size_t)j * NP + is]; }
       }
@@ -460,12 +480,12 @@ __device__ void l2_propose_slice(double* __restrict__ Gc, int NP, int KD, L2Smem
       const double* U = sm.U + (size_t)spin * KD * NP;
       const double* W = sm.W + (size_t)spin * KD * NP;
       const double gs = spin ? gd : gu;
-      double (&row)[L2_MAXQ] = row2[spin];
-      double (&col)[L2_MAXQ] = col2[spin];
+      double (&row)[QMAX] = row2[spin];
+      double (&col)[QMAX] = col2[spin];
       for (int m = 0; m < nd; ++m) {
         const double ui = U[(size_t)m * NP + is], wi = W[(size_t)m * NP + is];
 #pragma unroll
-        for (int q = 0; q < L2_MAXQ; ++q) {
+        for (int q = 0; q < QMAX; ++q) {
           const int j = tid + L2_THREADS * q;
           if (j < NP) {
             row[q] = rank1<EXACT>(row[q], ui, W[(size_t)m * NP + j]);
@@ -485,7 +505,7 @@ __device__ void l2_propose_slice(double* __restrict__ Gc, int NP, int KD, L2Smem
         const double r = __drcp_rn(den);
         const bool ok = div_safe(den);
 #pragma unroll
-        for (int q = 0; q < L2_MAXQ; ++q) {
+        for (int q = 0; q < QMAX; ++q) {
           const int j = tid + L2_THREADS * q;
           if (j < NP) {
             double c = __dmul_rn(-gamma, row[q]);
@@ -500,7 +520,7 @@ __device__ void l2_propose_slice(double* __restrict__ Gc, int NP, int KD, L2Smem
         const double rr = __dadd_rn(1.0, __dmul_rn(__dsub_rn(1.0, gs), delta));
         const double fac = delta / rr;
 #pragma unroll
-        for (int q = 0; q < L2_MAXQ; ++q) {
+        for (int q = 0; q < QMAX; ++q) {
           const int j = tid + L2_THREADS * q;
           if (j < NP) {
             const double e = ((j == is) ? (1.0 - col[q]) : -col[q]) * fac;
@@ -532,6 +552,252 @@ __device__ void l2_propose_slice(double* __restrict__ Gc, int NP, int KD, L2Smem
 #ifdef LQMC_PHASE_CLOCKS
   { const long long tk1 = clock64(); tk_flush += tk1 - tk0;
     if (tid == 0) { double* ob = p.obs_sum + (size_t)blockIdx.x * 3 * N; ob[0] = (double)tk_scan; ob[1] = (double)tk_build; ob[2] = (double)tk_flush; ob[3] = (double)n_accepted; ob[4] = (double)tk_b1; ob[5] = (double)tk_b2; ob[6] = (double)tk_b3; } }
+#endif
+}
+
+// ---- NP <= 256: twice the delay depth, c vectors parked in tensor memory ---------------------------------------------------
+// The slice phase streams G through HBM once per flush (32 N^2 bytes for both spins) and, with every chain's G in flight
+// (296 MiB at 16x16), that traffic - not the FP64 pipe - bounds it: per-flush time is the same at delay depth 3, 6 and 12,
+// in EXACT and FMA arithmetic alike (profiles/r01_cfg4_summary.md).  The only lever is the delay depth, and shared memory
+// (4 KD NP doubles for U and W) caps it at 12 with two CTAs per SM.  Blackwell's tensor memory is idle in an FP64 code:
+// 256 KB per SM, 128 lanes x 512 32-bit columns, reached with tcgen05.ld / tcgen05.st.  In the 32x32b shape thread t of
+// warp w addresses lane 32 (w % 4) + t % 32, i.e. TMEM is a per-thread scratchpad.  So:
+//   * U (the e vectors) stays in shared memory, [2 spin][L2_KDT][NP]  (98 KB at NP = 256 for L2_KDT = 24);
+//   * thread j parks the c history of ITS column, c_m[j], in TMEM (2 L2_KDT doubles = 96 columns; warps w and w+4 share a
+//     lane quarter and use disjoint column windows; 256 columns per CTA, two CTAs per SM);
+//   * row rebuild   G0[i][j] - sum_m e_m[i] c_m[j] : e_m[i] broadcast from shared memory, c_m[j] own (TMEM);
+//     column rebuild G0[j][i] - sum_m e_m[j] c_m[i] : e_m[j] from shared memory, c_m[i] published by the warp that owns site i;
+//   * the flush walks G with thread <-> column (a warp covers 32 consecutive columns, 256-byte row segments), c_m[j] in
+//     registers for one spin at a time, e_m of eight rows as broadcast 128-bit shared loads.
+// Same roundings in the same order as the generic path and the reference's one-flip-at-a-time loop (lqmc.py:328-331).
+#ifndef LQMC_L2_KDT
+#define LQMC_L2_KDT 24
+#endif
+constexpr int L2_KDT = LQMC_L2_KDT;
+constexpr int L2_TMEM_COLS = 256;
+static_assert(L2_KDT % 8 == 0 && 8 * L2_KDT <= L2_TMEM_COLS, "two windows of 4 KDT columns; history read in chunks of 8 doubles");
+
+__device__ __forceinline__ void tmem_st_f64(uint32_t taddr, double v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"((uint32_t)__double2loint(v)),
+               "r"((uint32_t)__double2hiint(v))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld_f64x8(uint32_t taddr, double (&v)[8]) {
+  uint32_t r[16];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                 "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(taddr)
+               : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __hiloint2double((int)r[2 * i + 1], (int)r[2 * i]);
+}
+// one warp allocates L2_TMEM_COLS columns for the CTA; every thread gets the base address
+__device__ __forceinline__ uint32_t tmem_alloc_cta(uint32_t* slot) {
+  if ((threadIdx.x >> 5) == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "n"(L2_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  return *slot;
+}
+__device__ __forceinline__ void tmem_free_cta(uint32_t base) {
+  __syncthreads();
+  if ((threadIdx.x >> 5) == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "n"(L2_TMEM_COLS) : "memory");
+}
+
+template <bool EXACT>
+__device__ void l2_flush_tmem(double* __restrict__ Gc, int NP, int nd, const double* __restrict__ U3, uint32_t tm_my) {
+  const int tid = threadIdx.x;
+  if (tid < NP) {                                  // warp-uniform: NP is a multiple of 128
+    for (int spin = 0; spin < 2; ++spin) {
+      double cj[L2_KDT];
+#pragma unroll
+      for (int m0 = 0; m0 < L2_KDT; m0 += 8) {
+        double v[8];
+        tmem_ld_f64x8(tm_my + 2 * (spin * L2_KDT + m0), v);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) cj[m0 + q] = v[q];
+      }
+      double* const col = Gc + (size_t)spin * NP * NP + tid;
+      const double* const Us = U3 + (size_t)spin * L2_KDT * NP;
+      double nxt[8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) nxt[r] = col[(size_t)r * NP];
+      for (int r0 = 0; r0 < NP; r0 += 8) {
+        double g[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) g[r] = nxt[r];
+        if (r0 + 8 < NP) {
+#pragma unroll
+          for (int r = 0; r < 8; ++r) nxt[r] = col[(size_t)(r0 + 8 + r) * NP];
+        }
+#pragma unroll
+        for (int m = 0; m < L2_KDT; ++m) {
+          if (m < nd) {
+            const double* ur = Us + (size_t)m * NP + r0;
+#pragma unroll
+            for (int r = 0; r < 8; r += 2) {
+              const double2 e = *reinterpret_cast<const double2*>(ur + r);
+              g[r] = rank1<EXACT>(g[r], e.x, cj[m]);
+              g[r + 1] = rank1<EXACT>(g[r + 1], e.y, cj[m]);
+            }
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < 8; ++r) col[(size_t)(r0 + r) * NP] = g[r];
+      }
+    }
+  }
+  __syncthreads();
+}
+
+template <bool EXACT, bool PHYS>
+__device__ void l2_propose_slice_tmem(double* __restrict__ Gc, int NP, L2Smem& sm, const SweepParams& p, long long trace_base,
+                                      int& n_accepted, uint32_t tm_base) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int N = p.n_sites;
+  double* const U3 = sm.U;                       // [2][L2_KDT][NP]: exactly the generic path's U / W region at KD = L2_KDT / 2
+  double* const wis = sm.hist;                   // [2][L2_KDT] c history of the site being flipped
+  const int j = tid;
+  const bool act = j < NP;
+  // this thread's TMEM window: lane quarter of its warp, columns [0, 4 KDT) for warps 0-3, [4 KDT, 8 KDT) for warps 4-7
+  const uint32_t tm_my = tm_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)((warp >> 2) * 4 * L2_KDT);
+  for (int spin = 0; spin < 2; ++spin)
+    for (int q = tid; q < NP; q += L2_THREADS) sm.d[spin * NP + q] = Gc[(size_t)spin * NP * NP + (size_t)q * NP + q];
+  __syncthreads();
+  int nd = 0, i0 = 0, cur = 0;
+#ifdef LQMC_PHASE_CLOCKS
+  long long tk_scan = 0, tk_build = 0, tk_flush = 0, tk0 = clock64();
+  unsigned long long gt0; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt0));
+#endif
+  while (i0 < N) {
+    const double* dcur = sm.d + cur * 2 * NP;
+    double* dnxt = sm.d + (cur ^ 1) * 2 * NP;
+    const int i = i0 + lane;
+    bool acc = false;
+    double gu = 0.0, gd = 0.0, ratio = 0.0;
+    int8_t h = 1;
+    if (i < N) {
+      h = sm.h[i];
+      gu = dcur[i];
+      gd = dcur[NP + i];
+      const double fu = (h > 0) ? p.f_p2 : p.f_m2;
+      const double fd = (h > 0) ? p.f_m2 : p.f_p2;
+      const double du = __dadd_rn(1.0, __dmul_rn(__dsub_rn(1.0, gu), fu));
+      const double dd = __dadd_rn(1.0, __dmul_rn(__dsub_rn(1.0, gd), fd));
+      ratio = __dmul_rn(du, dd);
+      acc = sm.u[i] <= ratio;
+    }
+    const unsigned ballot = __ballot_sync(0xffffffffu, acc);
+    const int first = ballot ? (__ffs(ballot) - 1) : 32;
+    if (p.tr_ratio != nullptr && tid < 32 && i < N && lane <= first) {
+      p.tr_ratio[trace_base + i] = ratio;
+      p.tr_acc[trace_base + i] = (lane == first) ? 1 : 0;
+    }
+    if (!ballot) { i0 += 32; continue; }
+#ifdef LQMC_PHASE_CLOCKS
+    { const long long tk1 = clock64(); tk_scan += tk1 - tk0; tk0 = tk1; }
+#endif
+    const int is = i0 + first;
+    gu = __shfl_sync(0xffffffffu, gu, first);
+    gd = __shfl_sync(0xffffffffu, gd, first);
+    const int hs = __shfl_sync(0xffffffffu, (int)h, first);
+    const double fu = (hs > 0) ? p.f_p2 : p.f_m2;
+    const double fd = (hs > 0) ? p.f_m2 : p.f_p2;
+    // G0 row / column of the flipped site, both spins, issued together
+    double row[2] = {0.0, 0.0}, col[2] = {0.0, 0.0};
+    if (act) {
+#pragma unroll
+      for (int spin = 0; spin < 2; ++spin) {
+        const double* G = Gc + (size_t)spin * NP * NP;
+        row[spin] = G[(size_t)is * NP + j];
+        col[spin] = G[(size_t)j * NP + is];
+      }
+    }
+    // the warp that owns site `is` publishes that site's c history (tcgen05.ld is warp-collective)
+    if (warp == (is >> 5)) {
+      for (int m0 = 0; m0 < nd; m0 += 8) {
+#pragma unroll
+        for (int spin = 0; spin < 2; ++spin) {
+          double v[8];
+          tmem_ld_f64x8(tm_my + 2 * (spin * L2_KDT + m0), v);
+          if (lane == (is & 31)) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) wis[spin * L2_KDT + m0 + q] = v[q];
+          }
+        }
+      }
+    }
+    __syncthreads();
+    if (act) {
+      for (int m0 = 0; m0 < nd; m0 += 8) {
+        double wj[2][8];
+        tmem_ld_f64x8(tm_my + 2 * m0, wj[0]);
+        tmem_ld_f64x8(tm_my + 2 * (L2_KDT + m0), wj[1]);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int m = m0 + q;
+          if (m < nd) {
+#pragma unroll
+            for (int spin = 0; spin < 2; ++spin) {
+              const double* Um = U3 + ((size_t)spin * L2_KDT + m) * NP;
+              row[spin] = rank1<EXACT>(row[spin], Um[is], wj[spin][q]);
+              col[spin] = rank1<EXACT>(col[spin], Um[j], wis[spin * L2_KDT + m]);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int spin = 0; spin < 2; ++spin) {
+        const double gs = spin ? gd : gu;
+        double e, c;
+        if (!PHYS) {
+          const double gamma = spin ? fu : fd;            // exp(-arg)-1 for up, exp(+arg)-1 for down (lqmc.py:320-323)
+          const double ci = __dadd_rn(__dmul_rn(-gamma, gs), gamma);
+          const double den = __dadd_rn(1.0, ci);
+          const double r = __drcp_rn(den);
+          c = __dmul_rn(-gamma, row[spin]);
+          if (j == is) c = __dadd_rn(c, gamma);
+          e = EXACT ? div_shared_rcp(col[spin], den, r, div_safe(den)) : col[spin] * r;
+        } else {
+          const double delta = spin ? fd : fu;
+          const double rr = __dadd_rn(1.0, __dmul_rn(__dsub_rn(1.0, gs), delta));
+          const double fac = delta / rr;
+          e = ((j == is) ? (1.0 - col[spin]) : -col[spin]) * fac;
+          c = row[spin];
+        }
+        U3[((size_t)spin * L2_KDT + nd) * NP + j] = e;
+        tmem_st_f64(tm_my + 2 * (spin * L2_KDT + nd), c);
+        dnxt[spin * NP + j] = rank1<EXACT>(dcur[spin * NP + j], e, c);
+      }
+      tmem_wait_st();
+    }
+    ++n_accepted;
+    ++nd;
+    cur ^= 1;
+    __syncthreads();
+    if (tid == 0) sm.h[is] = (int8_t)(-hs);     // after the barrier: no warp is still scanning site `is`
+#ifdef LQMC_PHASE_CLOCKS
+    { const long long tk1 = clock64(); tk_build += tk1 - tk0; tk0 = tk1; }
+#endif
+    if (nd == L2_KDT) { l2_flush_tmem<EXACT>(Gc, NP, nd, U3, tm_my); nd = 0; }
+#ifdef LQMC_PHASE_CLOCKS
+    { const long long tk1 = clock64(); tk_flush += tk1 - tk0; tk0 = tk1; }
+#endif
+    i0 = is + 1;
+  }
+  if (nd > 0) l2_flush_tmem<EXACT>(Gc, NP, nd, U3, tm_my);
+#ifdef LQMC_PHASE_CLOCKS
+  { const long long tk1 = clock64(); tk_flush += tk1 - tk0;
+    if (tid == 0) { double* ob = p.obs_sum + (size_t)blockIdx.x * 3 * N; ob[0] = (double)tk_scan; ob[1] = (double)tk_build; ob[2] = (double)tk_flush; ob[3] = (double)n_accepted;
+      unsigned smid; asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+      unsigned long long gt1; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt1));
+      ob[4] = (double)smid; ob[5] = (double)(gt0 & 0xffffffffffffull); ob[6] = (double)(gt1 & 0xffffffffffffull); } }
 #endif
 }
 
@@ -708,11 +974,12 @@ __device__ void l2_wrap(double* __restrict__ Gc, double* __restrict__ Tc, int NP
 struct L2Params {
   SweepParams p;
   double* T;
+  int use_tmem;   // 1: slice path with the c history in tensor memory (NP <= 256)
   int* piv;       // [chain][2][NP] scratch
   int NP, KD;
 };
 
-template <bool EXACT, bool PHYS>
+template <bool EXACT, bool PHYS, bool TMEM>
 __global__ void __launch_bounds__(L2_THREADS, 2) sweep_l2_kernel(const L2Params lp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const SweepParams& p = lp.p;
@@ -725,6 +992,8 @@ __global__ void __launch_bounds__(L2_THREADS, 2) sweep_l2_kernel(const L2Params 
   double* Tc = lp.T + (size_t)chain * 2 * NP * NP;
   int* piv = lp.piv + (size_t)chain * 2 * NP;
   int n_accepted = 0;
+  uint32_t tm_base = 0;
+  if (TMEM) tm_base = tmem_alloc_cta(reinterpret_cast<uint32_t*>(sm.hist + 63));
   if (tid == 0) {
     for (int s0 = 0; s0 < L2_STAGES; ++s0) mbar_init(sm.full + s0, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -751,7 +1020,8 @@ __global__ void __launch_bounds__(L2_THREADS, 2) sweep_l2_kernel(const L2Params 
                     : lqmc_philox_uniform(p.seed, (uint64_t)(p.chain0 + chain), (uint64_t)(p.sweep0 + sweep), (uint32_t)(step * N + j));
           sm.u[j] = u;
         }
-        l2_propose_slice<EXACT, PHYS>(Gc, NP, KD, sm, p, base, n_accepted);
+        if (TMEM) l2_propose_slice_tmem<EXACT, PHYS>(Gc, NP, sm, p, base, n_accepted, tm_base);
+        else l2_propose_slice<EXACT, PHYS, L2_MAXQ>(Gc, NP, KD, sm, p, base, n_accepted);
         __syncthreads();
         for (int j = tid; j < NP; j += L2_THREADS) field[(size_t)l * NP + j] = sm.h[j];
       }
@@ -778,6 +1048,7 @@ __global__ void __launch_bounds__(L2_THREADS, 2) sweep_l2_kernel(const L2Params 
     }
   }
   if (tid == 0 && n_accepted) p.n_acc[chain] += n_accepted;
+  if (TMEM) tmem_free_cta(tm_base);
 }
 
 // ---- host side ------------------------------------------------------------------------------------------------
@@ -794,8 +1065,16 @@ inline int l2_alloc(L2Workspace& w, int n_sites, int np, int n_slices, int n_cha
   const size_t budget = (np <= 384) ? 110 * 1024 : 220 * 1024;
   int kd = 1;
   while (kd < 64 && l2_smem_bytes(np, kd + 1) <= budget) ++kd;
+  if (const char* env = getenv("LQMC_L2_KD")) { const int v = atoi(env); if (v >= 1 && v <= kd) kd = v; }   // experiments
   w.kd = kd;
   w.smem = l2_smem_bytes(np, kd);
+  if (np <= L2_THREADS) {
+    // the tensor-memory path keeps U [2][L2_KDT][NP] in the region the generic path sizes for U and W
+    size_t region = (size_t)4 * kd * np;
+    const size_t gemm = (size_t)L2_STAGES * L2_BK * (L2_BM + L2_BN + 8);
+    if (region < gemm) region = gemm;
+    w.tmem_ok = (size_t)2 * L2_KDT * np <= region;
+  }
   return 0;
 }
 inline void l2_free(L2Workspace& w) { if (w.T) cudaFree(w.T); w.T = nullptr; }
@@ -804,6 +1083,8 @@ inline int launch_l2(L2Workspace& w, const SweepParams& p, int np, uint32_t flag
                      size_t errlen) {
   L2Params lp;
   lp.p = p; lp.T = w.T; lp.NP = np; lp.KD = w.kd;
+  lp.use_tmem = (w.tmem_ok && p.do_propose) ? 1 : 0;
+  if (const char* env = getenv("LQMC_L2_SLICE_PATH")) { if (strcmp(env, "smem") == 0) lp.use_tmem = 0; }     // experiments
   lp.piv = reinterpret_cast<int*>(w.T + (size_t)p.n_chains * 2 * np * np);
   const bool exact = !(flags & 0x2u), phys = (flags & 0x1u) != 0;
   auto go = [&](auto kernel) -> int {
@@ -816,10 +1097,16 @@ inline int launch_l2(L2Workspace& w, const SweepParams& p, int np, uint32_t flag
     *launches += 1;
     return 0;
   };
-  if (exact && !phys) return go(sweep_l2_kernel<true, false>);
-  if (!exact && !phys) return go(sweep_l2_kernel<false, false>);
-  if (exact && phys) return go(sweep_l2_kernel<true, true>);
-  return go(sweep_l2_kernel<false, true>);
+  if (lp.use_tmem) {
+    if (exact && !phys) return go(sweep_l2_kernel<true, false, true>);
+    if (!exact && !phys) return go(sweep_l2_kernel<false, false, true>);
+    if (exact && phys) return go(sweep_l2_kernel<true, true, true>);
+    return go(sweep_l2_kernel<false, true, true>);
+  }
+  if (exact && !phys) return go(sweep_l2_kernel<true, false, false>);
+  if (!exact && !phys) return go(sweep_l2_kernel<false, false, false>);
+  if (exact && phys) return go(sweep_l2_kernel<true, true, false>);
+  return go(sweep_l2_kernel<false, true, false>);
 }
 
 }  // namespace lqmc

@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblqmc_b200.so")
+LIB_PATH = os.environ.get("LQMC_B200_LIB") or os.path.join(_HERE, "liblqmc_b200.so")     # override: kernel experiments
 
 MODE_PARITY = 0x0
 MODE_PHYSICS = 0x1

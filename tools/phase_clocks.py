@@ -24,5 +24,15 @@ for l in (lt - 1, lt - 2, lt - 3):
     eng.slice(l, None, seed=2)
     ob = eng.get_measurements()["obs_sum"][:, 0, :7]
     scan, build, flush, nacc, b1, b2, b3 = ob.mean(0)
+    full = eng.get_measurements()["obs_sum"][:, 0, :7]
+    if full[:, 5].max() > 1e6:          # tensor-memory path: columns 4..6 = SM id, start, end (globaltimer ns)
+        sm_id, t0, t1 = full[:, 4], full[:, 5], full[:, 6]
+        pairs = ov = 0
+        for a in range(chains):
+            for b2 in range(a + 1, chains):
+                if sm_id[a] == sm_id[b2]:
+                    pairs += 1
+                    ov += (t0[a] < t1[b2]) and (t0[b2] < t1[a])
+        print(f"  CTAs sharing an SM: {pairs} pairs, {ov} overlapping in time; kernel span {(t1.max() - t0.min()) / 1e3:.0f} us, mean CTA {np.mean(t1 - t0) / 1e3:.0f} us")
     print(f"slice {l}: per CTA clocks scan {scan:9.0f} build {build:9.0f} flush {flush:9.0f} total {scan+build+flush:9.0f}  accepted {nacc:6.1f}"
           f"  per flip: scan {scan/nacc:7.0f} build {build/nacc:7.0f} flush {flush/nacc:7.0f}   build split: loads {b1/nacc:6.0f} apply(2 spins) {b2/nacc:6.0f} vectors {b3/nacc:6.0f}")
