@@ -192,7 +192,7 @@ __device__ __forceinline__ void l2_issue_panel(const L2PanelIssue& pi, int NP, i
 // Compiled as a subroutine of its own (__noinline__, every argument by value): the register allocation of the GEMM main
 // loop must not depend on what else lives in the sweep kernel - measured: the same source ran 10 % slower inlined next to
 // the tensor-memory slice path.
-struct L2GemmCtx { double* pa; double* pb; uint64_t* full; double exp_pl, exp_ml; };
+struct L2GemmCtx { double* pa; double* pb; uint64_t* full; uint32_t* pipe_iter; double exp_pl, exp_ml; };
 __device__ __forceinline__ double hs_v2(int8_t h, int spin, bool inv, double exp_pl, double exp_ml) {
   return (((h > 0) != (spin != 0)) != inv) ? exp_ml : exp_pl;
 }
@@ -216,8 +216,19 @@ __device__ __noinline__ void l2_gemm_sub(const double* __restrict__ At, const do
       for (int a = 0; a < 4; ++a)
 #pragma unroll
         for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+      // field bytes of this thread's rows / column pairs for the epilogue scales: in flight during the main loop
+      int hr[4] = {1, 1, 1, 1};
+      unsigned hc[4] = {0x0101u, 0x0101u, 0x0101u, 0x0101u};
+      if (ep.hrow) {
+#pragma unroll
+        for (int m = 0; m < 4; ++m) hr[m] = ep.hrow[i0 + 32 * wm + 8 * m + lr];
+      }
+      if (ep.hcol) {
+#pragma unroll
+        for (int n = 0; n < 4; ++n) hc[n] = *reinterpret_cast<const unsigned short*>(ep.hcol + j0 + 32 * wn + 8 * n + 2 * lk);
+      }
 #if LQMC_L2_STAGING_TMA
-      const uint32_t it0 = pipe_iter_unused;
+      const uint32_t it0 = *sm.pipe_iter;
       L2PanelIssue pi;
       pi.srcA = At + (size_t)lane * NP + i0;
       pi.srcB = B + (size_t)lane * NP + j0;
@@ -250,7 +261,9 @@ __device__ __noinline__ void l2_gemm_sub(const double* __restrict__ At, const do
         __syncthreads();                     // every warp is done with stage st: refill it
         if (warp == 0 && kp + L2_STAGES < nk) l2_issue_panel(pi, NP, (kp + L2_STAGES) * L2_BK, st, lane);
       }
-      pipe_iter_unused = it0 + nk;
+      __syncthreads();
+      if (tid == 0) *sm.pipe_iter = it0 + nk;
+      __syncthreads();
 #else
       // LDGSTS ring: every thread copies 2 (A) + 4 (B) 16-byte chunks per panel; addresses set up once per tile
       const double* srcA = At + (size_t)(tid >> 5) * NP + i0 + 2 * (tid & 31);          // rows tid/32 (+8), chunk tid%32
@@ -295,23 +308,22 @@ __device__ __noinline__ void l2_gemm_sub(const double* __restrict__ At, const do
       __pipeline_wait_prior(0);
       __syncthreads();                               // panels free for the next tile
 #endif
-      // epilogue: element (row, col) = acc[m][n][s]
+      // epilogue: element (row, col) = acc[m][n][s]; the field bytes were fetched before the main loop
 #pragma unroll
       for (int m = 0; m < 4; ++m) {
         const int row = i0 + 32 * wm + 8 * m + lr;
-        const double rs = ep.hrow ? (hs_v2(ep.hrow[row], spin, ep.row_inv, sm.exp_pl, sm.exp_ml)) : 1.0;
+        const double rs = hs_v2((int8_t)hr[m], spin, ep.row_inv, sm.exp_pl, sm.exp_ml);
 #pragma unroll
         for (int n = 0; n < 4; ++n) {
+          const int col0 = j0 + 32 * wn + 8 * n + 2 * lk;
 #pragma unroll
           for (int s2 = 0; s2 < 2; ++s2) {
-            const int col = j0 + 32 * wn + 8 * n + 2 * lk + s2;
             double v = acc[m][n][s2];
             if (ep.hrow) v *= rs;
-            if (ep.hcol) v *= hs_v2(ep.hcol[col], spin, ep.col_inv, sm.exp_pl, sm.exp_ml);
-            if (ep.add_identity && row == col) v += 1.0;
+            if (ep.hcol) v *= hs_v2((int8_t)(s2 ? (hc[n] >> 8) : (hc[n] & 0xff)), spin, ep.col_inv, sm.exp_pl, sm.exp_ml);
+            if (ep.add_identity && row == col0 + s2) v += 1.0;
             acc[m][n][s2] = v;
           }
-          const int col0 = j0 + 32 * wn + 8 * n + 2 * lk;
           if (!ep.transposed_out) {
             *reinterpret_cast<double2*>(Cout + (size_t)row * NP + col0) = make_double2(acc[m][n][0], acc[m][n][1]);
           } else {
@@ -328,7 +340,8 @@ __device__ __noinline__ void l2_gemm_sub(const double* __restrict__ At, const do
 __device__ __forceinline__ void l2_gemm(const double* __restrict__ At, const double* __restrict__ B, double* __restrict__ Cout, int NP, int spin,
                                         const L2Epilogue& ep, const SweepParams& p, L2Smem& sm) {
   L2GemmCtx c;
-  c.pa = sm.pa; c.pb = sm.pb; c.full = sm.full; c.exp_pl = p.exp_pl; c.exp_ml = p.exp_ml;
+  c.pa = sm.pa; c.pb = sm.pb; c.full = sm.full; c.pipe_iter = reinterpret_cast<uint32_t*>(sm.hist + 62);
+  c.exp_pl = p.exp_pl; c.exp_ml = p.exp_ml;
   l2_gemm_sub(At, B, Cout, NP, spin, ep, c);
 }
 
@@ -996,6 +1009,7 @@ __global__ void __launch_bounds__(L2_THREADS, 2) sweep_l2_kernel(const L2Params 
   if (TMEM) tm_base = tmem_alloc_cta(reinterpret_cast<uint32_t*>(sm.hist + 63));
   if (tid == 0) {
     for (int s0 = 0; s0 < L2_STAGES; ++s0) mbar_init(sm.full + s0, 1);
+    *reinterpret_cast<uint32_t*>(sm.hist + 62) = 0;          // panels consumed so far (TMA staging: stage / phase parity)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
