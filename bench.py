@@ -364,9 +364,9 @@ def run_ours(args):
             accept_rate=accept, accepted_flips_per_s=value * accept,
             roofline=dict(bound="tensor", pipe="FP64 (DFMA and DMMA issue to the same pipe on sm_100a; no tcgen05 f64 kind)",
                           achieved=achieved, peak=peaks["fp64_tflops"], unit="TFLOP/s", frac=achieved / peaks["fp64_tflops"],
-                          traffic=load_traffic(args.workload), peak_source=peaks["source"],
+                          traffic=None if physics else load_traffic(args.workload), peak_source=peaks["source"],
                           kernel="sweep_reg_kernel" if info["family"] == "reg" else "sweep_l2_kernel",
-                          flops_per_launch=flops, hbm=hbm_leg(args.workload, kernel_ms, peaks)),
+                          flops_per_launch=flops, hbm=None if physics else hbm_leg(args.workload, kernel_ms, peaks)),
             e2e=dict(value=e2e_value, unit=UNIT,
                      h2d_bytes_per_step=int(world * (fields.nbytes + pin_uni.numel() * 8)),
                      d2h_bytes_per_step=int(world * (fields.nbytes + chains * 2 * n * n * 8)),
