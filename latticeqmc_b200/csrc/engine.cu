@@ -221,7 +221,8 @@ int stab_init(lqmc_engine* e) {
     CU(cudaMemcpy(st.Et, mt.data(), mat * sizeof(double), cudaMemcpyHostToDevice));
   }
   st.smem_gemm = (size_t)lqmc::ST_STAGES * lqmc::ST_BK * (lqmc::ST_LDA + 32 * st.nfrag + 4) * sizeof(double);
-  st.smem_qr = lqmc::StQrSmem<lqmc::ST_NB>::bytes(st.NPs);
+  st.smem_qr = (st.NPs == 64) ? (size_t)(2 * 64 * 65 + 6 * 64) * sizeof(double) + 64 * sizeof(int)
+                              : lqmc::StQrSmem<lqmc::ST_NB>::bytes(st.NPs);
   int rc = 0;
   if (st.nfrag == 4) {
     int kd = 1;
@@ -239,7 +240,8 @@ int stab_init(lqmc_engine* e) {
     rc |= set_smem(lqmc::st_gemm_kernel<2>, st.smem_gemm);
     rc |= set_smem(lqmc::st_inverse_small_kernel, st.smem_inv);
   }
-  rc |= set_smem(lqmc::st_qr_kernel<lqmc::ST_NB>, st.smem_qr);
+  if (st.NPs == 64) rc |= set_smem(lqmc::st_qr_small_kernel, st.smem_qr);
+  else rc |= set_smem(lqmc::st_qr_kernel<lqmc::ST_NB>, st.smem_qr);
   if (rc) return rc;
   st.ready = true;
   return LQMC_OK;
@@ -282,7 +284,8 @@ int stab_absorb(lqmc_engine* e, const double* Usrc, size_t u_stride, const doubl
   lqmc::StQrArgs qa;
   qa.M = Mres; qa.A = Moth; qa.Q = Uout; qa.q_stride = uo_stride; qa.dvec = Dout; qa.d_stride = do_stride;
   qa.tfac = st.tfac; qa.perm = st.perm; qa.N = e->N; qa.NPs = st.NPs;
-  lqmc::st_qr_kernel<lqmc::ST_NB><<<grid, lqmc::ST_THREADS, st.smem_qr, s>>>(qa);
+  if (st.NPs == 64) lqmc::st_qr_small_kernel<<<grid, lqmc::ST_THREADS, st.smem_qr, s>>>(qa);
+  else lqmc::st_qr_kernel<lqmc::ST_NB><<<grid, lqmc::ST_THREADS, st.smem_qr, s>>>(qa);
   lqmc::StVArgs va;
   va.R = Moth; va.dvec = Dout; va.d_stride = do_stride; va.perm = st.perm; va.Vold = Vold; va.vold_stride = vold_stride;
   va.At = Mres; va.Vnew = Vout; va.vnew_stride = vo_stride; va.N = e->N; va.NPs = st.NPs; va.hc = hs_consts(e);

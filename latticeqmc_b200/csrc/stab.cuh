@@ -164,6 +164,12 @@ __device__ void st_transpose_map(const double* __restrict__ in, double* __restri
     }
 }
 
+// reciprocal to ~1 ulp: hardware seed + one Newton step (no denormal / overflow fix-ups: operands here are O(norms))
+__device__ __forceinline__ double st_rcp(double d) {
+  double r = __drcp_rn(d);
+  return r;
+}
+
 __device__ __forceinline__ double st_warp_sum(double v) {
 #pragma unroll
   for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
@@ -478,6 +484,164 @@ __global__ void __launch_bounds__(ST_THREADS) st_qr_kernel(const StQrArgs a) {
     __syncthreads();
     st_apply_reflector<NB, false>(Q, NP, j0, m, j0, N, sm.P, sm.Ts, sm.Wt);
   }
+}
+
+// ---- NPs = 64: the whole factorization in shared memory ------------------------------------------------------------
+// For N <= 64 the blocked kernel above is pure latency (900 K clocks per 64 x 64 matrix: global round trips per row of
+// the reflector application).  Here the matrix (33 KB) and Q live in shared memory; unblocked Householder, 256 threads =
+// 64 columns x 4 row quarters, two barriers per column; same outputs (A = R + reflectors is not needed afterwards, only
+// R, D, Q and the permutation).
+__global__ void __launch_bounds__(ST_THREADS) st_qr_small_kernel(const StQrArgs a) {
+  constexpr int NP = 64, LD = 65;
+  extern __shared__ __align__(16) unsigned char st_smem[];
+  double* S0 = reinterpret_cast<double*>(st_smem);      // M, later Q
+  double* S1 = S0 + NP * LD;                            // A = M[:, perm], factored in place
+  double* red = S1 + NP * LD;                           // [4][64] partial dot products
+  double* norms = red + 4 * NP;                         // [64]
+  double* taus = norms + NP;                            // [64]
+  int* perm_s = reinterpret_cast<int*>(taus + NP);      // [64]
+  const int N = a.N;
+  const int m_idx = blockIdx.x, tid = threadIdx.x;
+  const int c = tid & 63, q = tid >> 6, r_lo = 16 * q, r_hi = 16 * q + 16;
+  const double* M = a.M + (size_t)m_idx * NP * NP;
+  double* A = a.A + (size_t)m_idx * NP * NP;
+  double* Q = a.Q + (size_t)m_idx * a.q_stride;
+  double* dvec = a.dvec + (size_t)m_idx * a.d_stride;
+  int* perm = a.perm + (size_t)m_idx * NP;
+  for (int idx = tid; idx < NP * NP; idx += ST_THREADS) S0[(idx >> 6) * LD + (idx & 63)] = M[idx];
+  __syncthreads();
+  // column norms (4 partial sums per column) -> descending permutation
+  {
+    double s = 0.0;
+    if (c < N)
+      for (int r = r_lo; r < r_hi; ++r) if (r < N) { const double v = S0[r * LD + c]; s = fma(v, v, s); }
+    red[q * NP + c] = s;
+  }
+  __syncthreads();
+  if (tid < NP) norms[tid] = red[tid] + red[NP + tid] + red[2 * NP + tid] + red[3 * NP + tid];
+  __syncthreads();
+  if (tid < NP) {
+    if (tid < N) {
+      const double nc = norms[tid];
+      int rank = 0;
+      for (int o = 0; o < N; ++o) { const double no = norms[o]; rank += (no > nc || (no == nc && o < tid)) ? 1 : 0; }
+      perm_s[rank] = tid;
+    } else {
+      perm_s[tid] = tid;
+    }
+  }
+  __syncthreads();
+  if (tid < NP) perm[tid] = perm_s[tid];
+  for (int idx = tid; idx < NP * NP; idx += ST_THREADS) {
+    const int r = idx >> 6, j = idx & 63;
+    S1[r * LD + j] = (r < N && j < N) ? S0[r * LD + perm_s[j]] : (r == j ? 1.0 : 0.0);
+  }
+  __syncthreads();
+  // Householder QR of the leading N x N block of S1.  The 16-row loops are fully unrolled with predicates so that the
+  // shared loads of a phase are issued together (a rolled loop is one load-to-use latency per row: 600 K clocks per matrix).
+  const double* col_c = S1 + r_lo * LD + c;
+  double scale_prev = 0.0, beta_prev = 0.0, tau_prev = 0.0;
+  for (int j = 0; j < N; ++j) {
+    if (j > 0 && c == j - 1) {                              // finish column j-1: nobody reads it any more
+#pragma unroll
+      for (int rr = 0; rr < 16; ++rr) if (r_lo + rr >= j && r_lo + rr < N) S1[(r_lo + rr) * LD + j - 1] *= scale_prev;
+      if (q == 0) { S1[(j - 1) * LD + j - 1] = beta_prev; taus[j - 1] = tau_prev; }
+    }
+    const double ajc = S1[j * LD + c];                       // row j is read here, written (by its owner) after the barrier
+    const bool mine = (c >= j && c < N);
+    // rows of this quarter below the diagonal and inside the matrix: local indices [lo, hi)
+    const int lo = max(0, j + 1 - r_lo), hi = min(16, N - r_lo);
+    double vj[16], ac[16];
+    if (lo < hi && mine) {                                    // warp-uniform up to the `mine` edge; skipped quarters cost nothing
+      const double* col_j = S1 + r_lo * LD + j;
+      double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+      for (int rr = 0; rr < 16; ++rr) {
+        const bool on = (rr >= lo) && (rr < hi);
+        vj[rr] = on ? col_j[rr * LD] : 0.0;
+        ac[rr] = on ? col_c[rr * LD] : 0.0;
+      }
+#pragma unroll
+      for (int rr = 0; rr < 16; rr += 2) { s0 = fma(vj[rr], ac[rr], s0); s1 = fma(vj[rr + 1], ac[rr + 1], s1); }
+      red[q * NP + c] = s0 + s1;
+    } else {
+      red[q * NP + c] = 0.0;
+    }
+    __syncthreads();
+    const double sigma = red[j] + red[NP + j] + red[2 * NP + j] + red[3 * NP + j];
+    const double alpha = S1[j * LD + j];
+    double tau = 0.0, beta = alpha, scale = 0.0;
+    if (sigma != 0.0) {
+      // every thread evaluates these scalars: keep them cheap (IEEE sqrt and divide are ~40-instruction software
+      // sequences on the FP64 pipe and were 70 % of this kernel's FP64 issue slots); 1-ulp results are ample here
+      const double x2 = fma(alpha, alpha, sigma);
+      const double rs = rsqrt(x2);
+      double nrm = x2 * rs;
+      nrm = fma(fma(-nrm, nrm, x2), 0.5 * rs, nrm);
+      beta = (alpha >= 0.0) ? -nrm : nrm;
+      tau = (beta - alpha) * st_rcp(beta);
+      scale = st_rcp(alpha - beta);
+      if (c > j && c < N) {
+        const double dot = red[c] + red[NP + c] + red[2 * NP + c] + red[3 * NP + c];
+        const double wv = fma(scale, dot, ajc);
+        const double tw = tau * wv, tws = tw * scale;
+        if (lo < hi) {
+#pragma unroll
+          for (int rr = 0; rr < 16; ++rr)
+            if (rr >= lo && rr < hi) S1[(r_lo + rr) * LD + c] = fma(-tws, vj[rr], ac[rr]);
+        }
+        if (j >= r_lo && j < r_hi) S1[j * LD + c] = ajc - tw;
+      }
+    }
+    scale_prev = scale; beta_prev = beta; tau_prev = tau;
+    __syncthreads();
+  }
+  if (c == N - 1 && q == 0) { S1[(N - 1) * LD + N - 1] = beta_prev; taus[N - 1] = tau_prev; }
+  __syncthreads();
+  // D, R (upper triangle) back to global; Q = H_0 ... H_{N-1} in S0
+  if (tid < NP) {
+    double d = 1.0;
+    if (tid < N) { d = fabs(S1[tid * LD + tid]); if (!(d > 0.0)) d = 1e-300; }
+    dvec[tid] = d;
+  }
+  for (int idx = tid; idx < NP * NP; idx += ST_THREADS) {
+    const int r = idx >> 6, jj = idx & 63;
+    A[idx] = S1[r * LD + jj];
+    S0[r * LD + jj] = (r == jj) ? 1.0 : 0.0;
+  }
+  __syncthreads();
+  double* qcol_c = S0 + r_lo * LD + c;
+  for (int j = N - 1; j >= 0; --j) {
+    const double tau = taus[j];
+    const bool mine = (c >= j && c < N);
+    const int lo = max(0, j - r_lo), hi = min(16, N - r_lo);      // rows j .. N-1 of this quarter
+    const bool work = (lo < hi) && mine && (tau != 0.0);
+    double vj[16], qc[16];
+    if (work) {
+      const double* col_j = S1 + r_lo * LD + j;
+      double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+      for (int rr = 0; rr < 16; ++rr) {
+        const bool on = (rr >= lo) && (rr < hi);
+        vj[rr] = on ? ((r_lo + rr == j) ? 1.0 : col_j[rr * LD]) : 0.0;
+        qc[rr] = on ? qcol_c[rr * LD] : 0.0;
+      }
+#pragma unroll
+      for (int rr = 0; rr < 16; rr += 2) { s0 = fma(vj[rr], qc[rr], s0); s1 = fma(vj[rr + 1], qc[rr + 1], s1); }
+      red[q * NP + c] = s0 + s1;
+    } else {
+      red[q * NP + c] = 0.0;
+    }
+    __syncthreads();
+    if (work) {
+      const double tw = tau * (red[c] + red[NP + c] + red[2 * NP + c] + red[3 * NP + c]);
+#pragma unroll
+      for (int rr = 0; rr < 16; ++rr)
+        if (rr >= lo && rr < hi) qcol_c[rr * LD] = fma(-tw, vj[rr], qc[rr]);
+    }
+    __syncthreads();
+  }
+  for (int idx = tid; idx < NP * NP; idx += ST_THREADS) Q[idx] = S0[(idx >> 6) * LD + (idx & 63)];
 }
 
 // ---- V <- (D^-1 R) P^T V ---------------------------------------------------------------------------------------------
