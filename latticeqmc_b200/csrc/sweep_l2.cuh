@@ -108,17 +108,7 @@ struct L2Epilogue {
   bool add_identity = false;
 };
 
-// FP64 tensor-core MMA, D(8x8) += A(8x4) * B(4x8).  Fragment layout (PTX ISA, mma.m8n8k4 .f64):
-//   a : A[row = lane/4][k = lane%4]      b : B[k = lane%4][col = lane/4]
-//   c0, c1 : C[row = lane/4][col = 2*(lane%4) + {0,1}]
-// On sm_100a DMMA issues to the same FP64 pipe as DFMA (same peak); what it buys is operand traffic: a lane
-// loads 1 double per 8 multiply-adds instead of 1 per <= 2.7 for a 4x8 register-tiled DFMA loop, which is the
-// difference between a shared-memory-bound and an FP64-pipe-bound GEMM (profiles/r01_cfg4_summary.md).
-__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-               : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
-}
-
+// (dmma884, the FP64 tensor-core MMA wrapper, lives in sweep_reg.cuh)
 constexpr int L2_LDA = L2_BM + 4;    // panel row strides = 4 mod 16 doubles: the 4 k-rows a fragment load touches
 constexpr int L2_LDB = L2_BN + 4;    // fall into disjoint bank groups (conflict-free LDS.64)
 

@@ -166,6 +166,69 @@ __device__ __forceinline__ void gemm_kmajor(double (&acc)[C::TR][C::TC], const d
   }
 }
 
+// FP64 tensor-core MMA, D(8x8) += A(8x4) * B(4x8).  Fragment layout (PTX ISA, mma.m8n8k4 .f64):
+//   a : A[row = lane/4][k = lane%4]      b : B[k = lane%4][col = lane/4]
+//   c0, c1 : C[row = lane/4][col = 2*(lane%4) + {0,1}]
+// On sm_100a DMMA issues to the same FP64 pipe as DFMA (same peak); what it buys is operand traffic: a lane
+// loads 1 double per 8 multiply-adds instead of 1 per <= 2.7 for a 4x8 register-tiled DFMA loop, which is the
+// difference between a shared-memory-bound and an FP64-pipe-bound GEMM (profiles/r01_cfg4_summary.md).
+__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+
+
+// ---- NP = 64: the 64 x 64 x 64 GEMMs on DMMA fragments --------------------------------------------------------------
+// One spin group = 128 threads = 4 warps in a 2 x 2 grid of 32 x 32 warp tiles; acc[m][n][s] is element
+// (32 wm + 8 m + lane/4, 32 wn + 8 n + 2 (lane%4) + s).  A is k-major (A[k*lda + row]), B is row-major by k.
+// The register-tiled DFMA loop above needs one shared-memory double per 2.7 FMAs and is LSU-bound (52 % wavefronts at
+// 40 % FP64 pipe, profiles/r01_cfg2_summary.md); a DMMA fragment needs one per 8.
+template <bool GA, bool GB>
+__device__ __forceinline__ void gemm64_dmma(double (&acc)[4][4][2], const double* __restrict__ A, int lda,
+                                            const double* __restrict__ B, int ldb, int wm, int wn, int lr, int lk) {
+  const double* ap = A + lk * lda + 32 * wm + lr;
+  const double* bp = B + lk * ldb + 32 * wn + lr;
+#pragma unroll 4
+  for (int k4 = 0; k4 < 16; ++k4) {
+    double a[4], b[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) a[m] = GA ? __ldg(ap + 4 * k4 * lda + 8 * m) : ap[4 * k4 * lda + 8 * m];
+#pragma unroll
+    for (int n = 0; n < 4; ++n) b[n] = GB ? __ldg(bp + 4 * k4 * ldb + 8 * n) : bp[4 * k4 * ldb + 8 * n];
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+#pragma unroll
+      for (int n = 0; n < 4; ++n) dmma884(acc[m][n], a[m], b[n]);
+  }
+}
+__device__ __forceinline__ void zero_acc(double (&acc)[4][4][2]) {
+#pragma unroll
+  for (int m = 0; m < 4; ++m)
+#pragma unroll
+    for (int n = 0; n < 4; ++n) acc[m][n][0] = acc[m][n][1] = 0.0;
+}
+// fragment tile -> shared, row-major M[row][col] / transposed M[col][row], row stride S; element scaled by rs[m] * cs[n][s]
+template <int S, bool TRANSPOSED, bool ADD_ID>
+__device__ __forceinline__ void store_acc(double* M, const double (&acc)[4][4][2], const double (&rs)[4], const double (&cs)[4][2],
+                                          int wm, int wn, int lr, int lk) {
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    const int row = 32 * wm + 8 * m + lr;
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      const int col0 = 32 * wn + 8 * n + 2 * lk;
+      double v0 = acc[m][n][0] * rs[m] * cs[n][0], v1 = acc[m][n][1] * rs[m] * cs[n][1];
+      if (ADD_ID) { if (row == col0) v0 += 1.0; if (row == col0 + 1) v1 += 1.0; }
+      if (!TRANSPOSED) {
+        *reinterpret_cast<double2*>(M + row * S + col0) = make_double2(v0, v1);
+      } else {
+        M[col0 * S + row] = v0;
+        M[(col0 + 1) * S + row] = v1;
+      }
+    }
+  }
+}
+
 // tile -> shared, row-major M[row][col]
 template <class C>
 __device__ __forceinline__ void store_tile(double* M, const double (&g)[C::TR][C::TC], int ty, int tx) {
@@ -305,6 +368,47 @@ __device__ void recompute_g(double (&g)[C::TR][C::TC], RegSmem<C>& sm, const Swe
   const int L = p.n_slices;
   double* stage = sm.stage + spin * NP * S;
   int l = (l0 - 1 + L) % L;
+  if constexpr (NP == 64) {
+    // DMMA chain: the running product stays in shared memory (k-major), the fragment accumulators never become a tile
+    const int lane = threadIdx.x & 31, w = t >> 5, wm = w >> 1, wn = w & 1, lr = lane >> 2, lk = lane & 3;
+    const double one4[4] = {1.0, 1.0, 1.0, 1.0};
+    {
+      const int8_t* hl = field + l * NP;
+      for (int q = t; q < NP * NP; q += C::TPS) {               // stage[col][row] = E[row][col] * v[col]
+        const int col = q >> 6, row = q & 63;
+        stage[col * S + row] = p.Et[col * NP + row] * hs_v(hl[col], spin, p);
+      }
+    }
+    double acc[4][4][2];
+    for (int m = 1; m < L; ++m) {
+      l = (l0 - 1 - m + 2 * L) % L;
+      __syncthreads();
+      zero_acc(acc);
+      gemm64_dmma<false, true>(acc, stage, S, p.E, NP, wm, wn, lr, lk);
+      const int8_t* hl = field + l * NP;
+      double cs[4][2];
+#pragma unroll
+      for (int n = 0; n < 4; ++n)
+#pragma unroll
+        for (int s2 = 0; s2 < 2; ++s2) cs[n][s2] = hs_v(hl[32 * wn + 8 * n + 2 * lk + s2], spin, p);
+      __syncthreads();                                          // every warp is done reading the old product
+      if (m < L - 1) store_acc<S, true, false>(stage, acc, one4, cs, wm, wn, lr, lk);
+      else store_acc<S, false, true>(stage, acc, one4, cs, wm, wn, lr, lk);
+    }
+    if (L == 1) {
+      // single factor: I + E diag(v), row-major
+      __syncthreads();
+      const int8_t* hl = field + l * NP;
+      for (int q = t; q < NP * NP; q += C::TPS) {
+        const int row = q >> 6, col = q & 63;
+        stage[row * S + col] = p.E[row * NP + col] * hs_v(hl[col], spin, p) + (row == col ? 1.0 : 0.0);
+      }
+    }
+    __syncthreads();
+    gj_inverse<C>(stage, sm, spin, t);
+    load_tile<C>(stage, S, g, ty, tx);
+    return;
+  }
   {
     const int8_t* hl = field + l * NP;
 #pragma unroll
@@ -352,6 +456,37 @@ __device__ void wrap_g(double (&g)[C::TR][C::TC], RegSmem<C>& sm, const SweepPar
   double* stage = sm.stage + spin * NP * S;
   store_tile<C>(stage, g, ty, tx);
   __syncthreads();
+  if constexpr (NP == 64) {
+    const int t = threadIdx.x % C::TPS, lane = threadIdx.x & 31, w = t >> 5, wm = w >> 1, wn = w & 1, lr = lane >> 2, lk = lane & 3;
+    const double one4[4] = {1.0, 1.0, 1.0, 1.0};
+    const double one42[4][2] = {{1.0, 1.0}, {1.0, 1.0}, {1.0, 1.0}, {1.0, 1.0}};
+    double acc[4][4][2];
+    zero_acc(acc);
+    gemm64_dmma<true, false>(acc, PHYS ? p.Eit : p.Et, NP, stage, S, wm, wn, lr, lk);      // T = E G  (or E^-1 G)
+    __syncthreads();
+    store_acc<S, true, false>(stage, acc, one4, one42, wm, wn, lr, lk);                     // k-major for the second product
+    __syncthreads();
+    zero_acc(acc);
+    gemm64_dmma<false, true>(acc, stage, S, PHYS ? p.E : p.Ei, NP, wm, wn, lr, lk);
+    double rs[4], cs[4][2];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const int8_t hr = sm.hn[32 * wm + 8 * m + lr];
+      rs[m] = PHYS ? hs_vinv(hr, spin, p) : hs_v(hr, spin, p);
+    }
+#pragma unroll
+    for (int n = 0; n < 4; ++n)
+#pragma unroll
+      for (int s2 = 0; s2 < 2; ++s2) {
+        const int8_t hc = sm.hn[32 * wn + 8 * n + 2 * lk + s2];
+        cs[n][s2] = PHYS ? hs_v(hc, spin, p) : hs_vinv(hc, spin, p);
+      }
+    __syncthreads();
+    store_acc<S, false, false>(stage, acc, rs, cs, wm, wn, lr, lk);
+    __syncthreads();
+    load_tile<C>(stage, S, g, ty, tx);
+    return;
+  }
   double acc[TR][TC];
   zero_tile<C>(acc);
   gemm_kmajor<C, true, false>(acc, PHYS ? p.Eit : p.Et, NP, stage, S, ty, tx);

@@ -122,3 +122,41 @@ def test_delayed_updates_equal_undelayed_bitwise():
     assert 0.2 < accs.mean() < 0.95
     assert np.array_equal(acc[0, 0, 0], accs) and np.array_equal(ratio[0, 0, 0], ratios)
     assert np.array_equal(out[0], gu) and np.array_equal(out[1], gd)
+
+
+def test_cfg5_slice_is_bit_exact_at_full_size():
+    """BASELINE configs[4] size (24x24, N=576 -> padded 640, U=6, beta=10, L=100; the shared-memory delayed-update path
+    with four entries per thread): from the oracle's sweep-start G, the 576 proposals of the first slice give the
+    oracle's decisions, ratios and - EXACT mode - its G bit for bit; then the wrap within 1e-10."""
+    ham = so.ideal_square_kinetic(24, 1.0, 3.0)
+    n, lt = 576, 100
+    dtau, lamb, exp_k = so.set_beta_constants(ham, 6.0, 10.0, lt)
+    h = so.initial_field(n, lt, seed=11)
+    # a well-scaled stand-in for the sweep-start G (the raw product at beta = 10 is roundoff, SURVEY.md H8): G of the
+    # last 8 slices only, which exercises the same arithmetic on O(1) numbers
+    prod = np.eye(n)
+    for l in range(lt - 8, lt):
+        prod = (exp_k * np.exp(-lamb * h[:, l])[None, :]) @ prod
+    gu = np.linalg.inv(np.eye(n) + prod)
+    prod = np.eye(n)
+    for l in range(lt - 8, lt):
+        prod = (exp_k * np.exp(+lamb * h[:, l])[None, :]) @ prod
+    gd = np.linalg.inv(np.eye(n) + prod)
+    u = np.random.RandomState(5).rand(n)
+    with _engine(exp_k, lamb, lt, trace=True) as eng:
+        assert eng.info()["family"] == "l2" and eng.info()["n_pad"] == 640
+        eng.set_field(h[None])
+        eng.set_g(np.stack([gu, gd])[None])
+        eng.slice(lt - 1, u[None])
+        acc, ratio = eng.get_trace()
+        out = eng.get_g()[0]
+        h_out = eng.get_field()[0]
+        eng.wrap(lt - 1)
+        w = eng.get_g()[0]
+    ratios, accs = so.slice_proposals(gu, gd, h, lt - 1, lamb, u)
+    assert 0.2 < accs.mean() < 0.95
+    assert np.array_equal(acc[0, 0, 0], accs) and np.array_equal(ratio[0, 0, 0], ratios)
+    assert np.array_equal(out[0], gu) and np.array_equal(out[1], gd)
+    assert np.array_equal(h_out, h)
+    wu, wd = so.wrap(gu, gd, h, lt - 1, exp_k, lamb)
+    assert _close(w[0], wu) and _close(w[1], wd)
