@@ -115,6 +115,12 @@ int lqmc_get_trace(lqmc_engine* e, uint8_t* acc, double* ratio);
 int lqmc_get_measurements(lqmc_engine* e, double* g_sum, double* obs_sum, int64_t* n_meas,
                           int64_t* n_accepted);
 int lqmc_reset_measurements(lqmc_engine* e);
+/* Restore accumulators saved with lqmc_get_measurements (same layouts; any pointer may be NULL): the resume half of
+ * checkpoint / resume.  The reference only caches finished beta points (multiprocessing.py:312-333, broken on
+ * numpy >= 1.24: SURVEY.md section 5); the Markov state here is field + sweep counter + accumulators - the Philox
+ * stream is a pure function of (seed, chain, sweep, proposal), so a resumed run repeats the uninterrupted one bit for bit. */
+int lqmc_set_measurements(lqmc_engine* e, const double* g_sum, const double* obs_sum, const int64_t* n_meas,
+                          const int64_t* n_accepted);
 
 /* Raw device pointers, for plumbing that must stay on the device (torch.distributed all-reduce of the
  * accumulators over NCCL, device-side uniforms).  which: 0 field (int8 [chain][slice][NP], slice-major,

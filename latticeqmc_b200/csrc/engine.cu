@@ -770,6 +770,19 @@ int lqmc_get_measurements(lqmc_engine* e, double* g_sum, double* obs_sum, int64_
   return LQMC_OK;
 }
 
+int lqmc_set_measurements(lqmc_engine* e, const double* g_sum, const double* obs_sum, const int64_t* n_meas,
+                          const int64_t* n_accepted) {
+  if (!e) return fail(LQMC_ERR_INVALID, "engine is NULL");
+  CU(cudaSetDevice(e->device));
+  CU(cudaStreamSynchronize(e->stream));
+  const size_t C = e->C, N = e->N;
+  if (g_sum) CU(cudaMemcpy(e->dGsum, g_sum, C * 2 * N * N * sizeof(double), cudaMemcpyHostToDevice));
+  if (obs_sum) CU(cudaMemcpy(e->dObs, obs_sum, C * 3 * N * sizeof(double), cudaMemcpyHostToDevice));
+  if (n_meas) CU(cudaMemcpy(e->dNmeas, n_meas, C * sizeof(long long), cudaMemcpyHostToDevice));
+  if (n_accepted) CU(cudaMemcpy(e->dNacc, n_accepted, C * sizeof(long long), cudaMemcpyHostToDevice));
+  return LQMC_OK;
+}
+
 int lqmc_reset_measurements(lqmc_engine* e) {
   if (!e) return fail(LQMC_ERR_INVALID, "engine is NULL");
   CU(cudaSetDevice(e->device));

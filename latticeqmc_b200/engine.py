@@ -24,6 +24,7 @@ EXPORTS = (
     "lqmc_get_trace", "lqmc_get_measurements", "lqmc_reset_measurements", "lqmc_device_ptr", "lqmc_info",
     "lqmc_set_sweep_counter", "lqmc_set_chain_offset", "lqmc_philox_uniforms", "lqmc_last_error",
     "lqmc_version", "lqmc_selftest_division", "lqmc_recompute_stable", "lqmc_set_stabilization",
+    "lqmc_set_measurements",
 )
 
 
@@ -66,6 +67,7 @@ def load_library(path=None):
     lib.lqmc_get_trace.argtypes = [vp, vp, vp]
     lib.lqmc_get_measurements.argtypes = [vp, vp, vp, vp, vp]
     lib.lqmc_reset_measurements.argtypes = [vp]
+    lib.lqmc_set_measurements.argtypes = [vp, vp, vp, vp, vp]
     lib.lqmc_device_ptr.argtypes = [vp, ctypes.c_int, ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_uint64)]
     lib.lqmc_info.argtypes = [vp, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int64),
                               ctypes.POINTER(ctypes.c_int64), ctypes.c_char_p]
@@ -148,6 +150,7 @@ class SweepEngine:
         self._check(self._lib.lqmc_create(ctypes.byref(self._h), self.device, self.n_sites, self.n_slices,
                                           self.n_chains, exp_k.ctypes.data_as(dp), exp_k_inv.ctypes.data_as(dp),
                                           self.lamb, hs.ctypes.data_as(dp), flags))
+        self._chain_offset = 0
         if chain_offset:
             self.set_chain_offset(chain_offset)
         self.stab_every = 0
@@ -271,6 +274,40 @@ class SweepEngine:
     def reset_measurements(self):
         self._check(self._lib.lqmc_reset_measurements(self._h))
 
+    def set_measurements(self, m):
+        """Restore accumulators from a `get_measurements()` dict."""
+        c, n = self.n_chains, self.n_sites
+        g_sum = np.ascontiguousarray(m["g_sum"], dtype=np.float64).reshape(c, 2, n, n)
+        obs = np.ascontiguousarray(m["obs_sum"], dtype=np.float64).reshape(c, 3, n)
+        n_meas = np.ascontiguousarray(m["n_meas"], dtype=np.int64).reshape(c)
+        n_acc = np.ascontiguousarray(m["n_accepted"], dtype=np.int64).reshape(c)
+        self._check(self._lib.lqmc_set_measurements(self._h, g_sum.ctypes.data, obs.ctypes.data, n_meas.ctypes.data,
+                                                    n_acc.ctypes.data))
+
+    # -- checkpoint / resume -------------------------------------------------------------------
+    def save_checkpoint(self, path, seed=0):
+        """Markov state of every chain as one `.npz`: HS field (int8), global sweep counter, chain offset, RNG seed and
+        the measurement accumulators.  With the device Philox stream (a pure function of seed / chain / sweep /
+        proposal) this is everything: G is rebuilt from the field at the next sweep start."""
+        m = self.get_measurements()
+        info = self.info()
+        np.savez_compressed(path, field=self.get_field(), sweep_counter=np.int64(info["sweep_counter"]),
+                            chain_offset=np.int64(self._chain_offset), seed=np.uint64(seed), n_sites=self.n_sites,
+                            n_slices=self.n_slices, n_chains=self.n_chains, mode=self.mode, stab_every=self.stab_every,
+                            g_sum=m["g_sum"], obs_sum=m["obs_sum"], n_meas=m["n_meas"], n_accepted=m["n_accepted"])
+
+    def load_checkpoint(self, path):
+        """Restore a `save_checkpoint` file into this engine (same lattice size, slices and chain count).  Returns the
+        RNG seed stored with it."""
+        with np.load(path) as z:
+            if (int(z["n_sites"]), int(z["n_slices"]), int(z["n_chains"])) != (self.n_sites, self.n_slices, self.n_chains):
+                raise ValueError("checkpoint does not match this engine's (n_sites, n_slices, n_chains)")
+            self.set_field(z["field"])
+            self.set_sweep_counter(int(z["sweep_counter"]))
+            self.set_chain_offset(int(z["chain_offset"]))
+            self.set_measurements(dict(g_sum=z["g_sum"], obs_sum=z["obs_sum"], n_meas=z["n_meas"], n_accepted=z["n_accepted"]))
+            return int(z["seed"])
+
     def device_ptr(self, which):
         """Raw `(pointer, n_bytes)` of an engine buffer (see lqmc_device_ptr)."""
         ptr = ctypes.c_void_p()
@@ -291,3 +328,4 @@ class SweepEngine:
 
     def set_chain_offset(self, chain0):
         self._check(self._lib.lqmc_set_chain_offset(self._h, int(chain0)))
+        self._chain_offset = int(chain0)

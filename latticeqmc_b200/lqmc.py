@@ -31,7 +31,7 @@ _UNIFORM_CHUNK_BYTES = 256 << 20
 class LatticeQMC:
 
     def __init__(self, model, beta, time_steps, warmup=300, sweeps=2000, det_mode=False, log_lvl=DEBUG,
-                 *, mode="parity", arith="exact", rng="numpy", seed=0, device=0, trace=True):
+                 *, mode="parity", arith="exact", rng="numpy", seed=0, device=0, trace=True, stab_every=0):
         if log_lvl is not None:
             self.logger = get_logger()
             self.logger.setLevel(log_lvl)
@@ -64,6 +64,7 @@ class LatticeQMC:
 
         # engine options (additions; reference defaults unchanged)
         self.mode, self.arith, self.rng, self.seed, self.device, self.trace = mode, arith, rng, seed, device, trace
+        self.stab_every = stab_every        # physics mode: QR/UDV-stabilised G every this many slices (0 = off)
         self._engine = None
 
         self._log_debug(f"u=          {self.model.u}")
@@ -120,7 +121,8 @@ class LatticeQMC:
         """The device engine for the current beta (created on first use; raises without CUDA)."""
         if self._engine is None:
             self._engine = SweepEngine(self.exp_k, self.lamb, self.time_steps, n_chains=1, exp_k_inv=self.exp_k_inv,
-                                       device=self.device, mode=self.mode, arith=self.arith, trace=self.trace)
+                                       device=self.device, mode=self.mode, arith=self.arith, trace=self.trace,
+                                       stab_every=self.stab_every)
         return self._engine
 
     # ------------------------------------------------------------------ inspection helpers (host, O(N^2))

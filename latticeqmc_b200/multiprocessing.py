@@ -240,8 +240,9 @@ class ParallelProcessManager(ProcessManager):
     CORE_COUNT = multiprocessing.cpu_count()
 
     def __init__(self, model, beta, time_steps, warmup=300, det_mode=False, procs=None, *, seeds=None,
-                 rng="numpy", mode="parity", arith="exact", device=None, seed=0):
+                 rng="numpy", mode="parity", arith="exact", device=None, seed=0, stab_every=0):
         super().__init__(procs, model=model, beta=beta, time_steps=time_steps, warmup=warmup, det_mode=det_mode)
+        self.stab_every = stab_every
         if det_mode:
             raise NotImplementedError("det_mode is outside the accelerated hot path (see LatticeQMC)")
         self.seeds = list(seeds) if seeds is not None else [os.getpid() + c for c in range(self.max_procs)]
@@ -295,7 +296,7 @@ class ParallelProcessManager(ProcessManager):
                     done += k
 
             with SweepEngine(exp_k, lamb, lt, n_chains=hi - lo, exp_k_inv=exp_k_inv, device=device, mode=self.mode,
-                             arith=self.arith, chain_offset=lo) as eng:
+                             arith=self.arith, chain_offset=lo, stab_every=self.stab_every) as eng:
                 eng.set_field(fields)
                 batched(eng, warm, False)
                 batched(eng, base, True)
@@ -303,7 +304,7 @@ class ParallelProcessManager(ProcessManager):
                 extra = sweeplist[0] - base
                 if extra and lo == 0:
                     with SweepEngine(exp_k, lamb, lt, n_chains=1, exp_k_inv=exp_k_inv, device=device, mode=self.mode,
-                                     arith=self.arith) as tail:
+                                     arith=self.arith, stab_every=self.stab_every) as tail:
                         tail.set_field(eng.get_field()[:1])
                         tail.set_sweep_counter(warm + base)
                         batched(tail, extra, True, us=lambda k: None if self.rng != "numpy" else

@@ -89,3 +89,38 @@ def compute_pole_gf_tau(ham, beta):
     diag_gf = pole_gf_tau(tau, xi[..., np.newaxis], weights=1, beta=beta)
     gf = reconstruct(rv, diag_gf, rv_inv)
     return tau, np.moveaxis(gf, 0, -1)
+
+
+def chain_statistics(measurements):
+    """Equal-time observables with error bars from independent chains.
+
+    `measurements`: the dict of `SweepEngine.get_measurements()` (per-chain sums over measured sweeps of the site-resolved
+    `n_up`, `n_dn` and the **per-configuration** product `n_up * n_dn`, which the device accumulates; the reference only
+    averages G and factorises afterwards, `tools.py:107-109`, which is wrong for correlated quantities).  Chains are
+    independent Markov chains, so the standard error of the mean over chains is an honest error bar, and a delete-one
+    jackknife over chains gives the error of the non-linear local moment.  Returns
+    `{name: (mean, stderr)}` for `n_up, n_dn, density, docc, moment`, plus `n_chains`, `n_meas`.
+    """
+    obs = np.asarray(measurements["obs_sum"], dtype=np.float64)            # (C, 3, N)
+    n_meas = np.asarray(measurements["n_meas"], dtype=np.float64)
+    keep = n_meas > 0
+    if not keep.any():
+        raise ValueError("no measured sweeps")
+    per_chain = obs[keep].mean(axis=2) / n_meas[keep, None]                  # (C', 3): site-averaged chain means
+    c = per_chain.shape[0]
+
+    def mean_err(x):
+        return float(x.mean()), float(x.std(ddof=1) / np.sqrt(c)) if c > 1 else float("nan")
+
+    n_up, n_dn, docc = per_chain[:, 0], per_chain[:, 1], per_chain[:, 2]
+    out = dict(n_up=mean_err(n_up), n_dn=mean_err(n_dn), density=mean_err(n_up + n_dn), docc=mean_err(docc))
+    moment = n_up + n_dn - 2 * docc
+    if c > 1:
+        total = moment.sum()
+        jack = (total - moment) / (c - 1)                                    # delete-one means
+        out["moment"] = (float(moment.mean()), float(np.sqrt((c - 1) / c * np.sum((jack - jack.mean()) ** 2))))
+    else:
+        out["moment"] = (float(moment.mean()), float("nan"))
+    out["n_chains"] = int(c)
+    out["n_meas"] = int(n_meas[keep].sum())
+    return out

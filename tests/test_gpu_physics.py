@@ -180,3 +180,54 @@ def test_stabilised_physics_agrees_with_ed_at_low_temperature():
     assert abs(docc - exact["docc"]) < 0.015 + 4 * err[2]
     moment = n_up + n_dn - 2 * docc
     assert abs(moment - exact["moment"]) < 0.03 + 8 * err.max()
+
+
+def test_checkpoint_resume_repeats_the_uninterrupted_run(tmp_path):
+    """field + sweep counter + accumulators is the whole Markov state with the device Philox stream; a run
+    resumed in a fresh engine is bit-identical to the uninterrupted one (field, G, accumulators)."""
+    from latticeqmc_b200 import SweepEngine
+    ham, lamb, exp_k, exp_k_inv = _setup(4.0, 2.0, 20)
+    n, lt, chains, seed = 4, 20, 5, 4242
+    fields = np.stack([so.initial_field(n, lt, 60 + c) for c in range(chains)])
+    kw = dict(n_chains=chains, exp_k_inv=exp_k_inv, mode="physics", stab_every=5, chain_offset=3)
+    with SweepEngine(exp_k, lamb, lt, **kw) as eng:
+        eng.set_field(fields)
+        eng.sweep(3, None, seed=seed)
+        eng.sweep(4, None, seed=seed, measure=True)
+        ref_field, ref_g, ref_m = eng.get_field(), eng.get_g(), eng.get_measurements()
+    path = str(tmp_path / "state.npz")
+    with SweepEngine(exp_k, lamb, lt, **kw) as eng:
+        eng.set_field(fields)
+        eng.sweep(3, None, seed=seed)
+        eng.sweep(2, None, seed=seed, measure=True)
+        eng.save_checkpoint(path, seed=seed)
+    with SweepEngine(exp_k, lamb, lt, n_chains=chains, exp_k_inv=exp_k_inv, mode="physics", stab_every=5) as eng:
+        assert eng.load_checkpoint(path) == seed
+        assert eng.info()["sweep_counter"] == 5
+        eng.sweep(2, None, seed=seed, measure=True)
+        f, g, m = eng.get_field(), eng.get_g(), eng.get_measurements()
+    assert np.array_equal(f, ref_field) and np.array_equal(g, ref_g)
+    for key in ("g_sum", "obs_sum", "n_meas", "n_accepted"):
+        assert np.array_equal(m[key], ref_m[key]), key
+
+
+def test_chain_statistics_on_device_accumulators():
+    """Error bars from `chain_statistics` on a real run: ED values inside mean +- 4 sigma + Trotter error."""
+    from latticeqmc_b200 import SweepEngine
+    from latticeqmc_b200.tools import chain_statistics
+    ham, lamb, exp_k, exp_k_inv = _setup(4.0, 2.0, 20)
+    hop = ham.copy()
+    np.fill_diagonal(hop, 0.0)
+    exact = ed.thermal_observables(hop, 4.0, 2.0, 2.0)
+    chains = 256
+    fields = np.stack([so.initial_field(4, 20, 300 + c) for c in range(chains)])
+    with SweepEngine(exp_k, lamb, 20, n_chains=chains, exp_k_inv=exp_k_inv, mode="physics", arith="fma") as eng:
+        eng.set_field(fields)
+        eng.sweep(40, None, seed=5)
+        eng.sweep(100, None, seed=5, measure=True)
+        st = chain_statistics(eng.get_measurements())
+    assert st["n_chains"] == chains and st["n_meas"] == chains * 100
+    assert 0 < st["docc"][1] < 5e-3 and 0 < st["moment"][1] < 1e-2
+    assert abs(st["density"][0] - 1.0) < 0.01 + 4 * st["density"][1]
+    assert abs(st["docc"][0] - exact["docc"]) < 0.01 + 4 * st["docc"][1]
+    assert abs(st["moment"][0] - exact["moment"]) < 0.02 + 4 * st["moment"][1]

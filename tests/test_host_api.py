@@ -66,3 +66,25 @@ def test_tools_observables():
     tau, gf = compute_pole_gf_tau(ham, 2.0)
     from scipy.linalg import expm
     assert np.allclose(-gf[:, :, 0], np.linalg.inv(np.eye(6) + expm(-2.0 * ham)), atol=1e-12)
+
+
+def test_chain_statistics_error_bars():
+    """`chain_statistics`: means and chain-to-chain standard errors of the device accumulators."""
+    import numpy as np
+    from latticeqmc_b200.tools import chain_statistics
+    rs = np.random.RandomState(0)
+    chains, n, meas = 400, 6, 25
+    # per-chain means scatter around (0.5, 0.5, 0.1) with known spreads
+    base = np.stack([0.5 + 0.02 * rs.randn(chains), 0.5 + 0.02 * rs.randn(chains), 0.1 + 0.01 * rs.randn(chains)], axis=1)
+    obs = base[:, :, None] * meas * np.ones((1, 1, n))
+    m = dict(obs_sum=obs, n_meas=np.full(chains, meas), n_accepted=np.zeros(chains, dtype=np.int64))
+    st = chain_statistics(m)
+    assert st["n_chains"] == chains and st["n_meas"] == chains * meas
+    assert abs(st["n_up"][0] - 0.5) < 4 * st["n_up"][1] and abs(st["n_up"][1] - 0.02 / np.sqrt(chains)) < 3e-4
+    assert abs(st["docc"][0] - 0.1) < 4 * st["docc"][1]
+    mom = base[:, 0] + base[:, 1] - 2 * base[:, 2]
+    assert abs(st["moment"][0] - mom.mean()) < 1e-12
+    assert abs(st["moment"][1] - mom.std(ddof=1) / np.sqrt(chains)) < 1e-12        # jackknife of a mean = standard error
+    # chains without measurements are ignored
+    m["n_meas"][:10] = 0
+    assert chain_statistics(m)["n_chains"] == chains - 10
