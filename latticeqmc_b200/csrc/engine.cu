@@ -49,6 +49,8 @@ struct lqmc_engine {
   // device state
   double *dE = nullptr, *dEt = nullptr, *dEi = nullptr, *dEit = nullptr;
   int8_t* dField = nullptr;
+  int8_t* dFieldRaw = nullptr;     // [chain][site][slice]: the host layout, converted on the device
+  int* dBad = nullptr;
   double* dG = nullptr;
   double* dGsum = nullptr;
   double* dObs = nullptr;
@@ -83,6 +85,46 @@ struct lqmc_engine {
 };
 
 namespace {
+
+// host layout [chain][site][slice]  <->  device layout [chain][slice][NP] (pad = +1); one CTA per (chain, 32-slice block)
+__global__ void field_to_device_kernel(const int8_t* __restrict__ raw, int8_t* __restrict__ dev, int N, int L, int NP, int* bad) {
+  __shared__ int8_t tile[32][33];
+  const int c = blockIdx.y, l0 = blockIdx.x * 32;
+  const int8_t* src = raw + (size_t)c * N * L;
+  int8_t* dst = dev + (size_t)c * L * NP;
+  for (int i0 = 0; i0 < NP; i0 += 32) {
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+      const int i = i0 + r, l = l0 + threadIdx.x;
+      int8_t v = 1;
+      if (i < N && l < L) { v = src[(size_t)i * L + l]; if (v != 1 && v != -1) atomicExch(bad, 1 + (int)(((size_t)c * N + i) * L + l)); }
+      tile[r][threadIdx.x] = v;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+      const int l = l0 + r, i = i0 + threadIdx.x;
+      if (l < L && i < NP) dst[(size_t)l * NP + i] = tile[threadIdx.x][r];
+    }
+    __syncthreads();
+  }
+}
+__global__ void field_to_host_kernel(const int8_t* __restrict__ dev, int8_t* __restrict__ raw, int N, int L, int NP) {
+  __shared__ int8_t tile[32][33];
+  const int c = blockIdx.y, l0 = blockIdx.x * 32;
+  const int8_t* src = dev + (size_t)c * L * NP;
+  int8_t* dst = raw + (size_t)c * N * L;
+  for (int i0 = 0; i0 < N; i0 += 32) {
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+      const int l = l0 + r, i = i0 + threadIdx.x;
+      tile[r][threadIdx.x] = (l < L && i < NP) ? src[(size_t)l * NP + i] : (int8_t)1;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+      const int i = i0 + r, l = l0 + threadIdx.x;
+      if (i < N && l < L) dst[(size_t)i * L + l] = tile[threadIdx.x][r];
+    }
+    __syncthreads();
+  }
+}
 
 size_t field_bytes(const lqmc_engine* e) { return (size_t)e->C * e->L * e->NP; }
 size_t g_elems(const lqmc_engine* e) { return (size_t)e->C * 2 * e->NP * e->NP; }
@@ -553,6 +595,7 @@ int lqmc_create(lqmc_engine** out, int device, int n_sites, int n_slices, int n_
   }
   const size_t nG = g_elems(e);
   if (cudaMalloc(&e->dField, field_bytes(e)) != cudaSuccess || cudaMalloc(&e->dG, nG * sizeof(double)) != cudaSuccess ||
+      cudaMalloc(&e->dFieldRaw, (size_t)e->C * N * e->L) != cudaSuccess || cudaMalloc(&e->dBad, sizeof(int)) != cudaSuccess ||
       cudaMalloc(&e->dGsum, (size_t)e->C * 2 * N * N * sizeof(double)) != cudaSuccess ||
       cudaMalloc(&e->dObs, (size_t)e->C * 3 * N * sizeof(double)) != cudaSuccess ||
       cudaMalloc(&e->dNmeas, (size_t)e->C * sizeof(long long)) != cudaSuccess ||
@@ -575,7 +618,7 @@ int lqmc_create(lqmc_engine** out, int device, int n_sites, int n_slices, int n_
 void lqmc_destroy(lqmc_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
-  void* ptrs[] = {e->dE, e->dEt, e->dEi, e->dEit, e->dField, e->dG, e->dGsum, e->dObs, e->dNmeas, e->dNacc, e->dUni, e->dTrRatio, e->dTrAcc};
+  void* ptrs[] = {e->dE, e->dEt, e->dEi, e->dEit, e->dField, e->dFieldRaw, e->dBad, e->dG, e->dGsum, e->dObs, e->dNmeas, e->dNacc, e->dUni, e->dTrRatio, e->dTrAcc};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   lqmc::l2_free(e->l2);
@@ -590,16 +633,21 @@ int lqmc_set_field(lqmc_engine* e, const int8_t* field) {
   if (!e || !field) return fail(LQMC_ERR_INVALID, "engine or field is NULL");
   CU(cudaSetDevice(e->device));
   const int N = e->N, L = e->L, NP = e->NP;
-  memset(e->hostField, 1, field_bytes(e));
-  for (int c = 0; c < e->C; ++c)
-    for (int i = 0; i < N; ++i)
-      for (int l = 0; l < L; ++l) {
-        const int8_t v = field[((size_t)c * N + i) * L + l];
-        if (v != 1 && v != -1) return fail(LQMC_ERR_INVALID, "field[%d][%d][%d] = %d is not +-1", c, i, l, (int)v);
-        e->hostField[((size_t)c * L + l) * NP + i] = v;
-      }
-  CU(cudaMemcpyAsync(e->dField, e->hostField, field_bytes(e), cudaMemcpyHostToDevice, e->stream));
+  // raw upload, layout conversion and the +-1 check on the device (a scalar host loop over C*N*L bytes cost more than the copy)
+  const size_t raw_bytes = (size_t)e->C * N * L;
+  memcpy(e->hostField, field, raw_bytes);
+  CU(cudaMemcpyAsync(e->dFieldRaw, e->hostField, raw_bytes, cudaMemcpyHostToDevice, e->stream));
+  CU(cudaMemsetAsync(e->dBad, 0, sizeof(int), e->stream));
+  field_to_device_kernel<<<dim3((L + 31) / 32, e->C), dim3(32, 8), 0, e->stream>>>(e->dFieldRaw, e->dField, N, L, NP, e->dBad);
+  CU(cudaGetLastError());
+  int bad = 0;
+  CU(cudaMemcpyAsync(&bad, e->dBad, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
   CU(cudaStreamSynchronize(e->stream));
+  if (bad) {
+    const size_t idx = (size_t)bad - 1;
+    return fail(LQMC_ERR_INVALID, "field[%zu][%zu][%zu] = %d is not +-1", idx / ((size_t)N * L), (idx / L) % N, idx % L,
+                (int)field[idx]);
+  }
   return LQMC_OK;
 }
 
@@ -607,11 +655,12 @@ int lqmc_get_field(lqmc_engine* e, int8_t* field) {
   if (!e || !field) return fail(LQMC_ERR_INVALID, "engine or field is NULL");
   CU(cudaSetDevice(e->device));
   const int N = e->N, L = e->L, NP = e->NP;
-  CU(cudaMemcpyAsync(e->hostField, e->dField, field_bytes(e), cudaMemcpyDeviceToHost, e->stream));
+  const size_t raw_bytes = (size_t)e->C * N * L;
+  field_to_host_kernel<<<dim3((L + 31) / 32, e->C), dim3(32, 8), 0, e->stream>>>(e->dField, e->dFieldRaw, N, L, NP);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(e->hostField, e->dFieldRaw, raw_bytes, cudaMemcpyDeviceToHost, e->stream));
   CU(cudaStreamSynchronize(e->stream));
-  for (int c = 0; c < e->C; ++c)
-    for (int i = 0; i < N; ++i)
-      for (int l = 0; l < L; ++l) field[((size_t)c * N + i) * L + l] = e->hostField[((size_t)c * L + l) * NP + i];
+  memcpy(field, e->hostField, raw_bytes);
   return LQMC_OK;
 }
 
@@ -619,13 +668,19 @@ int lqmc_set_g(lqmc_engine* e, const double* g) {
   if (!e || !g) return fail(LQMC_ERR_INVALID, "engine or g is NULL");
   CU(cudaSetDevice(e->device));
   const int N = e->N, NP = e->NP;
-  memset(e->hostG, 0, g_elems(e) * sizeof(double));
-  for (size_t m = 0; m < (size_t)e->C * 2; ++m) {
-    double* dst = e->hostG + m * NP * NP;
-    for (int i = 0; i < NP; ++i) dst[(size_t)i * NP + i] = 1.0;
-    for (int i = 0; i < N; ++i) memcpy(dst + (size_t)i * NP, g + (m * N + i) * N, sizeof(double) * N);
+  const size_t mats = (size_t)e->C * 2;
+  if (N != NP) {
+    // identity padding first, then the N x N blocks (strided copy straight from the caller's buffer)
+    memset(e->hostG, 0, g_elems(e) * sizeof(double));
+    for (size_t m = 0; m < mats; ++m)
+      for (int i = N; i < NP; ++i) e->hostG[m * NP * NP + (size_t)i * NP + i] = 1.0;
+    CU(cudaMemcpyAsync(e->dG, e->hostG, g_elems(e) * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    for (size_t m = 0; m < mats; ++m)
+      CU(cudaMemcpy2DAsync(e->dG + m * NP * NP, (size_t)NP * sizeof(double), g + m * N * N, (size_t)N * sizeof(double),
+                           (size_t)N * sizeof(double), N, cudaMemcpyHostToDevice, e->stream));
+  } else {
+    CU(cudaMemcpyAsync(e->dG, g, g_elems(e) * sizeof(double), cudaMemcpyHostToDevice, e->stream));
   }
-  CU(cudaMemcpyAsync(e->dG, e->hostG, g_elems(e) * sizeof(double), cudaMemcpyHostToDevice, e->stream));
   CU(cudaStreamSynchronize(e->stream));
   return LQMC_OK;
 }
@@ -634,10 +689,16 @@ int lqmc_get_g(lqmc_engine* e, double* g) {
   if (!e || !g) return fail(LQMC_ERR_INVALID, "engine or g is NULL");
   CU(cudaSetDevice(e->device));
   const int N = e->N, NP = e->NP;
-  CU(cudaMemcpyAsync(e->hostG, e->dG, g_elems(e) * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  const size_t mats = (size_t)e->C * 2;
+  if (N != NP) {
+    for (size_t m = 0; m < mats; ++m)
+      CU(cudaMemcpy2DAsync(g + m * N * N, (size_t)N * sizeof(double), e->dG + m * NP * NP, (size_t)NP * sizeof(double),
+                           (size_t)N * sizeof(double), N, cudaMemcpyDeviceToHost, e->stream));
+  } else {
+    // no padding: one copy straight into the caller's buffer (no staging pass on the host)
+    CU(cudaMemcpyAsync(g, e->dG, g_elems(e) * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  }
   CU(cudaStreamSynchronize(e->stream));
-  for (size_t m = 0; m < (size_t)e->C * 2; ++m)
-    for (int i = 0; i < N; ++i) memcpy(g + (m * N + i) * N, e->hostG + m * NP * NP + (size_t)i * NP, sizeof(double) * N);
   return LQMC_OK;
 }
 

@@ -191,8 +191,13 @@ class SweepEngine:
         f = np.ascontiguousarray(field, dtype=np.int8).reshape(self.n_chains, self.n_sites, self.n_slices)
         self._check(self._lib.lqmc_set_field(self._h, f.ctypes.data))
 
-    def get_field(self):
-        out = np.empty((self.n_chains, self.n_sites, self.n_slices), dtype=np.int8)
+    def get_field(self, out=None):
+        """`out`: optional preallocated C-contiguous int8 `(n_chains, N, L)` array (e.g. a view of pinned memory)."""
+        shape = (self.n_chains, self.n_sites, self.n_slices)
+        if out is None:
+            out = np.empty(shape, dtype=np.int8)
+        elif out.dtype != np.int8 or out.shape != shape or not out.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous int8 array of shape (n_chains, N, L)")
         self._check(self._lib.lqmc_get_field(self._h, out.ctypes.data))
         return out
 
@@ -200,8 +205,14 @@ class SweepEngine:
         g = np.ascontiguousarray(g, dtype=np.float64).reshape(self.n_chains, 2, self.n_sites, self.n_sites)
         self._check(self._lib.lqmc_set_g(self._h, g.ctypes.data))
 
-    def get_g(self):
-        out = np.empty((self.n_chains, 2, self.n_sites, self.n_sites), dtype=np.float64)
+    def get_g(self, out=None):
+        """`(gf_up, gf_dn)` of every chain, `(n_chains, 2, N, N)`.  `out`: optional preallocated C-contiguous float64
+        array of that shape; page-locked memory makes the device->host copy a straight DMA."""
+        shape = (self.n_chains, 2, self.n_sites, self.n_sites)
+        if out is None:
+            out = np.empty(shape, dtype=np.float64)
+        elif out.dtype != np.float64 or out.shape != shape or not out.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous float64 array of shape (n_chains, 2, N, N)")
         self._check(self._lib.lqmc_get_g(self._h, out.ctypes.data))
         return out
 
