@@ -103,6 +103,17 @@ int lqmc_sweep_async(lqmc_engine* e, int n_sweeps, const double* d_uniforms, uin
                      void* stream);
 int lqmc_sync(lqmc_engine* e);
 
+/* det mode: n_sweeps x LatticeQMC._update_step_det (lqmc.py:236-259), the reference's slow validation sampler -
+ * every proposal flips h[i,l], rebuilds get_m(l, +-1) from the field, and accepts on
+ * u <= det(M_up) det(M_dn) / old_det (un-flipping on reject).  One call is one of the reference's loops:
+ * old_det is initialised from get_m(0, +-1) at the start of the call (warmup_loop_det lqmc.py:261-270;
+ * measure_loop_det :272-299) and carried through the n_sweeps sweeps; with measure != 0, inv(get_m(0, +-1)) is
+ * added to the accumulators after every sweep (lqmc.py:293-297).  uniforms / seed / trace as in lqmc_sweep.
+ * Independent of the engine's mode flag.  N <= 64 (LQMC_ERR_UNSUPPORTED above): it is a validation tool. */
+int lqmc_sweep_det(lqmc_engine* e, int n_sweeps, const double* uniforms, uint64_t seed, int measure);
+/* old_det of every chain after the last lqmc_sweep_det (what _update_step_det returns, lqmc.py:259): f64 [chain]. */
+int lqmc_get_det(lqmc_engine* e, double* det_old);
+
 /* Per-proposal record of the last lqmc_sweep / lqmc_slice call (needs LQMC_TRACE): what the
  * reference exposes as self.ratio / self.acc and logs through _debug (lqmc.py:217-232,316-317).
  * acc: u8 [chain][sweep][step][site]; ratio: f64, same shape.  Either pointer may be NULL. */

@@ -16,6 +16,7 @@
 #include "sweep_reg.cuh"
 #include "sweep_l2.cuh"
 #include "stab.cuh"
+#include "sweep_det.cuh"
 
 namespace {
 
@@ -56,6 +57,7 @@ struct lqmc_engine {
   double* dObs = nullptr;
   long long* dNmeas = nullptr;
   long long* dNacc = nullptr;
+  double* dDetOld = nullptr;       // det mode: old_det per chain (lqmc.py:236-259)
   double* dUni = nullptr;   size_t uniCap = 0;     // staged host uniforms
   double* dTrRatio = nullptr; uint8_t* dTrAcc = nullptr; size_t trCap = 0; size_t trCount = 0;
   lqmc::L2Workspace l2;
@@ -618,7 +620,7 @@ int lqmc_create(lqmc_engine** out, int device, int n_sites, int n_slices, int n_
 void lqmc_destroy(lqmc_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
-  void* ptrs[] = {e->dE, e->dEt, e->dEi, e->dEit, e->dField, e->dFieldRaw, e->dBad, e->dG, e->dGsum, e->dObs, e->dNmeas, e->dNacc, e->dUni, e->dTrRatio, e->dTrAcc};
+  void* ptrs[] = {e->dE, e->dEt, e->dEi, e->dEit, e->dField, e->dFieldRaw, e->dBad, e->dG, e->dGsum, e->dObs, e->dNmeas, e->dNacc, e->dUni, e->dTrRatio, e->dTrAcc, e->dDetOld};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   lqmc::l2_free(e->l2);
@@ -807,6 +809,62 @@ int lqmc_sweep(lqmc_engine* e, int n_sweeps, const double* uniforms, uint64_t se
   int rc = lqmc_sweep_async(e, n_sweeps, d_u, seed, measure, e->stream);
   if (rc) return rc;
   CU(cudaStreamSynchronize(e->stream));
+  return LQMC_OK;
+}
+
+int lqmc_sweep_det(lqmc_engine* e, int n_sweeps, const double* uniforms, uint64_t seed, int measure) {
+  if (!e) return fail(LQMC_ERR_INVALID, "engine is NULL");
+  if (n_sweeps < 0) return fail(LQMC_ERR_INVALID, "n_sweeps = %d is negative", n_sweeps);
+  if (n_sweeps == 0) return LQMC_OK;
+  if (e->N > lqmc::DET_MAX_N)
+    return fail(LQMC_ERR_UNSUPPORTED, "det mode keeps its matrices in shared memory: N = %d > %d", e->N, lqmc::DET_MAX_N);
+  const size_t smem = lqmc::det_smem_bytes(e->N, e->L);
+  if (smem > 227 * 1024) return fail(LQMC_ERR_UNSUPPORTED, "det mode needs %zu bytes of shared memory (N = %d, L = %d)", smem, e->N, e->L);
+  CU(cudaSetDevice(e->device));
+  cudaStream_t s = e->stream;
+  if (!e->dDetOld) CU(cudaMalloc(&e->dDetOld, (size_t)e->C * sizeof(double)));
+  const double* d_u = nullptr;
+  if (uniforms) {
+    int rc = stage_uniforms(e, uniforms, (size_t)e->C * n_sweeps * e->L * e->N, s);
+    if (rc) return rc;
+    d_u = e->dUni;
+  }
+  int rc = ensure_trace(e, (size_t)e->C * n_sweeps * e->L * e->N);
+  if (rc) return rc;
+  CU(cudaFuncSetAttribute(lqmc::sweep_det_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  lqmc::DetParams p;
+  memset(&p, 0, sizeof(p));
+  p.n_sites = e->N; p.n_slices = e->L; p.NPf = e->NP; p.ldE = e->NP;
+  p.E = e->dE; p.field = e->dField; p.uniforms = d_u; p.seed = seed; p.chain0 = e->chain0;
+  p.buf_sweeps = n_sweeps; p.det_old = e->dDetOld; p.n_acc = e->dNacc;
+  if (e->flags & LQMC_TRACE) { p.tr_ratio = e->dTrRatio; p.tr_acc = e->dTrAcc; }
+  p.exp_pl = e->hs[0]; p.exp_ml = e->hs[1];
+  // measured: one launch per sweep, each followed by G = inv(get_m(0)) + accumulation (the sweep kernels' recompute);
+  // unmeasured: all sweeps in one launch
+  const int per_launch = measure ? 1 : n_sweeps;
+  for (int s0 = 0; s0 < n_sweeps; s0 += per_launch) {
+    p.n_sweeps = per_launch; p.buf_sweep0 = s0; p.sweep0 = e->sweep_counter + s0; p.init_det = (s0 == 0);
+    lqmc::sweep_det_kernel<<<e->C, lqmc::DET_THREADS, smem, s>>>(p);
+    CU(cudaGetLastError());
+    e->launches += 1;
+    if (measure) {
+      RunSpec r;
+      r.recompute = true; r.l0 = 0; r.measure = true;
+      rc = run(e, r, s);
+      if (rc) return rc;
+    }
+  }
+  e->sweep_counter += n_sweeps;
+  CU(cudaStreamSynchronize(s));
+  return LQMC_OK;
+}
+
+int lqmc_get_det(lqmc_engine* e, double* det_old) {
+  if (!e || !det_old) return fail(LQMC_ERR_INVALID, "engine or det_old is NULL");
+  if (!e->dDetOld) return fail(LQMC_ERR_INVALID, "no det-mode sweep has run on this engine");
+  CU(cudaSetDevice(e->device));
+  CU(cudaStreamSynchronize(e->stream));
+  CU(cudaMemcpy(det_old, e->dDetOld, (size_t)e->C * sizeof(double), cudaMemcpyDeviceToHost));
   return LQMC_OK;
 }
 

@@ -24,7 +24,7 @@ EXPORTS = (
     "lqmc_get_trace", "lqmc_get_measurements", "lqmc_reset_measurements", "lqmc_device_ptr", "lqmc_info",
     "lqmc_set_sweep_counter", "lqmc_set_chain_offset", "lqmc_philox_uniforms", "lqmc_last_error",
     "lqmc_version", "lqmc_selftest_division", "lqmc_recompute_stable", "lqmc_set_stabilization",
-    "lqmc_set_measurements",
+    "lqmc_set_measurements", "lqmc_sweep_det", "lqmc_get_det",
 )
 
 
@@ -62,6 +62,8 @@ def load_library(path=None):
     lib.lqmc_slice.argtypes = [vp, ctypes.c_int, vp, ctypes.c_uint64]
     lib.lqmc_wrap.argtypes = [vp, ctypes.c_int]
     lib.lqmc_sweep.argtypes = [vp, ctypes.c_int, vp, ctypes.c_uint64, ctypes.c_int]
+    lib.lqmc_sweep_det.argtypes = [vp, ctypes.c_int, vp, ctypes.c_uint64, ctypes.c_int]
+    lib.lqmc_get_det.argtypes = [vp, vp]
     lib.lqmc_sweep_async.argtypes = [vp, ctypes.c_int, vp, ctypes.c_uint64, ctypes.c_int, vp]
     lib.lqmc_sync.argtypes = [vp]
     lib.lqmc_get_trace.argtypes = [vp, vp, vp]
@@ -249,6 +251,23 @@ class SweepEngine:
             ptr = u.ctypes.data
         self._check(self._lib.lqmc_sweep(self._h, int(n_sweeps), ptr, int(seed), int(bool(measure))))
         self._last_trace_shape = (self.n_chains, int(n_sweeps), self.n_slices, self.n_sites)
+
+    def sweep_det(self, n_sweeps=1, uniforms=None, seed=0, measure=False):
+        """`n_sweeps` x `LatticeQMC._update_step_det` (lqmc.py:236-259) as one of the reference's det-mode loops:
+        `old_det` from `get_m(0, +-1)` at the start of the call; `measure` adds `inv(get_m(0, +-1))` after every sweep
+        (lqmc.py:293-297).  `uniforms` as in `sweep`.  N <= 64."""
+        ptr = None
+        if uniforms is not None:
+            u = np.ascontiguousarray(uniforms, dtype=np.float64).reshape(self.n_chains, n_sweeps, self.n_slices, self.n_sites)
+            ptr = u.ctypes.data
+        self._check(self._lib.lqmc_sweep_det(self._h, int(n_sweeps), ptr, int(seed), int(bool(measure))))
+        self._last_trace_shape = (self.n_chains, int(n_sweeps), self.n_slices, self.n_sites)
+
+    def get_det(self):
+        """`old_det` of every chain after the last `sweep_det` (the return value of `_update_step_det`, lqmc.py:259)."""
+        out = np.empty(self.n_chains, dtype=np.float64)
+        self._check(self._lib.lqmc_get_det(self._h, out.ctypes.data))
+        return out
 
     def sweep_async(self, n_sweeps=1, d_uniforms=0, seed=0, measure=False, stream=0):
         """Device-resident variant: `d_uniforms` is a raw device pointer (0 = Philox), `stream` a raw

@@ -13,8 +13,11 @@ numbers as N*L successive `np.random.rand()` calls - so a seeded drop-in run wal
 same accept/reject sequence as the reference.  `rng="philox"` uses the device counter-based stream
 instead (no host traffic).
 
-`det_mode=True` (the reference's O(L N^3)-per-proposal validation sampler, lqmc.py:236-299) is not
-part of the accelerated path and is not provided here; `oracle/` holds CPU validation code.
+`det_mode=True` (the reference's validation sampler, lqmc.py:236-299: every proposal rebuilds `get_m(l, +-1)` and
+takes two determinants) runs on the device too (`SweepEngine.sweep_det`, `csrc/sweep_det.cuh`; N <= 64).  One
+`warmup_loop_det` / `measure_loop_det` call is one engine call, so `old_det` is initialised from `get_m(0, +-1)` at the
+start of each loop and carried through it exactly as in the reference (loops longer than 256 MiB of uniforms are split,
+and `old_det` is re-initialised from the field at the split).
 """
 import time
 
@@ -38,9 +41,6 @@ class LatticeQMC:
             self._log_debug("INIT")
         else:
             self.logger = None
-        if det_mode:
-            raise NotImplementedError("det_mode (lqmc.py:236-299) is the reference's slow validation sampler and is "
-                                      "outside the accelerated hot path; see oracle/ for CPU validation code")
         if rng not in ("numpy", "philox"):
             raise ValueError("rng must be 'numpy' or 'philox'")
         self.model = model
@@ -166,7 +166,7 @@ class LatticeQMC:
             return None
         return np.random.rand(n_sweeps * self.time_steps * self.n_sites).reshape(1, n_sweeps, self.time_steps, self.n_sites)
 
-    def _run_sweeps(self, n_sweeps, measure):
+    def _run_sweeps(self, n_sweeps, measure, det=False):
         eng = self.engine
         eng.set_field(self.config.config[None])
         per_sweep = self.time_steps * self.n_sites * 8
@@ -174,7 +174,7 @@ class LatticeQMC:
         done = 0
         while done < n_sweeps:
             k = min(chunk, n_sweeps - done)
-            eng.sweep(k, self._draw_uniforms(k), seed=self.seed, measure=measure)
+            (eng.sweep_det if det else eng.sweep)(k, self._draw_uniforms(k), seed=self.seed, measure=measure)
             done += k
         self.config.config[...] = eng.get_field()[0]
         if self.trace and n_sweeps:
@@ -217,7 +217,38 @@ class LatticeQMC:
         return dict(n_up=m["obs_sum"][:, 0] / n, n_dn=m["obs_sum"][:, 1] / n, docc=m["obs_sum"][:, 2] / n,
                     n_meas=m["n_meas"].copy(), n_accepted=m["n_accepted"].copy())
 
+    # ------------------------------------------------------------------ det mode (lqmc.py:236-299)
+    def _update_step_det(self, old_det=None):
+        """One det-mode sweep on the device (lqmc.py:236-259); returns the new `old_det`.  The engine starts the call
+        from `det(get_m(0, +1)) * det(get_m(0, -1))` of the current field, which is what the reference's loops pass
+        in for their first sweep; `old_det` is accepted for signature compatibility."""
+        self._run_sweeps(1, measure=False, det=True)
+        return float(self.engine.get_det()[0])
+
+    def warmup_loop_det(self):
+        self.status = "Warmup"
+        self._log_debug(self.status.upper())
+        self._run_sweeps(self.warm_sweeps, measure=False, det=True)
+        self.it = max(self.warm_sweeps - 1, 0)
+        self._log_debug("END " + self.status.upper())
+
+    def measure_loop_det(self):
+        """Mean of `inv(get_m(0, +-1))` after each of `meas_sweeps` det-mode sweeps, `(2, N, N)` (lqmc.py:272-299)."""
+        self.status = "Measurement"
+        self._log_debug(self.status.upper())
+        eng = self.engine
+        eng.reset_measurements()
+        self._run_sweeps(self.meas_sweeps, measure=True, det=True)
+        self.it = max(self.meas_sweeps - 1, 0)
+        m = eng.get_measurements()
+        self.observables = self._observables(m)
+        self._log_debug("END " + self.status.upper())
+        return m["g_sum"][0] / self.meas_sweeps
+
     def run_lqmc(self):
+        if self.det_mode:
+            self.warmup_loop_det()
+            return self.measure_loop_det()
         self.warmup_loop()
         return self.measure_loop()
 

@@ -243,8 +243,6 @@ class ParallelProcessManager(ProcessManager):
                  rng="numpy", mode="parity", arith="exact", device=None, seed=0, stab_every=0):
         super().__init__(procs, model=model, beta=beta, time_steps=time_steps, warmup=warmup, det_mode=det_mode)
         self.stab_every = stab_every
-        if det_mode:
-            raise NotImplementedError("det_mode is outside the accelerated hot path (see LatticeQMC)")
         self.seeds = list(seeds) if seeds is not None else [os.getpid() + c for c in range(self.max_procs)]
         if len(self.seeds) != self.max_procs:
             raise ValueError("need one seed per chain")
@@ -292,7 +290,8 @@ class ParallelProcessManager(ProcessManager):
                 done = 0
                 while done < count:
                     k = min(chunk, count - done)
-                    engine.sweep(k, us(k) if us else uniforms(k), seed=self.seed, measure=measure)
+                    step = engine.sweep_det if kw["det_mode"] else engine.sweep
+                    step(k, us(k) if us else uniforms(k), seed=self.seed, measure=measure)
                     done += k
 
             with SweepEngine(exp_k, lamb, lt, n_chains=hi - lo, exp_k_inv=exp_k_inv, device=device, mode=self.mode,

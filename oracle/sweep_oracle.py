@@ -1,7 +1,7 @@
 """CPU oracle for the HS-field Metropolis sweep - TEST INFRASTRUCTURE, NOT PRODUCT CODE.
 
 A NumPy restatement of the reference algorithm ``LatticeQMC._update_step`` and its helpers
-(`/root/reference/lqmc/lqmc.py:93-117,132-185,301-375`).  Only ``tests/``,
+(`/root/reference/lqmc/lqmc.py:93-117,132-185,236-299,301-375`).  Only ``tests/``,
 ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may
 import this module, and only as the checker / the timed CPU baseline; the product path
 (``latticeqmc_b200``) never does and fails loudly when its CUDA library is missing.
@@ -189,6 +189,60 @@ def measure_loop(h, exp_k, lamb, sweeps, uniforms=None):
         gf_up, gf_dn, _, _ = update_step(h, exp_k, lamb, u)
         tot_up += gf_up
         tot_dn += gf_dn
+    return np.asarray([tot_up, tot_dn]) / sweeps
+
+
+# ----------------------------------------------------------------------------------------------
+# det mode: the reference's slow validation sampler (lqmc.py:236-299), literal restatement
+# ----------------------------------------------------------------------------------------------
+
+def det_product(h, exp_k, lamb):
+    """``det(M_up(0)) * det(M_dn(0))``: how ``warmup_loop_det`` / ``measure_loop_det`` initialise
+    ``old_det`` (lqmc.py:264-268, 283-287)."""
+    return np.linalg.det(get_m(h, exp_k, lamb, 0, +1)) * np.linalg.det(get_m(h, exp_k, lamb, 0, -1))
+
+
+def det_update_step(h, exp_k, lamb, old_det, uniforms=None):
+    """One det-mode sweep = ``LatticeQMC._update_step_det`` (lqmc.py:236-259): flip, rebuild
+    ``get_m(l, +-1)`` from the field, ``ratio = det(M_up) det(M_dn) / old_det``, Metropolis test
+    ``u <= ratio``, un-flip on reject.  ``h`` is mutated in place.  ``uniforms``: ``(L, N)`` in visiting
+    order or ``None`` for the global stream.  Returns ``old_det, ratios (L, N), accs (L, N)``."""
+    n, time_steps = h.shape
+    ratios = np.empty((time_steps, n), dtype=np.float64)
+    accs = np.zeros((time_steps, n), dtype=bool)
+    for step, l in enumerate(reversed(range(time_steps))):
+        for i in range(n):
+            h[i, l] *= -1
+            m_up = get_m(h, exp_k, lamb, l, +1)
+            m_dn = get_m(h, exp_k, lamb, l, -1)
+            new_det = np.linalg.det(m_up) * np.linalg.det(m_dn)
+            ratio = new_det / old_det
+            u = np.random.rand() if uniforms is None else uniforms[step, i]
+            acc = u <= ratio
+            if acc:
+                old_det = new_det
+            else:
+                h[i, l] *= -1
+            ratios[step, i] = ratio
+            accs[step, i] = acc
+    return old_det, ratios, accs
+
+
+def det_measure_loop(h, exp_k, lamb, sweeps, uniforms=None, trace=None):
+    """``LatticeQMC.measure_loop_det`` (lqmc.py:274-299): ``old_det`` from ``get_m(0, +-1)`` once, then
+    per sweep one ``_update_step_det`` and ``inv(get_m(0, +-1))`` added to the totals.  ``trace``:
+    optional list receiving ``(ratios, accs)`` per sweep."""
+    n = h.shape[0]
+    old_det = det_product(h, exp_k, lamb)
+    tot_up = np.zeros((n, n), dtype=np.float64)
+    tot_dn = np.zeros((n, n), dtype=np.float64)
+    for s in range(sweeps):
+        u = None if uniforms is None else uniforms[s]
+        old_det, ratios, accs = det_update_step(h, exp_k, lamb, old_det, u)
+        if trace is not None:
+            trace.append((ratios, accs))
+        tot_up += np.linalg.inv(get_m(h, exp_k, lamb, 0, +1))
+        tot_dn += np.linalg.inv(get_m(h, exp_k, lamb, 0, -1))
     return np.asarray([tot_up, tot_dn]) / sweeps
 
 

@@ -242,8 +242,44 @@ def case_lattice(lqmc):
     save("lattice_ham", **out)
 
 
+def case_det(lqmc):
+    """det_mode (lqmc.py:236-299), the reference's slow validation sampler: 2x2 U=4 beta=2 L=20 (2 warm-up + 3
+    measured sweeps) and 3x2 U=6 beta=1 L=10 (1 + 2), through the reference's own `run_lqmc`.  Per-proposal
+    ratio / acc via the `_debug` hook; the uniforms are replayed from a copy of the MT19937 state."""
+    for tag, (w, h), u, beta, lt, seed, warm, meas in (("2x2", (2, 2), 4, 2.0, 20, 61, 2, 3),
+                                                       ("3x2", (3, 2), 6, 1.0, 10, 62, 1, 2)):
+        model = lqmc.HubbardModel(u=u, t=1)
+        model.build(w, h, cycling=(0, 1) if w == h else 0)
+        np.random.seed(seed)
+        solver = lqmc.LatticeQMC(model, beta, lt, warmup=warm, sweeps=meas, det_mode=True, log_lvl=None)
+        n = solver.n_sites
+        field0 = solver.config.config.copy()
+        state = np.random.get_state()
+        uniforms = np.random.rand((warm + meas) * lt * n).reshape(warm + meas, lt, n)
+        np.random.set_state(state)
+        ratios, accs, fields = [], [], []
+
+        def hook(i, l, solver=solver, ratios=ratios, accs=accs, fields=fields, n=n):
+            ratios.append(solver.ratio)
+            accs.append(bool(solver.acc))
+            if l == 0 and i == n - 1:
+                fields.append(solver.config.config.copy())
+
+        solver._debug = hook
+        solver.iter_sweeps = lambda count: range(count)        # no console progress
+        gf = solver.run_lqmc()
+        probe = np.random.get_state()
+        np.random.set_state(state)
+        np.random.rand((warm + meas) * lt * n)
+        assert np.array_equal(np.random.get_state()[1], probe[1]) and np.random.get_state()[2] == probe[2]
+        save(f"det_{tag}", ham=model.ham_kinetic(), u=float(u), beta=beta, lamb=solver.lamb, exp_k=solver.exp_k,
+             field0=field0, uniforms=uniforms, warm=warm, meas=meas,
+             ratios=np.array(ratios).reshape(warm + meas, lt, n), accs=np.array(accs).reshape(warm + meas, lt, n),
+             fields=np.stack(fields), gf=np.asarray(gf))
+
+
 CASES = dict(cfg1=case_cfg1, small=case_small, cfg2=case_cfg2, cfg3=case_cfg3, cfg4=case_cfg4, u0=case_u0,
-             lattice=case_lattice)
+             lattice=case_lattice, det=case_det)
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()

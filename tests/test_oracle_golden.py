@@ -145,3 +145,26 @@ def test_u0_known_answer(golden):
     exact = np.linalg.inv(np.eye(10) + expm(-4.0 * g["ham"]))
     assert np.max(np.abs(gu - exact)) < 1e-9
     assert np.max(np.abs(gu + g["pole_gf_tau0"])) < 1e-9
+
+
+@pytest.mark.parametrize("name", ["det_2x2", "det_3x2"])
+def test_det_mode_golden(golden, name):
+    """det_mode (lqmc.py:236-299): the reference's own `run_lqmc(det_mode=True)` replayed through the oracle's
+    literal restatement - warm-up loop (fresh old_det), measurement loop (fresh old_det, inv(get_m(0)) per sweep)."""
+    g = golden(name)
+    h = g["field0"].copy()
+    lamb, exp_k = float(g["lamb"]), g["exp_k"]
+    warm, meas = int(g["warm"]), int(g["meas"])
+    old = so.det_product(h, exp_k, lamb)
+    for s in range(warm):
+        old, ratios, accs = so.det_update_step(h, exp_k, lamb, old, g["uniforms"][s])
+        assert np.array_equal(accs, g["accs"][s])
+        assert _bitwise_or_close(ratios, g["ratios"][s], 1e-10)
+        assert np.array_equal(h, g["fields"][s])
+    trace = []
+    gf = so.det_measure_loop(h, exp_k, lamb, meas, g["uniforms"][warm:], trace=trace)
+    for s, (ratios, accs) in enumerate(trace):
+        assert np.array_equal(accs, g["accs"][warm + s])
+        assert _bitwise_or_close(ratios, g["ratios"][warm + s], 1e-10)
+    assert np.array_equal(h, g["fields"][-1])
+    assert _bitwise_or_close(gf, g["gf"], 1e-10)
