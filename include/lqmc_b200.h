@@ -102,6 +102,12 @@ int lqmc_sweep(lqmc_engine* e, int n_sweeps, const double* uniforms, uint64_t se
 int lqmc_sweep_async(lqmc_engine* e, int n_sweeps, const double* d_uniforms, uint64_t seed, int measure,
                      void* stream);
 int lqmc_sync(lqmc_engine* e);
+/* lqmc_sweep without the final wait: host uniforms (or NULL = Philox) are staged and the sweeps are queued on the
+ * engine's own stream; the call returns as soon as the work is submitted (`uniforms` may be released on return).  Lets
+ * one host thread drive many engines at once - a beta / U scan (measure_betas, lqmc/__init__.py:57-96;
+ * SerialProcessManager, multiprocessing.py:292-341) runs one engine per parameter point, all concurrently on one GPU,
+ * where the reference runs one OS process per point.  Pair with lqmc_sync. */
+int lqmc_sweep_submit(lqmc_engine* e, int n_sweeps, const double* uniforms, uint64_t seed, int measure);
 
 /* det mode: n_sweeps x LatticeQMC._update_step_det (lqmc.py:236-259), the reference's slow validation sampler -
  * every proposal flips h[i,l], rebuilds get_m(l, +-1) from the field, and accepts on

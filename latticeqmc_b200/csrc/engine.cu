@@ -859,6 +859,20 @@ int lqmc_sweep_det(lqmc_engine* e, int n_sweeps, const double* uniforms, uint64_
   return LQMC_OK;
 }
 
+int lqmc_sweep_submit(lqmc_engine* e, int n_sweeps, const double* uniforms, uint64_t seed, int measure) {
+  if (!e) return fail(LQMC_ERR_INVALID, "engine is NULL");
+  if (n_sweeps < 0) return fail(LQMC_ERR_INVALID, "n_sweeps = %d is negative", n_sweeps);
+  if (n_sweeps == 0) return LQMC_OK;
+  CU(cudaSetDevice(e->device));
+  const double* d_u = nullptr;
+  if (uniforms) {
+    int rc = stage_uniforms(e, uniforms, (size_t)e->C * n_sweeps * e->L * e->N, e->stream);
+    if (rc) return rc;
+    d_u = e->dUni;
+  }
+  return lqmc_sweep_async(e, n_sweeps, d_u, seed, measure, e->stream);
+}
+
 int lqmc_get_det(lqmc_engine* e, double* det_old) {
   if (!e || !det_old) return fail(LQMC_ERR_INVALID, "engine or det_old is NULL");
   if (!e->dDetOld) return fail(LQMC_ERR_INVALID, "no det-mode sweep has run on this engine");

@@ -24,7 +24,7 @@ EXPORTS = (
     "lqmc_get_trace", "lqmc_get_measurements", "lqmc_reset_measurements", "lqmc_device_ptr", "lqmc_info",
     "lqmc_set_sweep_counter", "lqmc_set_chain_offset", "lqmc_philox_uniforms", "lqmc_last_error",
     "lqmc_version", "lqmc_selftest_division", "lqmc_recompute_stable", "lqmc_set_stabilization",
-    "lqmc_set_measurements", "lqmc_sweep_det", "lqmc_get_det",
+    "lqmc_set_measurements", "lqmc_sweep_det", "lqmc_get_det", "lqmc_sweep_submit",
 )
 
 
@@ -64,6 +64,7 @@ def load_library(path=None):
     lib.lqmc_sweep.argtypes = [vp, ctypes.c_int, vp, ctypes.c_uint64, ctypes.c_int]
     lib.lqmc_sweep_det.argtypes = [vp, ctypes.c_int, vp, ctypes.c_uint64, ctypes.c_int]
     lib.lqmc_get_det.argtypes = [vp, vp]
+    lib.lqmc_sweep_submit.argtypes = [vp, ctypes.c_int, vp, ctypes.c_uint64, ctypes.c_int]
     lib.lqmc_sweep_async.argtypes = [vp, ctypes.c_int, vp, ctypes.c_uint64, ctypes.c_int, vp]
     lib.lqmc_sync.argtypes = [vp]
     lib.lqmc_get_trace.argtypes = [vp, vp, vp]
@@ -274,6 +275,16 @@ class SweepEngine:
         cudaStream_t (0 = the engine's stream).  Returns immediately; call `sync()`."""
         self._check(self._lib.lqmc_sweep_async(self._h, int(n_sweeps), ctypes.c_void_p(d_uniforms or None), int(seed),
                                                int(bool(measure)), ctypes.c_void_p(stream or None)))
+        self._last_trace_shape = (self.n_chains, int(n_sweeps), self.n_slices, self.n_sites)
+
+    def sweep_submit(self, n_sweeps=1, uniforms=None, seed=0, measure=False):
+        """`sweep` without the final wait: queued on the engine's stream, returns at once (`sync()` waits).  Several
+        engines driven this way run concurrently on one GPU (beta scans)."""
+        ptr = None
+        if uniforms is not None:
+            u = np.ascontiguousarray(uniforms, dtype=np.float64).reshape(self.n_chains, n_sweeps, self.n_slices, self.n_sites)
+            ptr = u.ctypes.data
+        self._check(self._lib.lqmc_sweep_submit(self._h, int(n_sweeps), ptr, int(seed), int(bool(measure))))
         self._last_trace_shape = (self.n_chains, int(n_sweeps), self.n_slices, self.n_sites)
 
     def sync(self):

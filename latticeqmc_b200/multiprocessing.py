@@ -3,7 +3,8 @@
 
 `ParallelProcessManager(procs=C)` runs C independent Markov chains of the same model as ONE
 engine (one CTA per chain, no communication during the sweeps); `SerialProcessManager` runs one
-chain per beta, each on its own engine / CUDA stream.  Public methods, job splitting
+chain per beta, each on its own engine / CUDA stream, ALL AT ONCE (`_run_batch`: beta is a per-chain
+parameter, the kernels of the different points run concurrently on the GPU).  Public methods, job splitting
 (`sweeps/procs` each, remainder to chain 0, multiprocessing.py:260-263) and the unweighted mean over
 chains (`:265-267`) are the reference's.  Differences, all deliberate:
 
@@ -341,12 +342,19 @@ class SerialProcessManager(ProcessManager):
     CORE_COUNT = multiprocessing.cpu_count()
     TMP_FILE = "tmp_data.npz"
 
+    MAX_CONCURRENT = 128      # resident grids per device (hardware limit of concurrently running kernels)
+
     def __init__(self, model, time_steps, warmup=300, sweeps=2000, det_mode=False, procs=None, caching=True,
-                 **engine_kwargs):
+                 concurrent=None, **engine_kwargs):
+        engine_kwargs.setdefault("trace", False)
         super().__init__(procs, model=model, time_steps=time_steps, warmup=warmup, sweeps=sweeps,
                          det_mode=det_mode, **engine_kwargs)
         self.caching = caching
         self._tmp_file = "tmp_gf_series.npz"
+        # parameter points in flight at once on the GPU (the reference: `procs` OS processes, multiprocessing.py:55-75;
+        # here the limit is the device's, not the host's core count)
+        self.concurrent = self.MAX_CONCURRENT if concurrent is None else max(1, int(concurrent))
+        self.observables = None
 
     def set_jobs(self, betas):
         super().set_jobs(beta=betas)
@@ -369,13 +377,82 @@ class SerialProcessManager(ProcessManager):
                 print(f"Found temporary data. Continuing at job {self.idx}...")
         return args
 
-    def end_process(self, item):
-        super().end_process(item)
+    def _save_cache(self):
         if self.caching:
             done = np.array([r is not None for r in self.result])
             shape = next(r.shape for r in self.result if r is not None)
             values = np.stack([r if r is not None else np.zeros(shape) for r in self.result])
             np.savez(self._tmp_file, beta=np.asarray(self.var_kwargs["beta"]), data=values, done=done)
+
+    def end_process(self, item):
+        super().end_process(item)
+        self._save_cache()
+
+    def _run_batch(self, batch):
+        """One engine (own CUDA stream) per parameter point of `batch`, all in flight at once: beta is a per-chain
+        parameter (own `dtau`, `lamb`, `exp_k`), sweeps are submitted round-robin with `SweepEngine.sweep_submit` and
+        the kernels of the different points run concurrently.  Every chain sees exactly the numbers its sequential
+        `LqmcProcess.run` would (multiprocessing.py:45-52): stream seeded with its pid, field first, then `N*L`
+        uniforms per sweep - so the results are bit-identical to running the points one after the other."""
+        procs = []
+        for idx in batch:
+            p = LqmcProcess(idx, self.iters, None, **self.job_kwargs(idx))
+            state = np.random.get_state()
+            np.random.seed(p.pid)
+            p.config.initialize()
+            p._rs = np.random.RandomState()
+            p._rs.set_state(np.random.get_state())
+            np.random.set_state(state)
+            p.engine.set_field(p.config.config[None])
+            procs.append(p)
+
+        def phase(count_of, measure):
+            done = [0] * len(procs)
+            budget = max(1, _UNIFORM_CHUNK_BYTES // len(procs))
+            while True:
+                busy = False
+                for j, p in enumerate(procs):
+                    left = count_of(p) - done[j]
+                    if left <= 0:
+                        continue
+                    busy = True
+                    per_sweep = p.time_steps * p.n_sites
+                    k = min(left, max(1, budget // (per_sweep * 8)))
+                    u = p._rs.rand(k * per_sweep).reshape(1, k, p.time_steps, p.n_sites) if p.rng == "numpy" else None
+                    p.engine.sweep_submit(k, u, seed=p.seed, measure=measure)
+                    done[j] += k
+                if not busy:
+                    break
+                for p in procs:
+                    p.engine.sync()
+
+        phase(lambda p: p.warm_sweeps, False)
+        for p in procs:
+            p.engine.reset_measurements()
+        phase(lambda p: p.meas_sweeps, True)
+        for p in procs:
+            m = p.engine.get_measurements()
+            p.observables = p._observables(m)
+            p.config.config[...] = p.engine.get_field()[0]
+            p.result = m["g_sum"][0] / max(p.meas_sweeps, 1)
+            self.result[p.idx] = np.array(p.result)
+            self.observables[p.idx] = p.observables
+            self.iters[p.idx] = p.warm_sweeps + p.meas_sweeps
+            p.engine.close()
+
+    def run(self, sleep=0.5):
+        if self.default_kwargs.get("det_mode"):
+            return super().run(sleep)                 # det-mode sweeps are synchronous engine calls: one point at a time
+        self.t0 = time.time()
+        args = self.start()
+        self.observables = [None] * self.total
+        while self.idx < self.total:
+            batch = list(range(self.idx, min(self.total, self.idx + self.concurrent)))
+            self._run_batch(batch)
+            self.idx = batch[-1] + 1
+            self._save_cache()
+            args = self.update(*args)
+        self.end(args)
 
     def delete_cache(self):
         if os.path.isfile(self._tmp_file):

@@ -357,3 +357,39 @@ def test_measure_single_core_matches_run(golden):
     ref_up = g["gf_up"][4:10].sum(0) / 6
     ref_dn = g["gf_dn"][4:10].sum(0) / 6
     assert _close(gf_up, ref_up, 1e-9) and _close(gf_dn, ref_dn, 1e-9)
+
+
+def test_measure_betas_concurrent_scan(tmp_path, monkeypatch):
+    """`lqmc.measure_betas` / SerialProcessManager (lqmc/__init__.py:57-96, multiprocessing.py:292-341): one chain per
+    beta, every point with its own dtau / lamb / exp_k, all points in flight at once on the GPU.  Each point must equal
+    what a reference process seeded with that pid computes (multiprocessing.py:45-52): checked against the oracle run
+    point by point, and against the same scan with `concurrent=1`."""
+    import lqmc
+    monkeypatch.chdir(tmp_path)                      # the scan cache is written to the cwd, like the reference's
+    model = lqmc.HubbardModel(u=4, t=1)
+    model.build_square(2)
+    n, lt, warm, sweeps = 4, 20, 3, 5
+    betas = [0.5, 1.0, 2.0]
+    mgr = lqmc.SerialProcessManager(model, lt, warm, sweeps, procs=2, caching=True)
+    mgr.set_jobs(betas)
+    mgr.run()
+    scan = mgr.get_result()
+    assert scan.shape == (3, 2, n, n)
+    assert not (tmp_path / "tmp_gf_series.npz").exists()          # cache deleted on success (multiprocessing.py:335-341)
+    pid = __import__("os").getpid()
+    for j, beta in enumerate(betas):
+        dtau, lamb, exp_k = so.set_beta_constants(model.ham_kinetic(), 4, beta, lt)
+        state = np.random.get_state()
+        np.random.seed(pid + j)
+        h = (2 * np.random.randint(0, 2, size=(n, lt)) - 1).astype(np.int8)
+        for _ in range(warm):
+            so.update_step(h, exp_k, lamb, None)
+        ref = so.measure_loop(h, exp_k, lamb, sweeps, None)
+        np.random.set_state(state)
+        assert _close(scan[j, 0], ref[0], 1e-9) and _close(scan[j, 1], ref[1], 1e-9), f"beta = {beta}"
+    one = lqmc.SerialProcessManager(model, lt, warm, sweeps, procs=2, caching=False, concurrent=1)
+    one.set_jobs(betas)
+    one.run()
+    assert np.array_equal(one.get_result(), scan)
+    gf_up, gf_dn = lqmc.measure_betas(model, betas, lt, warmup=warm, sweeps=sweeps, caching=False)
+    assert gf_up.shape == (3, n, n) and np.array_equal(gf_up, scan[:, 0]) and np.array_equal(gf_dn, scan[:, 1])
