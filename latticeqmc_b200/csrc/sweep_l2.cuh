@@ -576,6 +576,7 @@ __device__ void l2_propose_slice(double* __restrict__ Gc, int NP, int KD, L2Smem
 #ifndef LQMC_L2_KDT
 #define LQMC_L2_KDT 24
 #endif
+
 constexpr int L2_KDT = LQMC_L2_KDT;
 constexpr int L2_TMEM_COLS = 256;
 static_assert(L2_KDT % 8 == 0 && 8 * L2_KDT <= L2_TMEM_COLS, "two windows of 4 KDT columns; history read in chunks of 8 doubles");
@@ -596,6 +597,26 @@ __device__ __forceinline__ void tmem_ld_f64x8(uint32_t taddr, double (&v)[8]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 8; ++i) v[i] = __hiloint2double((int)r[2 * i + 1], (int)r[2 * i]);
+}
+// two 8-double loads in flight, one wait (both spins' history chunks of one thread)
+__device__ __forceinline__ void tmem_ld_f64x8_pair(uint32_t taddr0, uint32_t taddr1, double (&v0)[8], double (&v1)[8]) {
+  uint32_t r[16], q[16];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                 "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(taddr0)
+               : "memory");
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]), "=r"(q[8]), "=r"(q[9]),
+                 "=r"(q[10]), "=r"(q[11]), "=r"(q[12]), "=r"(q[13]), "=r"(q[14]), "=r"(q[15])
+               : "r"(taddr1)
+               : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    v0[i] = __hiloint2double((int)r[2 * i + 1], (int)r[2 * i]);
+    v1[i] = __hiloint2double((int)q[2 * i + 1], (int)q[2 * i]);
+  }
 }
 // one warp allocates L2_TMEM_COLS columns for the CTA; every thread gets the base address
 __device__ __forceinline__ uint32_t tmem_alloc_cta(uint32_t* slot) {
@@ -654,6 +675,61 @@ __device__ void l2_flush_tmem(double* __restrict__ Gc, int NP, int nd, const dou
 #pragma unroll
         for (int r = 0; r < 8; ++r) col[(size_t)(r0 + r) * NP] = g[r];
       }
+    }
+  }
+  __syncthreads();
+}
+
+// NP == 256: two columns per thread.  Every update needs e_m[row] from shared memory, and a broadcast load delivers one
+// double per two LSU wavefronts whatever its width.  Warps w and w+4 address the same TMEM lane quarter, so thread t can read
+// the c history of column t % 128 (window 0) AND of column t % 128 + 128 (window 1): it updates both columns with every e
+// value it loads - half the shared-memory traffic per update - while the two thread halves split the rows.  The history is
+// re-read from tensor memory per 8-row chunk in three parts of eight (16 doubles in registers at a time).  Same operations
+// per element in the same order: still bit-identical.  Measured (clock64 split, profiles/r01e_cfg4_summary.md): alone on an SM
+// a flush takes the same 162 K clocks as the one-column version (98 K is the FP64 floor of 2 issue slots per exact update),
+// with two resident CTAs the flush cost per flip falls 12.2 K -> 11.1 K clocks and the slice phase 2.04 -> 1.93 ms.
+template <bool EXACT>
+__device__ void l2_flush_tmem2(double* __restrict__ Gc, int nd, const double* __restrict__ U3, uint32_t tm_base) {
+  constexpr int NP = 256;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int jj = tid & 127, rbase = (tid >> 7) * (NP / 2);
+  const uint32_t tm_lane = tm_base + ((uint32_t)(32 * (warp & 3)) << 16);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  for (int spin = 0; spin < 2; ++spin) {
+    double* const col = Gc + (size_t)spin * NP * NP + (size_t)rbase * NP + jj;
+    const double* const Us = U3 + (size_t)spin * L2_KDT * NP + rbase;
+    const uint32_t tm0 = tm_lane + 2 * (spin * L2_KDT), tm1 = tm0 + 4 * L2_KDT;
+    double nxt[8][2];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) { nxt[r][0] = col[(size_t)r * NP]; nxt[r][1] = col[(size_t)r * NP + 128]; }
+    for (int r0 = 0; r0 < NP / 2; r0 += 8) {
+      double g[8][2];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) { g[r][0] = nxt[r][0]; g[r][1] = nxt[r][1]; }
+      if (r0 + 8 < NP / 2) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) { nxt[r][0] = col[(size_t)(r0 + 8 + r) * NP]; nxt[r][1] = col[(size_t)(r0 + 8 + r) * NP + 128]; }
+      }
+      for (int m0 = 0; m0 < nd; m0 += 8) {
+        double c0[8], c1[8];
+        tmem_ld_f64x8_pair(tm0 + 2 * m0, tm1 + 2 * m0, c0, c1);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          if (m0 + q < nd) {
+            const double* ur = Us + (size_t)(m0 + q) * NP + r0;
+#pragma unroll
+            for (int r = 0; r < 8; r += 2) {
+              const double2 e = *reinterpret_cast<const double2*>(ur + r);
+              g[r][0] = rank1<EXACT>(g[r][0], e.x, c0[q]);
+              g[r][1] = rank1<EXACT>(g[r][1], e.x, c1[q]);
+              g[r + 1][0] = rank1<EXACT>(g[r + 1][0], e.y, c0[q]);
+              g[r + 1][1] = rank1<EXACT>(g[r + 1][1], e.y, c1[q]);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 8; ++r) { col[(size_t)(r0 + r) * NP] = g[r][0]; col[(size_t)(r0 + r) * NP + 128] = g[r][1]; }
     }
   }
   __syncthreads();
@@ -725,14 +801,11 @@ __device__ void l2_propose_slice_tmem(double* __restrict__ Gc, int NP, L2Smem& s
     // the warp that owns site `is` publishes that site's c history (tcgen05.ld is warp-collective)
     if (warp == (is >> 5)) {
       for (int m0 = 0; m0 < nd; m0 += 8) {
+        double v0[8], v1[8];
+        tmem_ld_f64x8_pair(tm_my + 2 * m0, tm_my + 2 * (L2_KDT + m0), v0, v1);
+        if (lane == (is & 31)) {
 #pragma unroll
-        for (int spin = 0; spin < 2; ++spin) {
-          double v[8];
-          tmem_ld_f64x8(tm_my + 2 * (spin * L2_KDT + m0), v);
-          if (lane == (is & 31)) {
-#pragma unroll
-            for (int q = 0; q < 8; ++q) wis[spin * L2_KDT + m0 + q] = v[q];
-          }
+          for (int q = 0; q < 8; ++q) { wis[m0 + q] = v0[q]; wis[L2_KDT + m0 + q] = v1[q]; }
         }
       }
     }
@@ -740,8 +813,7 @@ __device__ void l2_propose_slice_tmem(double* __restrict__ Gc, int NP, L2Smem& s
     if (act) {
       for (int m0 = 0; m0 < nd; m0 += 8) {
         double wj[2][8];
-        tmem_ld_f64x8(tm_my + 2 * m0, wj[0]);
-        tmem_ld_f64x8(tm_my + 2 * (L2_KDT + m0), wj[1]);
+        tmem_ld_f64x8_pair(tm_my + 2 * m0, tm_my + 2 * (L2_KDT + m0), wj[0], wj[1]);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           const int m = m0 + q;
@@ -779,6 +851,7 @@ __device__ void l2_propose_slice_tmem(double* __restrict__ Gc, int NP, L2Smem& s
         dnxt[spin * NP + j] = rank1<EXACT>(dcur[spin * NP + j], e, c);
       }
       tmem_wait_st();
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");    // the two-column flush reads the partner warp's window
     }
     ++n_accepted;
     ++nd;
@@ -788,13 +861,18 @@ __device__ void l2_propose_slice_tmem(double* __restrict__ Gc, int NP, L2Smem& s
 #ifdef LQMC_PHASE_CLOCKS
     { const long long tk1 = clock64(); tk_build += tk1 - tk0; tk0 = tk1; }
 #endif
-    if (nd == L2_KDT) { l2_flush_tmem<EXACT>(Gc, NP, nd, U3, tm_my); nd = 0; }
+    if (nd == L2_KDT) {
+      if (NP == 256) l2_flush_tmem2<EXACT>(Gc, nd, U3, tm_base); else l2_flush_tmem<EXACT>(Gc, NP, nd, U3, tm_my);
+      nd = 0;
+    }
 #ifdef LQMC_PHASE_CLOCKS
     { const long long tk1 = clock64(); tk_flush += tk1 - tk0; tk0 = tk1; }
 #endif
     i0 = is + 1;
   }
-  if (nd > 0) l2_flush_tmem<EXACT>(Gc, NP, nd, U3, tm_my);
+  if (nd > 0) {
+    if (NP == 256) l2_flush_tmem2<EXACT>(Gc, nd, U3, tm_base); else l2_flush_tmem<EXACT>(Gc, NP, nd, U3, tm_my);
+  }
 #ifdef LQMC_PHASE_CLOCKS
   { const long long tk1 = clock64(); tk_flush += tk1 - tk0;
     if (tid == 0) { double* ob = p.obs_sum + (size_t)blockIdx.x * 3 * N; ob[0] = (double)tk_scan; ob[1] = (double)tk_build; ob[2] = (double)tk_flush; ob[3] = (double)n_accepted;
