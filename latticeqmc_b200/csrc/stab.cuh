@@ -27,6 +27,11 @@ constexpr int ST_BM = 64, ST_BK = 16, ST_STAGES = 3;
 constexpr int ST_LDA = ST_BM + 4;
 constexpr int ST_NB = 16;                 // QR panel width
 constexpr int ST_CB = 256;                // columns per trailing-update block (2 per thread, thread pairs split the reflectors)
+constexpr int ST_LDS = 36;                // DMMA reflector application: row stride of a warp's private 16 x 32 W strip (72 words = 8 mod 32)
+constexpr int ST_WT_LD = (ST_THREADS / 32) * ST_LDS > ST_CB ? (ST_THREADS / 32) * ST_LDS : ST_CB;
+#ifndef LQMC_ST_APPLY_DMMA
+#define LQMC_ST_APPLY_DMMA 1              // 0: the DFMA register-tiled block-reflector application (kept as the timed comparison)
+#endif
 
 struct HsConsts { double exp_pl, exp_ml; };
 
@@ -234,9 +239,9 @@ __global__ void __launch_bounds__(ST_THREADS) st_chain_kernel(const StChainArgs 
 // V (m x NB, unit lower trapezoid, explicit) and T (NB x NB upper triangular) are in shared memory.  Thread pairs
 // (tid, tid + 128) share two columns {c, c + 128} of the block and split the reflector index range.
 template <int NB, bool TRANS_T>
-__device__ void st_apply_reflector(double* __restrict__ Amat, int ld, int row0, int m, int c0, int c1,
-                                   const double* __restrict__ Vs, const double* __restrict__ Ts, double* __restrict__ Wt) {
-  constexpr int LDV = NB + 2, NA = NB / 2;
+__device__ void st_apply_reflector_dfma(double* __restrict__ Amat, int ld, int row0, int m, int c0, int c1,
+                                        const double* __restrict__ Vs, const double* __restrict__ Ts, double* __restrict__ Wt) {
+  constexpr int LDV = NB + 4, NA = NB / 2;
   const int tid = threadIdx.x, cl = tid & 127, half = tid >> 7;
   const int a0 = half * NA;
   double* const abase = Amat + (size_t)row0 * ld;
@@ -300,15 +305,140 @@ __device__ void st_apply_reflector(double* __restrict__ Amat, int ld, int row0, 
   }
 }
 
+// The same block reflector on DMMA fragments (mma.sync.m8n8k4.f64).  The DFMA version above is LSU-bound: every V value it
+// loads (a broadcast shared-memory read) feeds two FMAs (ncu, profiles/r01d_stab_summary.md: 43 % LSU wavefronts, FP64 pipe
+// 22 %); a DMMA fragment is one double per 8 FMAs.  Work is split by COLUMN STRIPS, one warp per strip of 8 NT columns, and all
+// three steps of a strip are warp-local - no block barrier inside:
+//   W  = V^T A_strip     2 x NT accumulator tiles, k = rows: A fragments straight from global memory (a B fragment is 4 rows x
+//                        8 consecutive doubles: whole 32-byte sectors), V^T fragments from shared memory;
+//   W2 = -Top W          through the warp's private [16][ST_LDS] shared strip (accumulator layout -> B-fragment layout);
+//   A_strip += V W2      W2 fragments stay in registers for the whole strip, the accumulator tiles ARE the 16-row slabs of A
+//                        (128-bit loads / stores), the next slab's loads in flight behind the DMMAs of the current one.
+// Rows are processed in slabs of 16 up to mp = roundup(m, 16): the caller keeps V rows >= m zero, and the matrix padding
+// (rows / columns >= N) holds zeros (A) or the identity (Q), so no element masks are needed - only warp-uniform tile guards.
+template <int NT, bool TRANS_T>
+__device__ __forceinline__ void st_apply_strip(double* __restrict__ abase, int ld, int mp, int cw, int c1, const double* __restrict__ Vs,
+                                               const double* __restrict__ Ts, double* __restrict__ Ws, int lr, int lk) {
+  constexpr int NB = ST_NB, LDV = NB + 4;
+  bool nv[NT];
+#pragma unroll
+  for (int n = 0; n < NT; ++n) nv[n] = cw + 8 * n < c1;
+  // ---- W = V^T A_strip
+  double w[2][NT][2];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int n = 0; n < NT; ++n) w[mt][n][0] = w[mt][n][1] = 0.0;
+  for (int r = 0; r < mp; r += 16) {
+    double b[4][NT];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+      for (int n = 0; n < NT; ++n) b[ks][n] = nv[n] ? abase[(size_t)(r + 4 * ks + lk) * ld + cw + 8 * n + lr] : 0.0;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const double* vp = Vs + (r + 4 * ks + lk) * LDV + lr;
+      const double a0 = vp[0], a1 = vp[8];
+#pragma unroll
+      for (int n = 0; n < NT; ++n) { dmma884(w[0][n], a0, b[ks][n]); dmma884(w[1][n], a1, b[ks][n]); }
+    }
+  }
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int n = 0; n < NT; ++n)
+      *reinterpret_cast<double2*>(Ws + (8 * mt + lr) * ST_LDS + 8 * n + 2 * lk) = make_double2(w[mt][n][0], w[mt][n][1]);
+  __syncwarp();
+  // ---- W2 = -Top W   (Top = T^T for the factorization's Q^T A, T when forming Q)
+  double bw[4][NT];
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+    for (int n = 0; n < NT; ++n) bw[ks][n] = Ws[(4 * ks + lk) * ST_LDS + 8 * n + lr];
+  __syncwarp();
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+    double acc[NT][2];
+#pragma unroll
+    for (int n = 0; n < NT; ++n) acc[n][0] = acc[n][1] = 0.0;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const double t = TRANS_T ? Ts[(4 * ks + lk) * NB + 8 * mt + lr] : Ts[(8 * mt + lr) * NB + 4 * ks + lk];
+#pragma unroll
+      for (int n = 0; n < NT; ++n) dmma884(acc[n], -t, bw[ks][n]);
+    }
+#pragma unroll
+    for (int n = 0; n < NT; ++n)
+      *reinterpret_cast<double2*>(Ws + (8 * mt + lr) * ST_LDS + 8 * n + 2 * lk) = make_double2(acc[n][0], acc[n][1]);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+    for (int n = 0; n < NT; ++n) bw[ks][n] = Ws[(4 * ks + lk) * ST_LDS + 8 * n + lr];
+  __syncwarp();
+  // ---- A_strip += V W2, 16-row slabs
+  double2 nxt[2][NT];
+  auto load_slab = [&](int r, double2 (&dst)[2][NT]) {
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int n = 0; n < NT; ++n)
+        dst[mt][n] = nv[n] ? *reinterpret_cast<const double2*>(abase + (size_t)(r + 8 * mt + lr) * ld + cw + 8 * n + 2 * lk) : make_double2(0.0, 0.0);
+  };
+  if (mp > 0) load_slab(0, nxt);
+  for (int r = 0; r < mp; r += 16) {
+    double c[2][NT][2];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int n = 0; n < NT; ++n) { c[mt][n][0] = nxt[mt][n].x; c[mt][n][1] = nxt[mt][n].y; }
+    if (r + 16 < mp) load_slab(r + 16, nxt);
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const double* vp = Vs + (r + lr) * LDV + 4 * ks + lk;
+      const double a0 = vp[0], a1 = vp[8 * LDV];
+#pragma unroll
+      for (int n = 0; n < NT; ++n) { dmma884(c[0][n], a0, bw[ks][n]); dmma884(c[1][n], a1, bw[ks][n]); }
+    }
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int n = 0; n < NT; ++n)
+        if (nv[n]) *reinterpret_cast<double2*>(abase + (size_t)(r + 8 * mt + lr) * ld + cw + 8 * n + 2 * lk) = make_double2(c[mt][n][0], c[mt][n][1]);
+  }
+}
+
+template <int NB, bool TRANS_T>
+__device__ void st_apply_reflector(double* __restrict__ Amat, int ld, int row0, int m, int c0, int c1,
+                                   const double* __restrict__ Vs, const double* __restrict__ Ts, double* __restrict__ Wt) {
+#if LQMC_ST_APPLY_DMMA
+  static_assert(NB == 16, "two 8-row accumulator tiles per reflector block");
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, lr = lane >> 2, lk = lane & 3;
+  const int mp = (m + 15) & ~15;
+  double* const abase = Amat + (size_t)row0 * ld;
+  double* const Ws = Wt + warp * NB * ST_LDS;
+  constexpr int NW = ST_THREADS / 32;
+  if (c1 - c0 > 16 * NW) {
+    for (int cw = c0 + 32 * warp; cw < c1; cw += 32 * NW) st_apply_strip<4, TRANS_T>(abase, ld, mp, cw, c1, Vs, Ts, Ws, lr, lk);
+  } else {
+    for (int cw = c0 + 16 * warp; cw < c1; cw += 16 * NW) st_apply_strip<2, TRANS_T>(abase, ld, mp, cw, c1, Vs, Ts, Ws, lr, lk);
+  }
+  __syncthreads();
+#else
+  st_apply_reflector_dfma<NB, TRANS_T>(Amat, ld, row0, m, c0, c1, Vs, Ts, Wt);
+#endif
+}
+
 template <int NB>
 struct StQrSmem {
-  static constexpr int LDV = NB + 2;
+  static constexpr int LDV = NB + 4;     // 2 LDV = 8 (mod 32): the DMMA fragment loads of V are bank-conflict-free
   double* P;      // [rows][LDV] panel / reflectors
   double* Ts;     // [NB][NB]
   double* Gm;     // [NB][NB]
   double* taus;   // [NB]
   double* dots;   // [NB]
-  double* Wt;     // [NB][ST_CB]
+  double* Wt;     // [NB][ST_WT_LD]: DFMA variant [NB][ST_CB]; DMMA variant 8 warps x [NB][ST_LDS]
   __device__ StQrSmem(unsigned char* base, int rows) {
     P = reinterpret_cast<double*>(base);
     Ts = P + (size_t)rows * LDV;
@@ -317,13 +447,13 @@ struct StQrSmem {
     dots = taus + NB;
     Wt = dots + NB;
   }
-  static size_t bytes(int rows) { return ((size_t)rows * (NB + 2) + 2 * NB * NB + 2 * NB + (size_t)NB * ST_CB) * sizeof(double); }
+  static size_t bytes(int rows) { return ((size_t)rows * (NB + 4) + 2 * NB * NB + 2 * NB + (size_t)NB * ST_WT_LD) * sizeof(double); }
 };
 
 // T factor of the panel's block reflector from the explicit V in sm.P (m rows, w valid columns) and sm.taus
 template <int NB>
 __device__ void st_form_t(StQrSmem<NB>& sm, int m, int w) {
-  constexpr int LDV = NB + 2;
+  constexpr int LDV = NB + 4;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int q = tid; q < NB * NB; q += ST_THREADS) { sm.Ts[q] = 0.0; sm.Gm[q] = 0.0; }
   __syncthreads();
@@ -363,7 +493,7 @@ struct StQrArgs {
 
 template <int NB>
 __global__ void __launch_bounds__(ST_THREADS) st_qr_kernel(const StQrArgs a) {
-  constexpr int LDV = NB + 2;
+  constexpr int LDV = NB + 4;
   extern __shared__ __align__(16) unsigned char st_smem[];
   const int N = a.N, NP = a.NPs;
   StQrSmem<NB> sm(st_smem, NP);
@@ -396,15 +526,17 @@ __global__ void __launch_bounds__(ST_THREADS) st_qr_kernel(const StQrArgs a) {
   }
   __syncthreads();
   // 2. A = M[:, perm]
-  for (int r = warp; r < N; r += ST_THREADS / 32)
-    for (int j = lane; j < N; j += 32) A[(size_t)r * NP + j] = M[(size_t)r * NP + perm[j]];
+  // (rows up to roundup(N, 16) and all NP columns: the DMMA reflector application runs over whole tiles of zero padding)
+  const int n16 = (N + 15) & ~15;
+  for (int r = warp; r < n16; r += ST_THREADS / 32)
+    for (int j = lane; j < NP; j += 32) A[(size_t)r * NP + j] = (r < N && j < N) ? M[(size_t)r * NP + perm[j]] : 0.0;
   __syncthreads();
 
   // 3. panels
   for (int j0 = 0; j0 < N; j0 += NB) {
     const int w = min(NB, N - j0), m = N - j0;
-    for (int r = warp; r < m; r += ST_THREADS / 32)
-      if (lane < NB) sm.P[r * LDV + lane] = (lane < w) ? A[(size_t)(j0 + r) * NP + j0 + lane] : 0.0;
+    for (int r = warp; r < ((m + 15) & ~15); r += ST_THREADS / 32)
+      if (lane < NB) sm.P[r * LDV + lane] = (lane < w && r < m) ? A[(size_t)(j0 + r) * NP + j0 + lane] : 0.0;
     if (tid < NB) sm.taus[tid] = 0.0;
     __syncthreads();
     double scale_prev = 0.0, beta_prev = 0.0, tau_prev = 0.0;
@@ -474,10 +606,10 @@ __global__ void __launch_bounds__(ST_THREADS) st_qr_kernel(const StQrArgs a) {
   const int n_panels = (N + NB - 1) / NB;
   for (int pb = n_panels - 1; pb >= 0; --pb) {
     const int j0 = pb * NB, w = min(NB, N - j0), m = N - j0;
-    for (int r = warp; r < m; r += ST_THREADS / 32)
+    for (int r = warp; r < ((m + 15) & ~15); r += ST_THREADS / 32)
       if (lane < NB) {
         double v = 0.0;
-        if (lane < w) v = (r > lane) ? A[(size_t)(j0 + r) * NP + j0 + lane] : (r == lane ? 1.0 : 0.0);
+        if (lane < w && r < m) v = (r > lane) ? A[(size_t)(j0 + r) * NP + j0 + lane] : (r == lane ? 1.0 : 0.0);
         sm.P[r * LDV + lane] = v;
       }
     for (int q = tid; q < NB * NB; q += ST_THREADS) sm.Ts[q] = tfac[(size_t)j0 * NB + q];
