@@ -82,6 +82,8 @@ def _kin(kind, size, mu):
     ("square", 10, 4.0, 4.0, 40, 0.0, 3, 8),         # N = 100 (padded to 128)
     ("square", 12, 4.0, 2.0, 20, 0.0, 19, 5),        # N = 144 (padded to 256)
     ("square", 16, 4.0, 8.0, 80, 0.0, 0, 8),         # BASELINE configs[3] at true half filling
+    ("square", 9, 4.0, 3.0, 30, 0.0, 11, 6),         # N = 81: odd size above 64 (column tiles of the DMMA reflector straddle N)
+    ("square", 24, 6.0, 10.0, 100, 0.0, 0, 8),       # BASELINE configs[4] size: N = 576 (padded to 640), beta = 10
 ])
 def test_stabilised_recompute_matches_oracle(case):
     """`lqmc_recompute_stable` against the oracle's NumPy QR/UDV (`physics_g_stable`, same pre-pivoted scheme) and,
