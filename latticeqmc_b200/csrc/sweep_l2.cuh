@@ -23,6 +23,7 @@
 // FP64 has no tcgen05 kind, and DMMA issues to the same pipe as DFMA on sm_100a (profiles/fp64_peaks_r01.json),
 // so these GEMMs are register-tiled DFMA kernels measured against the FP64 pipe peak.
 #pragma once
+#include <type_traits>
 #include <cuda_runtime.h>
 #include <cuda_pipeline_primitives.h>
 #include <stdint.h>
@@ -36,7 +37,7 @@ namespace lqmc {
 struct L2Workspace {
   double* T = nullptr;      // [chain][2][NP][NP] second matrix buffer (two-GEMM wrap, running product)
   int kd = 0;               // delay depth the shared-memory budget allows
-  bool tmem_ok = false;     // the NP <= 256 tensor-memory slice path fits the shared-memory region
+  int tmem_mode = 0;        // tensor-memory slice path that fits the shared-memory region: 0 none, 1 NP <= 256, 2 NP = 512, 3 NP = 640
   size_t smem = 0;          // dynamic shared memory per CTA
 };
 
@@ -882,6 +883,223 @@ __device__ void l2_propose_slice_tmem(double* __restrict__ Gc, int NP, L2Smem& s
 #endif
 }
 
+// ---- 256 < NP <= 640: the tensor-memory slice path with several columns per thread ------------------------------------------
+// At N = 576 (BASELINE configs[4]) the generic path's delay depth is 9 (U and W in 220 KB of shared memory) and the flush -
+// 13 MB of G per 9 flips and chain - is 83 % of the slice phase and HBM-bound (5 TB/s with 148 chains, clock64 split in
+// profiles/r01e_cfg4_summary.md).  Same remedy as for NP <= 256: only U stays in shared memory, thread t parks the c history of
+// ITS columns t, t + 256, ... (CPT of them) in tensor memory, which buys delay depth KDX = 16 (NP = 640) / 24 (NP = 512).  One
+// CTA per SM at these sizes, so the whole 512-column TMEM is this CTA's: window of warp w = [4 CPT KDX (w / 4), ...), inside it
+// column-set q, spin s, update m at 32-bit column 2 ((2 q + s) KDX + m).  Same roundings in the same order as the generic path.
+constexpr int L2_TMEMX_COLS = 512;
+__device__ __forceinline__ uint32_t tmem_alloc_cta_x(uint32_t* slot) {
+  if ((threadIdx.x >> 5) == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "n"(L2_TMEMX_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  return *slot;
+}
+__device__ __forceinline__ void tmem_free_cta_x(uint32_t base) {
+  __syncthreads();
+  if ((threadIdx.x >> 5) == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "n"(L2_TMEMX_COLS) : "memory");
+}
+
+// All CPT columns of a thread in one pass per spin: with one CTA (8 warps) per SM the one-column walk cannot fill the FP64
+// pipe (clock64 split at N = 576: 53.8 K clocks per flip alone on an SM against a floor of 25.6 K); CPT columns per e value
+// loaded give CPT x 8 independent multiply-subtract chains per thread and 1 / CPT of the shared-memory loads per update.
+// The c histories of all columns (CPT x KDX doubles) live in registers for the pass - these kernels run one CTA per SM and
+// may use 255 registers.
+template <bool EXACT, int CPT, int KDX>
+__device__ void l2_flush_tmemx(double* __restrict__ Gc, int NP, int nd, const double* __restrict__ U3, uint32_t tm_my) {
+  const int tid = threadIdx.x;
+  bool jv[CPT];
+#pragma unroll
+  for (int q = 0; q < CPT; ++q) jv[q] = tid + L2_THREADS * q < NP;       // warp-uniform: NP is a multiple of 128
+  for (int spin = 0; spin < 2; ++spin) {
+    double cj[CPT][KDX];
+#pragma unroll
+    for (int q = 0; q < CPT; ++q)
+#pragma unroll
+      for (int m0 = 0; m0 < KDX; m0 += 8) {
+        double v[8];
+        tmem_ld_f64x8(tm_my + 2 * ((2 * q + spin) * KDX + m0), v);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) cj[q][m0 + t] = v[t];
+      }
+    double* const col = Gc + (size_t)spin * NP * NP + tid;
+    const double* const Us = U3 + (size_t)spin * KDX * NP;
+    double nxt[CPT][8];
+#pragma unroll
+    for (int q = 0; q < CPT; ++q)
+#pragma unroll
+      for (int r = 0; r < 8; ++r) nxt[q][r] = jv[q] ? col[(size_t)r * NP + L2_THREADS * q] : 0.0;
+    for (int r0 = 0; r0 < NP; r0 += 8) {
+      double g[CPT][8];
+#pragma unroll
+      for (int q = 0; q < CPT; ++q)
+#pragma unroll
+        for (int r = 0; r < 8; ++r) g[q][r] = nxt[q][r];
+      if (r0 + 8 < NP) {
+#pragma unroll
+        for (int q = 0; q < CPT; ++q)
+#pragma unroll
+          for (int r = 0; r < 8; ++r) nxt[q][r] = jv[q] ? col[(size_t)(r0 + 8 + r) * NP + L2_THREADS * q] : 0.0;
+      }
+#pragma unroll
+      for (int m = 0; m < KDX; ++m) {
+        if (m < nd) {
+          const double* ur = Us + (size_t)m * NP + r0;
+#pragma unroll
+          for (int r = 0; r < 8; r += 2) {
+            const double2 e = *reinterpret_cast<const double2*>(ur + r);
+#pragma unroll
+            for (int q = 0; q < CPT; ++q) {
+              g[q][r] = rank1<EXACT>(g[q][r], e.x, cj[q][m]);
+              g[q][r + 1] = rank1<EXACT>(g[q][r + 1], e.y, cj[q][m]);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < CPT; ++q)
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+          if (jv[q]) col[(size_t)(r0 + r) * NP + L2_THREADS * q] = g[q][r];
+    }
+  }
+  __syncthreads();
+}
+
+template <bool EXACT, bool PHYS, int CPT, int KDX>
+__device__ void l2_propose_slice_tmemx(double* __restrict__ Gc, int NP, L2Smem& sm, const SweepParams& p, long long trace_base,
+                                       int& n_accepted, uint32_t tm_base) {
+  static_assert(KDX % 8 == 0 && 8 * CPT * KDX <= L2_TMEMX_COLS && 2 * KDX <= 62, "TMEM windows / history slots");
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int N = p.n_sites;
+  double* const U3 = sm.U;                       // [2][KDX][NP]
+  double* const wis = sm.hist;                   // [2][KDX] c history of the site being flipped
+  const uint32_t tm_my = tm_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)((warp >> 2) * 4 * CPT * KDX);
+  for (int spin = 0; spin < 2; ++spin)
+    for (int q = tid; q < NP; q += L2_THREADS) sm.d[spin * NP + q] = Gc[(size_t)spin * NP * NP + (size_t)q * NP + q];
+  __syncthreads();
+  int nd = 0, i0 = 0, cur = 0;
+  while (i0 < N) {
+    const double* dcur = sm.d + cur * 2 * NP;
+    double* dnxt = sm.d + (cur ^ 1) * 2 * NP;
+    const int i = i0 + lane;
+    bool acc = false;
+    double gu = 0.0, gd = 0.0, ratio = 0.0;
+    int8_t h = 1;
+    if (i < N) {
+      h = sm.h[i];
+      gu = dcur[i];
+      gd = dcur[NP + i];
+      const double fu = (h > 0) ? p.f_p2 : p.f_m2;
+      const double fd = (h > 0) ? p.f_m2 : p.f_p2;
+      const double du = __dadd_rn(1.0, __dmul_rn(__dsub_rn(1.0, gu), fu));
+      const double dd = __dadd_rn(1.0, __dmul_rn(__dsub_rn(1.0, gd), fd));
+      ratio = __dmul_rn(du, dd);
+      acc = sm.u[i] <= ratio;
+    }
+    const unsigned ballot = __ballot_sync(0xffffffffu, acc);
+    const int first = ballot ? (__ffs(ballot) - 1) : 32;
+    if (p.tr_ratio != nullptr && tid < 32 && i < N && lane <= first) {
+      p.tr_ratio[trace_base + i] = ratio;
+      p.tr_acc[trace_base + i] = (lane == first) ? 1 : 0;
+    }
+    if (!ballot) { i0 += 32; continue; }
+    const int is = i0 + first;
+    gu = __shfl_sync(0xffffffffu, gu, first);
+    gd = __shfl_sync(0xffffffffu, gd, first);
+    const int hs = __shfl_sync(0xffffffffu, (int)h, first);
+    const double fu = (hs > 0) ? p.f_p2 : p.f_m2;
+    const double fd = (hs > 0) ? p.f_m2 : p.f_p2;
+    // G0 row / column of the flipped site, both spins, all of this thread's columns, issued together
+    double row[CPT][2], col[CPT][2];
+#pragma unroll
+    for (int q = 0; q < CPT; ++q) {
+      const int j = tid + L2_THREADS * q;
+#pragma unroll
+      for (int spin = 0; spin < 2; ++spin) {
+        const double* G = Gc + (size_t)spin * NP * NP;
+        row[q][spin] = (j < NP) ? G[(size_t)is * NP + j] : 0.0;
+        col[q][spin] = (j < NP) ? G[(size_t)j * NP + is] : 0.0;
+      }
+    }
+    // the warp that owns site `is` publishes that site's c history
+    {
+      const int t_is = is & (L2_THREADS - 1), q_is = is / L2_THREADS;
+      if (warp == (t_is >> 5)) {
+        for (int m0 = 0; m0 < nd; m0 += 8) {
+          double v0[8], v1[8];
+          tmem_ld_f64x8_pair(tm_my + 2 * ((2 * q_is) * KDX + m0), tm_my + 2 * ((2 * q_is + 1) * KDX + m0), v0, v1);
+          if (lane == (t_is & 31)) {
+#pragma unroll
+            for (int t = 0; t < 8; ++t) { wis[m0 + t] = v0[t]; wis[KDX + m0 + t] = v1[t]; }
+          }
+        }
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < CPT; ++q) {
+      const int j = tid + L2_THREADS * q;
+      if (j < NP) {
+        for (int m0 = 0; m0 < nd; m0 += 8) {
+          double wj[2][8];
+          tmem_ld_f64x8_pair(tm_my + 2 * ((2 * q) * KDX + m0), tm_my + 2 * ((2 * q + 1) * KDX + m0), wj[0], wj[1]);
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const int m = m0 + t;
+            if (m < nd) {
+#pragma unroll
+              for (int spin = 0; spin < 2; ++spin) {
+                const double* Um = U3 + ((size_t)spin * KDX + m) * NP;
+                row[q][spin] = rank1<EXACT>(row[q][spin], Um[is], wj[spin][t]);
+                col[q][spin] = rank1<EXACT>(col[q][spin], Um[j], wis[spin * KDX + m]);
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int spin = 0; spin < 2; ++spin) {
+          const double gs = spin ? gd : gu;
+          double e, c;
+          if (!PHYS) {
+            const double gamma = spin ? fu : fd;            // exp(-arg)-1 for up, exp(+arg)-1 for down (lqmc.py:320-323)
+            const double ci = __dadd_rn(__dmul_rn(-gamma, gs), gamma);
+            const double den = __dadd_rn(1.0, ci);
+            const double r = __drcp_rn(den);
+            c = __dmul_rn(-gamma, row[q][spin]);
+            if (j == is) c = __dadd_rn(c, gamma);
+            e = EXACT ? div_shared_rcp(col[q][spin], den, r, div_safe(den)) : col[q][spin] * r;
+          } else {
+            const double delta = spin ? fd : fu;
+            const double rr = __dadd_rn(1.0, __dmul_rn(__dsub_rn(1.0, gs), delta));
+            const double fac = delta / rr;
+            e = ((j == is) ? (1.0 - col[q][spin]) : -col[q][spin]) * fac;
+            c = row[q][spin];
+          }
+          U3[((size_t)spin * KDX + nd) * NP + j] = e;
+          tmem_st_f64(tm_my + 2 * ((2 * q + spin) * KDX + nd), c);
+          dnxt[spin * NP + j] = rank1<EXACT>(dcur[spin * NP + j], e, c);
+        }
+      }
+    }
+    tmem_wait_st();
+    ++n_accepted;
+    ++nd;
+    cur ^= 1;
+    __syncthreads();
+    if (tid == 0) sm.h[is] = (int8_t)(-hs);     // after the barrier: no warp is still scanning site `is`
+    if (nd == KDX) { l2_flush_tmemx<EXACT, CPT, KDX>(Gc, NP, nd, U3, tm_my); nd = 0; }
+    i0 = is + 1;
+  }
+  if (nd > 0) l2_flush_tmemx<EXACT, CPT, KDX>(Gc, NP, nd, U3, tm_my);
+}
+
 // ---- Gauss-Jordan inverse in memory (both spins in lockstep, in place), partial pivoting, delayed updates ----------
 // np.linalg.inv of the sweep-start matrix (lqmc.py:306-307).  A Gauss-Jordan step is a rank-1 update of the whole
 // matrix, so it is delayed exactly like the flips: the pivot column and pivot row of the *current* matrix are rebuilt
@@ -1074,13 +1292,15 @@ __device__ void l2_wrap(double* __restrict__ Gc, double* __restrict__ Tc, int NP
 struct L2Params {
   SweepParams p;
   double* T;
-  int use_tmem;   // 1: slice path with the c history in tensor memory (NP <= 256)
+  int use_tmem;   // slice path: 0 shared memory, 1 tensor memory (NP <= 256), 2 / 3 tensor memory with 2 / 3 columns per thread
   int* piv;       // [chain][2][NP] scratch
   int NP, KD;
 };
 
-template <bool EXACT, bool PHYS, bool TMEM>
-__global__ void __launch_bounds__(L2_THREADS, 2) sweep_l2_kernel(const L2Params lp) {
+// TMEM: 0 shared-memory slice path; 1 tensor-memory path, one column per thread (NP <= 256); 2 / 3 several columns per thread
+// (NP = 512: 2 x depth 24; NP = 640: 3 x depth 16; one CTA per SM at those sizes)
+template <bool EXACT, bool PHYS, int TMEM>
+__global__ void __launch_bounds__(L2_THREADS, TMEM >= 2 ? 1 : 2) sweep_l2_kernel(const L2Params lp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const SweepParams& p = lp.p;
   const int NP = lp.NP, KD = lp.KD;
@@ -1093,7 +1313,8 @@ __global__ void __launch_bounds__(L2_THREADS, 2) sweep_l2_kernel(const L2Params 
   int* piv = lp.piv + (size_t)chain * 2 * NP;
   int n_accepted = 0;
   uint32_t tm_base = 0;
-  if (TMEM) tm_base = tmem_alloc_cta(reinterpret_cast<uint32_t*>(sm.hist + 63));
+  if (TMEM == 1) tm_base = tmem_alloc_cta(reinterpret_cast<uint32_t*>(sm.hist + 63));
+  if (TMEM >= 2) tm_base = tmem_alloc_cta_x(reinterpret_cast<uint32_t*>(sm.hist + 63));
   if (tid == 0) {
     for (int s0 = 0; s0 < L2_STAGES; ++s0) mbar_init(sm.full + s0, 1);
     *reinterpret_cast<uint32_t*>(sm.hist + 62) = 0;          // panels consumed so far (TMA staging: stage / phase parity)
@@ -1121,7 +1342,9 @@ __global__ void __launch_bounds__(L2_THREADS, 2) sweep_l2_kernel(const L2Params 
                     : lqmc_philox_uniform(p.seed, (uint64_t)(p.chain0 + chain), (uint64_t)(p.sweep0 + sweep), (uint32_t)(step * N + j));
           sm.u[j] = u;
         }
-        if (TMEM) l2_propose_slice_tmem<EXACT, PHYS>(Gc, NP, sm, p, base, n_accepted, tm_base);
+        if (TMEM == 1) l2_propose_slice_tmem<EXACT, PHYS>(Gc, NP, sm, p, base, n_accepted, tm_base);
+        else if (TMEM == 2) l2_propose_slice_tmemx<EXACT, PHYS, 2, 24>(Gc, NP, sm, p, base, n_accepted, tm_base);
+        else if (TMEM == 3) l2_propose_slice_tmemx<EXACT, PHYS, 3, 16>(Gc, NP, sm, p, base, n_accepted, tm_base);
         else l2_propose_slice<EXACT, PHYS, L2_MAXQ>(Gc, NP, KD, sm, p, base, n_accepted);
         __syncthreads();
         for (int j = tid; j < NP; j += L2_THREADS) field[(size_t)l * NP + j] = sm.h[j];
@@ -1149,7 +1372,8 @@ __global__ void __launch_bounds__(L2_THREADS, 2) sweep_l2_kernel(const L2Params 
     }
   }
   if (tid == 0 && n_accepted) p.n_acc[chain] += n_accepted;
-  if (TMEM) tmem_free_cta(tm_base);
+  if (TMEM == 1) tmem_free_cta(tm_base);
+  if (TMEM >= 2) tmem_free_cta_x(tm_base);
 }
 
 // ---- host side ------------------------------------------------------------------------------------------------
@@ -1174,7 +1398,12 @@ inline int l2_alloc(L2Workspace& w, int n_sites, int np, int n_slices, int n_cha
     size_t region = (size_t)4 * kd * np;
     const size_t gemm = (size_t)L2_STAGES * L2_BK * (L2_BM + L2_BN + 8);
     if (region < gemm) region = gemm;
-    w.tmem_ok = (size_t)2 * L2_KDT * np <= region;
+    w.tmem_mode = ((size_t)2 * L2_KDT * np <= region) ? 1 : 0;
+  } else if (np == 512 || np == 640) {
+    // several columns per thread: U [2][24][512] / [2][16][640] in the generic path's U / W region, one CTA per SM
+    const size_t region = (size_t)4 * kd * np;
+    const size_t need = (np == 512) ? (size_t)2 * 24 * np : (size_t)2 * 16 * np;
+    w.tmem_mode = (need <= region) ? (np == 512 ? 2 : 3) : 0;
   }
   return 0;
 }
@@ -1184,7 +1413,7 @@ inline int launch_l2(L2Workspace& w, const SweepParams& p, int np, uint32_t flag
                      size_t errlen) {
   L2Params lp;
   lp.p = p; lp.T = w.T; lp.NP = np; lp.KD = w.kd;
-  lp.use_tmem = (w.tmem_ok && p.do_propose) ? 1 : 0;
+  lp.use_tmem = p.do_propose ? w.tmem_mode : 0;
   if (const char* env = getenv("LQMC_L2_SLICE_PATH")) { if (strcmp(env, "smem") == 0) lp.use_tmem = 0; }     // experiments
   lp.piv = reinterpret_cast<int*>(w.T + (size_t)p.n_chains * 2 * np * np);
   const bool exact = !(flags & 0x2u), phys = (flags & 0x1u) != 0;
@@ -1198,16 +1427,19 @@ inline int launch_l2(L2Workspace& w, const SweepParams& p, int np, uint32_t flag
     *launches += 1;
     return 0;
   };
-  if (lp.use_tmem) {
-    if (exact && !phys) return go(sweep_l2_kernel<true, false, true>);
-    if (!exact && !phys) return go(sweep_l2_kernel<false, false, true>);
-    if (exact && phys) return go(sweep_l2_kernel<true, true, true>);
-    return go(sweep_l2_kernel<false, true, true>);
+  auto pick = [&](auto tm) -> int {
+    constexpr int TM = decltype(tm)::value;
+    if (exact && !phys) return go(sweep_l2_kernel<true, false, TM>);
+    if (!exact && !phys) return go(sweep_l2_kernel<false, false, TM>);
+    if (exact && phys) return go(sweep_l2_kernel<true, true, TM>);
+    return go(sweep_l2_kernel<false, true, TM>);
+  };
+  switch (lp.use_tmem) {
+    case 1: return pick(std::integral_constant<int, 1>());
+    case 2: return pick(std::integral_constant<int, 2>());
+    case 3: return pick(std::integral_constant<int, 3>());
+    default: return pick(std::integral_constant<int, 0>());
   }
-  if (exact && !phys) return go(sweep_l2_kernel<true, false, false>);
-  if (!exact && !phys) return go(sweep_l2_kernel<false, false, false>);
-  if (exact && phys) return go(sweep_l2_kernel<true, true, false>);
-  return go(sweep_l2_kernel<false, true, false>);
 }
 
 }  // namespace lqmc

@@ -103,11 +103,14 @@ def test_free_running_sweep_10x10(arith):
         assert m["n_accepted"][c] == acc[c].sum() and m["n_meas"][c] == 2
 
 
-def test_delayed_updates_equal_undelayed_bitwise():
+@pytest.mark.parametrize("size", [12, 18, 20])
+def test_delayed_updates_equal_undelayed_bitwise(size):
     """EXACT mode: a slice run through the delayed rank-k path equals the oracle's one-flip-at-a-time
-    rank-1 updates bit for bit (same roundings per element), here with ~60% acceptance and N = 144."""
-    ham = so.ideal_square_kinetic(12, 1.0, 2.0)
-    n, lt = 144, 8
+    rank-1 updates bit for bit (same roundings per element), with ~60% acceptance: N = 144 (padded 256: tensor-memory path,
+    one column per thread, two-column flush), N = 324 (padded 384: shared-memory path), N = 400 (padded 512: tensor-memory
+    path with two columns per thread, delay depth 24)."""
+    ham = so.ideal_square_kinetic(size, 1.0, 2.0)
+    n, lt = size * size, 8
     dtau, lamb, exp_k = so.set_beta_constants(ham, 4.0, 1.0, lt)
     h = so.initial_field(n, lt, seed=5)
     gu, gd = so.sweep_start_g(h, exp_k, lamb)

@@ -39,6 +39,33 @@ def test_physics_sweep_matches_oracle():
         assert np.allclose(gg[c, 0], gu, atol=1e-7) and np.allclose(gg[c, 1], gd, atol=1e-7)
 
 
+@pytest.mark.parametrize("size", [20, 24])
+def test_physics_sweep_large_lattices_match_oracle(size):
+    """Physics-mode sweep on the multi-column tensor-memory slice paths: N = 400 (padded 512, two columns per thread, delay
+    depth 24) and N = 576 (padded 640, three columns, depth 16; BASELINE configs[4] size) at beta = 0.4, L = 4 - same accept /
+    reject decisions as the oracle's `physics_sweep` on the same uniforms, G to 1e-9."""
+    from latticeqmc_b200 import SweepEngine
+    ham = so.ideal_square_kinetic(size, 1.0, 0.0)
+    n, lt = size * size, 4
+    dtau, lamb, exp_k = so.set_beta_constants(ham, 4.0, 0.4, lt)
+    exp_k_inv = expm(dtau * ham)
+    field = so.initial_field(n, lt, 77)
+    uni = np.random.RandomState(9).rand(1, 1, lt, n)
+    with SweepEngine(exp_k, lamb, lt, n_chains=1, exp_k_inv=exp_k_inv, mode="physics", trace=True) as eng:
+        assert eng.info()["n_pad"] == (512 if size == 20 else 640)
+        eng.set_field(field[None])
+        eng.sweep(1, uni)
+        acc, ratio = eng.get_trace()
+        gg = eng.get_g()[0]
+        out = eng.get_field()[0]
+    h = field.copy()
+    gu, gd, r, a = so.physics_sweep(h, exp_k, exp_k_inv, lamb, uni[0, 0])
+    assert 0.2 < a.mean() < 0.95
+    assert np.array_equal(a, acc[0, 0]) and np.array_equal(h, out)
+    assert np.allclose(r, ratio[0, 0], rtol=1e-8, atol=1e-10)
+    assert np.abs(gg[0] - gu).max() < 1e-9 and np.abs(gg[1] - gd).max() < 1e-9
+
+
 def test_physics_mode_agrees_with_exact_diagonalisation():
     """2x2, U=4, t=1, beta=2, dtau=0.1, half filling: 512 chains x 150 measured sweeps.  ED: n = 0.5/0.5,
     <n_up n_dn> = 0.0873, local moment 0.8254.  Tolerance = Trotter error O(U t dtau^2) + statistics."""
