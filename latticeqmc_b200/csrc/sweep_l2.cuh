@@ -50,7 +50,14 @@ constexpr int L2_GY = 16, L2_GX = 16;                  // thread grid inside a b
 constexpr int L2_STAGES = 3;                           // operand-panel ring depth
 constexpr int L2_MAXQ = 4;                             // indices per thread in the vector phases (NP <= 1024)
 
-inline int l2_padded_size(int n_sites) {
+// Padded matrix size: a multiple of 128 (GEMM block tile 64 x 128, flush tiles of 128 columns) - except for 512 < N <= 576 in
+// parity mode, which gets 576 = 9 x 64: BASELINE configs[4] is N = 576, and padding it to 640 costs (640/576)^3 = 1.37 x the
+// GEMM work (ncu on the cfg5 wrap: DMMA pipe 80 % busy at 21.5 algorithmic TFLOP/s).  The GEMM and the generic flush handle
+// the half tile at the right edge; the stabilisation kernels (physics mode) keep the 128 multiple.
+inline int l2_padded_size(int n_sites, bool physics = false) {
+#if !LQMC_L2_STAGING_TMA
+  if (!physics && n_sites > 512 && n_sites <= 576) return 576;
+#endif
   const int np = (n_sites + 127) / 128 * 128;
   return np <= 1024 ? np : -1;
 }
@@ -214,7 +221,7 @@ __device__ __noinline__ void l2_gemm_sub(const double* __restrict__ At, const do
 #pragma unroll
         for (int m = 0; m < 4; ++m) hr[m] = ep.hrow[i0 + 32 * wm + 8 * m + lr];
       }
-      if (ep.hcol) {
+      if (ep.hcol && j0 + 32 * wn < NP) {
 #pragma unroll
         for (int n = 0; n < 4; ++n) hc[n] = *reinterpret_cast<const unsigned short*>(ep.hcol + j0 + 32 * wn + 8 * n + 2 * lk);
       }
@@ -259,6 +266,8 @@ __device__ __noinline__ void l2_gemm_sub(const double* __restrict__ At, const do
       // LDGSTS ring: every thread copies 2 (A) + 4 (B) 16-byte chunks per panel; addresses set up once per tile
       const double* srcA = At + (size_t)(tid >> 5) * NP + i0 + 2 * (tid & 31);          // rows tid/32 (+8), chunk tid%32
       const double* srcB = B + (size_t)(tid >> 6) * NP + j0 + 2 * (tid & 63);           // rows tid/64 (+4 q), chunk tid%64
+      const bool b_ok = j0 + 2 * (tid & 63) < NP;          // half tile at the right edge (NP = 64 mod 128): no copy, no compute
+      const bool w_ok = j0 + 32 * wn < NP;                 // warp-uniform
       double* dstA = sm.pa + (tid >> 5) * L2_LDA + 2 * (tid & 31);
       double* dstB = sm.pb + (tid >> 6) * L2_LDB + 2 * (tid & 63);
       auto issue = [&](int kpanel, int stage) {
@@ -266,9 +275,11 @@ __device__ __noinline__ void l2_gemm_sub(const double* __restrict__ At, const do
 #pragma unroll
         for (int q = 0; q < 2; ++q)
           __pipeline_memcpy_async(dstA + stage * L2_BK * L2_LDA + q * 8 * L2_LDA, srcA + koff + (size_t)q * 8 * NP, 16);
+        if (b_ok) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-          __pipeline_memcpy_async(dstB + stage * L2_BK * L2_LDB + q * 4 * L2_LDB, srcB + koff + (size_t)q * 4 * NP, 16);
+          for (int q = 0; q < 4; ++q)
+            __pipeline_memcpy_async(dstB + stage * L2_BK * L2_LDB + q * 4 * L2_LDB, srcB + koff + (size_t)q * 4 * NP, 16);
+        }
       };
 #pragma unroll
       for (int s0 = 0; s0 < L2_STAGES - 1; ++s0) {
@@ -283,23 +294,26 @@ __device__ __noinline__ void l2_gemm_sub(const double* __restrict__ At, const do
         __pipeline_commit();
         const double* ap = pa + st * L2_BK * L2_LDA + lk * L2_LDA + 32 * wm + lr;
         const double* bp = pb + st * L2_BK * L2_LDB + lk * L2_LDB + 32 * wn + lr;
+        if (w_ok) {
 #pragma unroll
-        for (int k4 = 0; k4 < L2_BK / 4; ++k4) {
-          double a[4], b[4];
+          for (int k4 = 0; k4 < L2_BK / 4; ++k4) {
+            double a[4], b[4];
 #pragma unroll
-          for (int m = 0; m < 4; ++m) a[m] = ap[4 * k4 * L2_LDA + 8 * m];
+            for (int m = 0; m < 4; ++m) a[m] = ap[4 * k4 * L2_LDA + 8 * m];
 #pragma unroll
-          for (int n = 0; n < 4; ++n) b[n] = bp[4 * k4 * L2_LDB + 8 * n];
+            for (int n = 0; n < 4; ++n) b[n] = bp[4 * k4 * L2_LDB + 8 * n];
 #pragma unroll
-          for (int m = 0; m < 4; ++m)
+            for (int m = 0; m < 4; ++m)
 #pragma unroll
-            for (int n = 0; n < 4; ++n) dmma884(acc[m][n], a[m], b[n]);
+              for (int n = 0; n < 4; ++n) dmma884(acc[m][n], a[m], b[n]);
+          }
         }
       }
       __pipeline_wait_prior(0);
       __syncthreads();                               // panels free for the next tile
 #endif
       // epilogue: element (row, col) = acc[m][n][s]; the field bytes were fetched before the main loop
+      if (j0 + 32 * wn >= NP) continue;        // half tile at the right edge: this warp owns no columns (warp-uniform)
 #pragma unroll
       for (int m = 0; m < 4; ++m) {
         const int row = i0 + 32 * wm + 8 * m + lr;
@@ -345,27 +359,27 @@ __device__ __forceinline__ void l2_gemm(const double* __restrict__ At, const dou
 template <bool EXACT, int NS = 2>
 __device__ void l2_flush(double* __restrict__ Gc, int NP, int nd, L2Smem& sm, int KD) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int n_tiles = NS * (NP / 32) * (NP / 128);
+  const int n_tiles = NS * (NP / 32) * ((NP + 127) / 128);     // NP = 64 mod 128: the last tile of a row band is half a tile
   double* const thread_base = Gc + (size_t)(4 * warp) * NP + 2 * lane;
   // tile walk (spin, i0, j0) kept as running offsets: no integer division in the loop (the XU pipe is 1/4 rate)
   struct Walk { int spin, i0, j0; };
   auto advance = [&](Walk& w) {
     w.j0 += 128;
-    if (w.j0 == NP) { w.j0 = 0; w.i0 += 32; if (w.i0 == NP) { w.i0 = 0; w.spin += 1; } }
+    if (w.j0 >= NP) { w.j0 = 0; w.i0 += 32; if (w.i0 == NP) { w.i0 = 0; w.spin += 1; } }
   };
   auto tile_ptr_w = [&](const Walk& w) -> double* { return thread_base + ((size_t)w.spin * NP + w.i0) * NP + w.j0; };
-  auto load_tile4 = [&](const double* base, double (&g)[4][4]) {
+  auto load_tile4 = [&](const double* base, double (&g)[4][4], bool full) {
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
-        const double2 v = *reinterpret_cast<const double2*>(base + (size_t)a * NP + 64 * q);
+        const double2 v = (q == 0 || full) ? *reinterpret_cast<const double2*>(base + (size_t)a * NP + 64 * q) : make_double2(0.0, 0.0);
         g[a][2 * q] = v.x; g[a][2 * q + 1] = v.y;
       }
   };
   Walk wc{0, 0, 0}, wn{0, 0, 0};
   double nxt[4][4];
-  load_tile4(tile_ptr_w(wn), nxt);
+  load_tile4(tile_ptr_w(wn), nxt, wn.j0 + 64 < NP);
   for (int t = 0; t < n_tiles; ++t) {
     double g[4][4];
 #pragma unroll
@@ -373,8 +387,9 @@ __device__ void l2_flush(double* __restrict__ Gc, int NP, int nd, L2Smem& sm, in
 #pragma unroll
       for (int b = 0; b < 4; ++b) g[a][b] = nxt[a][b];
     double* base = tile_ptr_w(wc);
+    const bool full = wc.j0 + 64 < NP;
     advance(wn);
-    if (t + 1 < n_tiles) load_tile4(tile_ptr_w(wn), nxt);
+    if (t + 1 < n_tiles) load_tile4(tile_ptr_w(wn), nxt, wn.j0 + 64 < NP);
     const double* U = sm.U + (size_t)wc.spin * KD * NP + wc.i0 + 4 * warp;
     const double* W = sm.W + (size_t)wc.spin * KD * NP + wc.j0 + 2 * lane;
     advance(wc);
@@ -404,7 +419,7 @@ __device__ void l2_flush(double* __restrict__ Gc, int NP, int nd, L2Smem& sm, in
     for (int a = 0; a < 4; ++a)
 #pragma unroll
       for (int q = 0; q < 2; ++q)
-        *reinterpret_cast<double2*>(base + (size_t)a * NP + 64 * q) = make_double2(g[a][2 * q], g[a][2 * q + 1]);
+        if (q == 0 || full) *reinterpret_cast<double2*>(base + (size_t)a * NP + 64 * q) = make_double2(g[a][2 * q], g[a][2 * q + 1]);
   }
   __syncthreads();
 }
@@ -1399,7 +1414,7 @@ inline int l2_alloc(L2Workspace& w, int n_sites, int np, int n_slices, int n_cha
     const size_t gemm = (size_t)L2_STAGES * L2_BK * (L2_BM + L2_BN + 8);
     if (region < gemm) region = gemm;
     w.tmem_mode = ((size_t)2 * L2_KDT * np <= region) ? 1 : 0;
-  } else if (np == 512 || np == 640) {
+  } else if (np == 512 || np == 576 || np == 640) {
     // several columns per thread: U [2][24][512] / [2][16][640] in the generic path's U / W region, one CTA per SM
     const size_t region = (size_t)4 * kd * np;
     const size_t need = (np == 512) ? (size_t)2 * 24 * np : (size_t)2 * 16 * np;

@@ -55,7 +55,9 @@ def test_cfg4_reference_slices(golden):
 
 
 @pytest.mark.parametrize("case", [("square", 9, 4.0, 1.0, 10), ("square", 12, 4.0, 1.0, 8), ("ring", 100, 2.0, 0.8, 8),
-                                   ("square", 16, 4.0, 0.8, 8)])
+                                   ("square", 16, 4.0, 0.8, 8),
+                                   ("square", 23, 4.0, 0.5, 5),    # N = 529, padded to 576 = 9 x 64: half GEMM / flush tile at the right edge
+                                   ("square", 24, 6.0, 0.6, 6)])   # N = 576: BASELINE configs[4] lattice, unpadded in parity mode
 def test_recompute_large(case):
     """Sweep-start G (get_m + inv, lqmc.py:156-185,303-307) on well-conditioned products; N = 81, 144, 100
     need padding to the 128-wide tile, 256 does not."""
@@ -73,6 +75,26 @@ def test_recompute_large(case):
         cond = np.linalg.cond(so.get_m(fields[c], exp_k, lamb, 0, +1))
         tol = max(RTOL_G, 50 * cond * 2.2e-16)
         assert _close(gg[c, 0], ref[0], tol) and _close(gg[c, 1], ref[1], tol), (case, c, cond)
+
+
+def test_free_running_sweep_23x23():
+    """N = 529 (padded to 576: the half-tile paths of the GEMM, the Gauss-Jordan flush and the three-column tensor-memory slice
+    phase), U=4, beta=0.4, L=4: one full free-running sweep against the oracle - identical accept / reject sequence, G to 1e-9."""
+    ham = so.ideal_square_kinetic(23, 1.0, 2.0)
+    n, lt = 529, 4
+    dtau, lamb, exp_k = so.set_beta_constants(ham, 4.0, 0.4, lt)
+    field = so.initial_field(n, lt, seed=404)
+    uni = np.random.RandomState(23).rand(1, 1, lt, n)
+    with _engine(exp_k, lamb, lt, n_chains=1, trace=True) as eng:
+        assert eng.info()["n_pad"] == 576
+        eng.set_field(field[None])
+        eng.sweep(1, uni, measure=True)
+        acc, ratio = eng.get_trace()
+        gg, ff = eng.get_g()[0], eng.get_field()[0]
+    h = field.copy()
+    gu, gd, r, a = so.update_step(h, exp_k, lamb, uni[0, 0])
+    assert np.array_equal(a, acc[0, 0]) and np.array_equal(h, ff)
+    assert _close(gg[0], gu, 1e-9) and _close(gg[1], gd, 1e-9)
 
 
 @pytest.mark.parametrize("arith", ["exact", "fma"])
@@ -147,7 +169,7 @@ def test_cfg5_slice_is_bit_exact_at_full_size():
     gd = np.linalg.inv(np.eye(n) + prod)
     u = np.random.RandomState(5).rand(n)
     with _engine(exp_k, lamb, lt, trace=True) as eng:
-        assert eng.info()["family"] == "l2" and eng.info()["n_pad"] == 640
+        assert eng.info()["family"] == "l2" and eng.info()["n_pad"] == 576      # 9 x 64: parity mode pads N = 576 to itself
         eng.set_field(h[None])
         eng.set_g(np.stack([gu, gd])[None])
         eng.slice(lt - 1, u[None])
