@@ -240,8 +240,8 @@ int stab_init(lqmc_engine* e) {
   CU(cudaSetDevice(e->device));
   st.NPs = lqmc::st_padded_size(e->N);
   if (e->N > 64 && st.NPs != e->NP)
-    return fail(LQMC_ERR_UNSUPPORTED, "the stabilisation kernels need the 128-padded layout (N = %d is padded to %d in parity mode): "
-                                      "create the engine in physics mode", e->N, e->NP);
+    return fail(LQMC_ERR_UNSUPPORTED, "stabilisation kernels and sweep kernels disagree on the padded size (N = %d: %d vs %d)", e->N,
+                st.NPs, e->NP);
   st.nfrag = (st.NPs == 64) ? 2 : 4;
   const size_t nm = (size_t)2 * e->C, mat = (size_t)st.NPs * st.NPs;
   for (int i = 0; i < 6; ++i)
@@ -574,7 +574,7 @@ int lqmc_create(lqmc_engine** out, int device, int n_sites, int n_slices, int n_
     e->NP = n_sites <= 16 ? 16 : (n_sites <= 32 ? 32 : 64);
   } else {
     e->family_reg = false;
-    e->NP = lqmc::l2_padded_size(n_sites, (flags & LQMC_MODE_PHYSICS) != 0);
+    e->NP = lqmc::l2_padded_size(n_sites);
     if (e->NP <= 0) { delete e; return fail(LQMC_ERR_UNSUPPORTED, "n_sites = %d exceeds the largest supported lattice", n_sites); }
   }
   const int NP = e->NP, N = e->N;

@@ -41,7 +41,7 @@ __device__ __forceinline__ double st_hs(int8_t h, int spin, bool inv, const HsCo
   return (minus != inv) ? c.exp_ml : c.exp_pl;
 }
 
-inline int st_padded_size(int n_sites) { return n_sites <= 64 ? 64 : (n_sites + 127) / 128 * 128; }
+inline int st_padded_size(int n_sites) { return n_sites <= 64 ? 64 : l2_padded_size(n_sites); }   // the sweep kernels' layout above 64
 
 // ---- GEMM  C = A * B,  A given k-major, B row-major (rows optionally gathered through bperm) ----------------------
 // how a scale vector enters: the value itself, 1 / max(v, 1)  (D_b^-1)  or  min(v, 1)  (D_s)
@@ -85,16 +85,20 @@ __device__ void st_gemm(const double* __restrict__ At, const double* __restrict_
       const double* srcA = At + (size_t)(tid >> 5) * NP + i0 + 2 * (tid & 31);
       double* dstA = pa + (tid >> 5) * ST_LDA + 2 * (tid & 31);
       double* dstB = pb + brow * LDB + 2 * bchunk;
+      const bool b_ok = j0 + 2 * bchunk < NP;               // half tile at the right edge (NP = 576): no copy, no compute, no store
+      const bool w_ok = j0 + 8 * NFRAG * wn < NP;           // warp-uniform
       auto issue = [&](int kpanel, int stage) {
         const int k0 = kpanel * ST_BK;
 #pragma unroll
         for (int q = 0; q < 2; ++q)
           __pipeline_memcpy_async(dstA + stage * ST_BK * ST_LDA + q * 8 * ST_LDA, srcA + (size_t)(k0 + q * 8) * NP, 16);
+        if (b_ok) {
 #pragma unroll
-        for (int q = 0; q < BQ; ++q) {
-          const int krow = k0 + brow + q * BSTEP;
-          const int srow = bperm ? bperm[krow] : krow;
-          __pipeline_memcpy_async(dstB + stage * ST_BK * LDB + q * BSTEP * LDB, B + (size_t)srow * NP + j0 + 2 * bchunk, 16);
+          for (int q = 0; q < BQ; ++q) {
+            const int krow = k0 + brow + q * BSTEP;
+            const int srow = bperm ? bperm[krow] : krow;
+            __pipeline_memcpy_async(dstB + stage * ST_BK * LDB + q * BSTEP * LDB, B + (size_t)srow * NP + j0 + 2 * bchunk, 16);
+          }
         }
       };
 #pragma unroll
@@ -110,21 +114,24 @@ __device__ void st_gemm(const double* __restrict__ At, const double* __restrict_
         __pipeline_commit();
         const double* ap = pa + st * ST_BK * ST_LDA + lk * ST_LDA + 32 * wm + lr;
         const double* bp = pb + st * ST_BK * LDB + lk * LDB + 8 * NFRAG * wn + lr;
+        if (w_ok) {
 #pragma unroll
-        for (int k4 = 0; k4 < ST_BK / 4; ++k4) {
-          double a[4], b[NFRAG];
+          for (int k4 = 0; k4 < ST_BK / 4; ++k4) {
+            double a[4], b[NFRAG];
 #pragma unroll
-          for (int m = 0; m < 4; ++m) a[m] = ap[4 * k4 * ST_LDA + 8 * m];
+            for (int m = 0; m < 4; ++m) a[m] = ap[4 * k4 * ST_LDA + 8 * m];
 #pragma unroll
-          for (int n = 0; n < NFRAG; ++n) b[n] = bp[4 * k4 * LDB + 8 * n];
+            for (int n = 0; n < NFRAG; ++n) b[n] = bp[4 * k4 * LDB + 8 * n];
 #pragma unroll
-          for (int m = 0; m < 4; ++m)
+            for (int m = 0; m < 4; ++m)
 #pragma unroll
-            for (int n = 0; n < NFRAG; ++n) dmma884(acc[m][n], a[m], b[n]);
+              for (int n = 0; n < NFRAG; ++n) dmma884(acc[m][n], a[m], b[n]);
+          }
         }
       }
       __pipeline_wait_prior(0);
       __syncthreads();
+      if (!w_ok) continue;
 #pragma unroll
       for (int m = 0; m < 4; ++m) {
         const int row = i0 + 32 * wm + 8 * m + lr;

@@ -50,13 +50,13 @@ constexpr int L2_GY = 16, L2_GX = 16;                  // thread grid inside a b
 constexpr int L2_STAGES = 3;                           // operand-panel ring depth
 constexpr int L2_MAXQ = 4;                             // indices per thread in the vector phases (NP <= 1024)
 
-// Padded matrix size: a multiple of 128 (GEMM block tile 64 x 128, flush tiles of 128 columns) - except for 512 < N <= 576 in
-// parity mode, which gets 576 = 9 x 64: BASELINE configs[4] is N = 576, and padding it to 640 costs (640/576)^3 = 1.37 x the
-// GEMM work (ncu on the cfg5 wrap: DMMA pipe 80 % busy at 21.5 algorithmic TFLOP/s).  The GEMM and the generic flush handle
-// the half tile at the right edge; the stabilisation kernels (physics mode) keep the 128 multiple.
-inline int l2_padded_size(int n_sites, bool physics = false) {
+// Padded matrix size: a multiple of 128 (GEMM block tile 64 x 128, flush tiles of 128 columns) - except for 512 < N <= 576,
+// which gets 576 = 9 x 64: BASELINE configs[4] is N = 576, and padding it to 640 costs (640/576)^3 = 1.37 x the GEMM work
+// (ncu on the cfg5 wrap: DMMA pipe 80 % busy at 21.5 algorithmic TFLOP/s).  The GEMMs (here and in stab.cuh) and the generic
+// flush handle the half tile at the right edge.
+inline int l2_padded_size(int n_sites) {
 #if !LQMC_L2_STAGING_TMA
-  if (!physics && n_sites > 512 && n_sites <= 576) return 576;
+  if (n_sites > 512 && n_sites <= 576) return 576;
 #endif
   const int np = (n_sites + 127) / 128 * 128;
   return np <= 1024 ? np : -1;

@@ -42,7 +42,7 @@ def test_physics_sweep_matches_oracle():
 @pytest.mark.parametrize("size", [20, 24])
 def test_physics_sweep_large_lattices_match_oracle(size):
     """Physics-mode sweep on the multi-column tensor-memory slice paths: N = 400 (padded 512, two columns per thread, delay
-    depth 24) and N = 576 (padded 640, three columns, depth 16; BASELINE configs[4] size) at beta = 0.4, L = 4 - same accept /
+    depth 24) and N = 576 (unpadded = 9 x 64, three columns, depth 16; BASELINE configs[4] size) at beta = 0.4, L = 4 - same accept /
     reject decisions as the oracle's `physics_sweep` on the same uniforms, G to 1e-9."""
     from latticeqmc_b200 import SweepEngine
     ham = so.ideal_square_kinetic(size, 1.0, 0.0)
@@ -52,7 +52,7 @@ def test_physics_sweep_large_lattices_match_oracle(size):
     field = so.initial_field(n, lt, 77)
     uni = np.random.RandomState(9).rand(1, 1, lt, n)
     with SweepEngine(exp_k, lamb, lt, n_chains=1, exp_k_inv=exp_k_inv, mode="physics", trace=True) as eng:
-        assert eng.info()["n_pad"] == (512 if size == 20 else 640)
+        assert eng.info()["n_pad"] == (512 if size == 20 else 576)
         eng.set_field(field[None])
         eng.sweep(1, uni)
         acc, ratio = eng.get_trace()
@@ -110,7 +110,8 @@ def _kin(kind, size, mu):
     ("square", 12, 4.0, 2.0, 20, 0.0, 19, 5),        # N = 144 (padded to 256)
     ("square", 16, 4.0, 8.0, 80, 0.0, 0, 8),         # BASELINE configs[3] at true half filling
     ("square", 9, 4.0, 3.0, 30, 0.0, 11, 6),         # N = 81: odd size above 64 (column tiles of the DMMA reflector straddle N)
-    ("square", 24, 6.0, 10.0, 100, 0.0, 0, 8),       # BASELINE configs[4] size: N = 576 (padded to 640), beta = 10
+    ("square", 24, 6.0, 10.0, 100, 0.0, 0, 8),       # BASELINE configs[4] size: N = 576 = 9 x 64 (half GEMM tile at the right edge), beta = 10
+    ("square", 23, 4.0, 4.0, 40, 0.0, 5, 8),         # N = 529, padded to 576
 ])
 def test_stabilised_recompute_matches_oracle(case):
     """`lqmc_recompute_stable` against the oracle's NumPy QR/UDV (`physics_g_stable`, same pre-pivoted scheme) and,
