@@ -50,15 +50,16 @@ constexpr int L2_GY = 16, L2_GX = 16;                  // thread grid inside a b
 constexpr int L2_STAGES = 3;                           // operand-panel ring depth
 constexpr int L2_MAXQ = 4;                             // indices per thread in the vector phases (NP <= 1024)
 
-// Padded matrix size: a multiple of 128 (GEMM block tile 64 x 128, flush tiles of 128 columns) - except for 512 < N <= 576,
-// which gets 576 = 9 x 64: BASELINE configs[4] is N = 576, and padding it to 640 costs (640/576)^3 = 1.37 x the GEMM work
-// (ncu on the cfg5 wrap: DMMA pipe 80 % busy at 21.5 algorithmic TFLOP/s).  The GEMMs (here and in stab.cuh) and the generic
-// flush handle the half tile at the right edge.
+// Padded matrix size: a multiple of 64.  The GEMM block tile is 64 x 128 and the flush tiles are 128 columns wide, but both
+// (here and in stab.cuh) handle a half tile at the right edge, and padding is expensive: BASELINE configs[4] is N = 576, which a
+// multiple of 128 would pad to 640 - (640/576)^3 = 1.37 x the GEMM work (ncu on the cfg5 wrap at NP = 640: DMMA pipe 80 % busy
+// at 21.5 algorithmic TFLOP/s).  The TMA staging variant copies whole 128-column rows and keeps the multiple of 128.
 inline int l2_padded_size(int n_sites) {
-#if !LQMC_L2_STAGING_TMA
-  if (n_sites > 512 && n_sites <= 576) return 576;
-#endif
+#if LQMC_L2_STAGING_TMA
   const int np = (n_sites + 127) / 128 * 128;
+#else
+  const int np = (n_sites + 63) / 64 * 64 < 128 ? 128 : (n_sites + 63) / 64 * 64;
+#endif
   return np <= 1024 ? np : -1;
 }
 
@@ -653,7 +654,7 @@ __device__ __forceinline__ void tmem_free_cta(uint32_t base) {
 template <bool EXACT>
 __device__ void l2_flush_tmem(double* __restrict__ Gc, int NP, int nd, const double* __restrict__ U3, uint32_t tm_my) {
   const int tid = threadIdx.x;
-  if (tid < NP) {                                  // warp-uniform: NP is a multiple of 128
+  if (tid < NP) {                                  // warp-uniform: NP is a multiple of 64
     for (int spin = 0; spin < 2; ++spin) {
       double cj[L2_KDT];
 #pragma unroll
@@ -931,7 +932,7 @@ __device__ void l2_flush_tmemx(double* __restrict__ Gc, int NP, int nd, const do
   const int tid = threadIdx.x;
   bool jv[CPT];
 #pragma unroll
-  for (int q = 0; q < CPT; ++q) jv[q] = tid + L2_THREADS * q < NP;       // warp-uniform: NP is a multiple of 128
+  for (int q = 0; q < CPT; ++q) jv[q] = tid + L2_THREADS * q < NP;       // warp-uniform: NP is a multiple of 64
   for (int spin = 0; spin < 2; ++spin) {
     double cj[CPT][KDX];
 #pragma unroll
@@ -1313,7 +1314,7 @@ struct L2Params {
 };
 
 // TMEM: 0 shared-memory slice path; 1 tensor-memory path, one column per thread (NP <= 256); 2 / 3 several columns per thread
-// (NP = 512: 2 x depth 24; NP = 640: 3 x depth 16; one CTA per SM at those sizes)
+// (384 < NP <= 512: 2 x depth 24; 512 < NP <= 768: 3 x depth 16 where it fits; one CTA per SM at those sizes)
 template <bool EXACT, bool PHYS, int TMEM>
 __global__ void __launch_bounds__(L2_THREADS, TMEM >= 2 ? 1 : 2) sweep_l2_kernel(const L2Params lp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1414,11 +1415,13 @@ inline int l2_alloc(L2Workspace& w, int n_sites, int np, int n_slices, int n_cha
     const size_t gemm = (size_t)L2_STAGES * L2_BK * (L2_BM + L2_BN + 8);
     if (region < gemm) region = gemm;
     w.tmem_mode = ((size_t)2 * L2_KDT * np <= region) ? 1 : 0;
-  } else if (np == 512 || np == 576 || np == 640) {
-    // several columns per thread: U [2][24][512] / [2][16][640] in the generic path's U / W region, one CTA per SM
+  } else if (np > 384 && np <= 3 * L2_THREADS) {
+    // several columns per thread, one CTA per SM: U [2][24][NP] (two columns, NP <= 512) / [2][16][NP] (three columns) in the
+    // generic path's U / W region
     const size_t region = (size_t)4 * kd * np;
-    const size_t need = (np == 512) ? (size_t)2 * 24 * np : (size_t)2 * 16 * np;
-    w.tmem_mode = (need <= region) ? (np == 512 ? 2 : 3) : 0;
+    const int mode = (np <= 2 * L2_THREADS) ? 2 : 3;
+    const size_t need = (size_t)2 * (mode == 2 ? 24 : 16) * np;
+    w.tmem_mode = (need <= region) ? mode : 0;
   }
   return 0;
 }

@@ -125,12 +125,13 @@ def test_free_running_sweep_10x10(arith):
         assert m["n_accepted"][c] == acc[c].sum() and m["n_meas"][c] == 2
 
 
-@pytest.mark.parametrize("size", [12, 18, 20])
+@pytest.mark.parametrize("size", [12, 16, 18, 20, 22, 26])
 def test_delayed_updates_equal_undelayed_bitwise(size):
     """EXACT mode: a slice run through the delayed rank-k path equals the oracle's one-flip-at-a-time
-    rank-1 updates bit for bit (same roundings per element), with ~60% acceptance: N = 144 (padded 256: tensor-memory path,
-    one column per thread, two-column flush), N = 324 (padded 384: shared-memory path), N = 400 (padded 512: tensor-memory
-    path with two columns per thread, delay depth 24)."""
+    rank-1 updates bit for bit (same roundings per element), with ~60% acceptance: N = 144 (padded 192: tensor-memory path,
+    one column per thread), N = 256 (two-column flush), N = 324 (padded 384: shared-memory path), N = 400 (padded 448) and
+    N = 484 (padded 512): tensor-memory path with two columns per thread, delay depth 24; N = 676 (padded 704: three columns,
+    depth 16)."""
     ham = so.ideal_square_kinetic(size, 1.0, 2.0)
     n, lt = size * size, 8
     dtau, lamb, exp_k = so.set_beta_constants(ham, 4.0, 1.0, lt)
@@ -150,8 +151,8 @@ def test_delayed_updates_equal_undelayed_bitwise(size):
 
 
 def test_cfg5_slice_is_bit_exact_at_full_size():
-    """BASELINE configs[4] size (24x24, N=576 -> padded 640, U=6, beta=10, L=100; the shared-memory delayed-update path
-    with four entries per thread): from the oracle's sweep-start G, the 576 proposals of the first slice give the
+    """BASELINE configs[4] size (24x24, N=576 = 9 x 64 unpadded, U=6, beta=10, L=100; the tensor-memory delayed-update path
+    with three columns per thread): from the oracle's sweep-start G, the 576 proposals of the first slice give the
     oracle's decisions, ratios and - EXACT mode - its G bit for bit; then the wrap within 1e-10."""
     ham = so.ideal_square_kinetic(24, 1.0, 3.0)
     n, lt = 576, 100

@@ -41,7 +41,7 @@ def test_physics_sweep_matches_oracle():
 
 @pytest.mark.parametrize("size", [20, 24])
 def test_physics_sweep_large_lattices_match_oracle(size):
-    """Physics-mode sweep on the multi-column tensor-memory slice paths: N = 400 (padded 512, two columns per thread, delay
+    """Physics-mode sweep on the multi-column tensor-memory slice paths: N = 400 (padded 448 = 7 x 64, two columns per thread, delay
     depth 24) and N = 576 (unpadded = 9 x 64, three columns, depth 16; BASELINE configs[4] size) at beta = 0.4, L = 4 - same accept /
     reject decisions as the oracle's `physics_sweep` on the same uniforms, G to 1e-9."""
     from latticeqmc_b200 import SweepEngine
@@ -52,7 +52,7 @@ def test_physics_sweep_large_lattices_match_oracle(size):
     field = so.initial_field(n, lt, 77)
     uni = np.random.RandomState(9).rand(1, 1, lt, n)
     with SweepEngine(exp_k, lamb, lt, n_chains=1, exp_k_inv=exp_k_inv, mode="physics", trace=True) as eng:
-        assert eng.info()["n_pad"] == (512 if size == 20 else 576)
+        assert eng.info()["n_pad"] == (448 if size == 20 else 576)
         eng.set_field(field[None])
         eng.sweep(1, uni)
         acc, ratio = eng.get_trace()
