@@ -15,13 +15,16 @@
 //  * The accept/reject scan is lane-parallel: a warp evaluates the ratios of the next 32 sites at once from
 //    the shared diagonal; the first accepted site is found with a ballot, everything before it is rejected
 //    for free (no flip happened in between, so those ratios were final).
-//  * Wrap and sweep-start product are tiled GEMMs (64 x 128 block tile, 4 x 8 per thread, k-major operand
-//    panels staged global -> shared with cp.async double buffering); the left operand is always kept
-//    k-major (transposed) in memory so both panels are contiguous row copies.  exp(V_l) is applied as a
-//    row / column scale in the epilogue.
+//  * Wrap and sweep-start product are tiled GEMMs on FP64 tensor-core fragments (mma.sync.m8n8k4.f64, SASS DMMA.8x8x4): 64 x 128
+//    block tile, 8 warps x (32 x 32) warp tiles, k-major operand panels staged global -> shared through a 3-stage cp.async ring
+//    (a cp.async.bulk + mbarrier variant is kept behind LQMC_L2_STAGING_TMA); the left operand is always kept k-major
+//    (transposed) in memory so both panels are contiguous row copies.  exp(V_l) is applied as a row / column scale in the
+//    epilogue.  Matrices are padded to a multiple of 64 (at least 128); the half tile at the right edge is skipped.
+//  * For NP <= 256 the c history of the delayed updates lives in tensor memory (tcgen05.ld / st as a per-thread scratchpad),
+//    which doubles the delay depth; 384 < NP <= 768 uses the same idea with two or three columns per thread (one CTA per SM).
 //
-// FP64 has no tcgen05 kind, and DMMA issues to the same pipe as DFMA on sm_100a (profiles/fp64_peaks_r01.json),
-// so these GEMMs are register-tiled DFMA kernels measured against the FP64 pipe peak.
+// FP64 has no tcgen05 kind, and DMMA issues to the same pipe as DFMA on sm_100a (profiles/fp64_peaks_r01.json): the roofline of
+// every phase here is the FP64 pipe peak; tensor-core fragments buy operand traffic (one double per 8 FMAs), not flops.
 #pragma once
 #include <type_traits>
 #include <cuda_runtime.h>
@@ -37,7 +40,7 @@ namespace lqmc {
 struct L2Workspace {
   double* T = nullptr;      // [chain][2][NP][NP] second matrix buffer (two-GEMM wrap, running product)
   int kd = 0;               // delay depth the shared-memory budget allows
-  int tmem_mode = 0;        // tensor-memory slice path that fits the shared-memory region: 0 none, 1 NP <= 256, 2 NP = 512, 3 NP = 640
+  int tmem_mode = 0;        // tensor-memory slice path that fits the shared-memory region: 0 none, 1 NP <= 256, 2 384 < NP <= 512, 3 512 < NP <= 768
   size_t smem = 0;          // dynamic shared memory per CTA
 };
 
@@ -903,7 +906,7 @@ __device__ void l2_propose_slice_tmem(double* __restrict__ Gc, int NP, L2Smem& s
 // At N = 576 (BASELINE configs[4]) the generic path's delay depth is 9 (U and W in 220 KB of shared memory) and the flush -
 // 13 MB of G per 9 flips and chain - is 83 % of the slice phase and HBM-bound (5 TB/s with 148 chains, clock64 split in
 // profiles/r01e_cfg4_summary.md).  Same remedy as for NP <= 256: only U stays in shared memory, thread t parks the c history of
-// ITS columns t, t + 256, ... (CPT of them) in tensor memory, which buys delay depth KDX = 16 (NP = 640) / 24 (NP = 512).  One
+// ITS columns t, t + 256, ... (CPT of them) in tensor memory, which buys delay depth KDX = 16 (three columns) / 24 (two columns).  One
 // CTA per SM at these sizes, so the whole 512-column TMEM is this CTA's: window of warp w = [4 CPT KDX (w / 4), ...), inside it
 // column-set q, spin s, update m at 32-bit column 2 ((2 q + s) KDX + m).  Same roundings in the same order as the generic path.
 constexpr int L2_TMEMX_COLS = 512;

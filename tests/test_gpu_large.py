@@ -60,7 +60,7 @@ def test_cfg4_reference_slices(golden):
                                    ("square", 24, 6.0, 0.6, 6)])   # N = 576: BASELINE configs[4] lattice, unpadded in parity mode
 def test_recompute_large(case):
     """Sweep-start G (get_m + inv, lqmc.py:156-185,303-307) on well-conditioned products; N = 81, 144, 100
-    need padding to the 128-wide tile, 256 does not."""
+    are padded to the next multiple of 64 (at least 128), 256 and 576 are not padded."""
     kind, size, u, beta, lt = case
     ham = so.ideal_square_kinetic(size, 1.0, u / 2) if kind == "square" else so.ideal_ring_kinetic(size, 1.0, u / 2)
     n = ham.shape[0]
