@@ -7,10 +7,26 @@ for r in rows:
     if r and r[0] == "Line No": hdr = r; break
 print(hdr[:12])
 cur=None; reg={}
+import os, re
+_SRC = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "latticeqmc_b200", "csrc", "sweep_l2.cuh")
+_ANCHORS = [("gemm", "struct L2PanelIssue"), ("flush_smem", "__device__ void l2_flush("), ("propose_smem", "__device__ void l2_propose_slice("),
+            ("tmem helpers", "constexpr int L2_KDT"), ("flush_tmem1", "__device__ void l2_flush_tmem("), ("flush_tmem2", "__device__ void l2_flush_tmem2("),
+            ("propose_tmem", "__device__ void l2_propose_slice_tmem("), ("tmemx", "constexpr int L2_TMEMX_COLS"),
+            ("gj_inverse", "__device__ void l2_gj_inverse("), ("recompute", "__device__ void l2_recompute("), ("wrap", "__device__ void l2_wrap("),
+            ("kernel", "struct L2Params")]
+_lines = open(_SRC).read().split("\n")
+_bounds = []
+for name, pat in _ANCHORS:
+    for i, l in enumerate(_lines):
+        if pat in l:
+            _bounds.append((i + 1, name)); break
+_bounds.sort()
 def region(f, ln):
     if f == "sweep_l2.cuh":
-        for name, lo, hi in (("gemm",160,345),("flush_smem",346,420),("propose_smem",421,600),("tmem helpers",601,640),("flush_tmem1",641,690),("flush_tmem2",691,750),("propose_tmem",751,905),("gj_inverse",906,1040),("recompute",1041,1085),("wrap",1086,1110),("kernel",1111,1200)):
-            if lo <= ln <= hi: return name
+        cur = "sweep_l2.cuh (head)"
+        for start, name in _bounds:
+            if ln >= start - 3: cur = name
+        return cur
     return f
 tot=0
 for r in rows:
