@@ -52,6 +52,13 @@ constexpr int L2_GY = 16, L2_GX = 16;                  // thread grid inside a b
 #endif
 constexpr int L2_STAGES = 3;                           // operand-panel ring depth
 constexpr int L2_MAXQ = 4;                             // indices per thread in the vector phases (NP <= 1024)
+#ifndef LQMC_L2_KDT
+#define LQMC_L2_KDT 24
+#endif
+constexpr int L2_KDT = LQMC_L2_KDT;                    // delay depth of the tensor-memory slice path (NP <= 256)
+constexpr int L2_TMEM_COLS = 256;
+constexpr int L2_RING = 8;                             // slots of the "history of the next candidate sites" ring (site & 7)
+constexpr int L2_PUB = 4;                              // sites after a flip whose c history is published with the flip itself
 
 // Padded matrix size: a multiple of 64.  The GEMM block tile is 64 x 128 and the flush tiles are 128 columns wide, but both
 // (here and in stab.cuh) handle a half tile at the right edge, and padding is expensive: BASELINE configs[4] is N = 576, which a
@@ -74,6 +81,7 @@ struct L2Smem {
   double* u;      // [NP]               uniforms of the slice
   double* red_v;  // [16]
   double* hist;   // [64]  (TMEM path: history of the flipped site, 2 x L2_KDT; [63] doubles as the TMEM base-address slot)
+  double* ring;   // [L2_RING][2][L2_KDT]  (TMEM path, NP <= 256: c histories of the next candidate sites, slot = site & 7)
   int* red_i;     // [16]
   int8_t* h;      // [NP]
   int8_t* hn;     // [NP]
@@ -95,7 +103,8 @@ struct L2Smem {
     u = d + 4 * NP;
     red_v = u + NP;
     hist = red_v + 16;
-    full = reinterpret_cast<uint64_t*>(hist + 64);
+    ring = hist + 64;
+    full = reinterpret_cast<uint64_t*>(ring + L2_RING * 2 * L2_KDT);
     red_i = reinterpret_cast<int*>(full + 4);
     h = reinterpret_cast<int8_t*>(red_i + 16);
     hn = h + NP;
@@ -106,7 +115,7 @@ inline size_t l2_smem_bytes(int NP, int KD, int ns = 2) {
   size_t vec = (size_t)2 * ns * KD * NP;
   const size_t gemm = (size_t)L2_STAGES * L2_BK * (L2_BM + L2_BN + 8);
   if (vec < gemm) vec = gemm;
-  return (vec + 5 * (size_t)NP + 16 + 64 + 4) * sizeof(double) + 16 * sizeof(int) + 2 * (size_t)NP + 16;
+  return (vec + 5 * (size_t)NP + 16 + 64 + L2_RING * 2 * L2_KDT + 4) * sizeof(double) + 16 * sizeof(int) + 2 * (size_t)NP + 16;
 }
 
 // ---- tiled GEMM:  C = A * B  with A given k-major (At[k*NP + i] = A[i][k]) and B row-major ------------------
@@ -593,12 +602,6 @@ __device__ void l2_propose_slice(double* __restrict__ Gc, int NP, int KD, L2Smem
 //   * the flush walks G with thread <-> column (a warp covers 32 consecutive columns, 256-byte row segments), c_m[j] in
 //     registers for one spin at a time, e_m of eight rows as broadcast 128-bit shared loads.
 // Same roundings in the same order as the generic path and the reference's one-flip-at-a-time loop (lqmc.py:328-331).
-#ifndef LQMC_L2_KDT
-#define LQMC_L2_KDT 24
-#endif
-
-constexpr int L2_KDT = LQMC_L2_KDT;
-constexpr int L2_TMEM_COLS = 256;
 static_assert(L2_KDT % 8 == 0 && 8 * L2_KDT <= L2_TMEM_COLS, "two windows of 4 KDT columns; history read in chunks of 8 doubles");
 
 __device__ __forceinline__ void tmem_st_f64(uint32_t taddr, double v) {
@@ -703,75 +706,295 @@ __device__ void l2_flush_tmem(double* __restrict__ Gc, int NP, int nd, const dou
 // NP == 256: two columns per thread.  Every update needs e_m[row] from shared memory, and a broadcast load delivers one
 // double per two LSU wavefronts whatever its width.  Warps w and w+4 address the same TMEM lane quarter, so thread t can read
 // the c history of column t % 128 (window 0) AND of column t % 128 + 128 (window 1): it updates both columns with every e
-// value it loads - half the shared-memory traffic per update - while the two thread halves split the rows.  The history is
-// re-read from tensor memory per 8-row chunk in three parts of eight (16 doubles in registers at a time).  Same operations
-// per element in the same order: still bit-identical.  Measured (clock64 split, profiles/r01e_cfg4_summary.md): alone on an SM
-// a flush takes the same 162 K clocks as the one-column version (98 K is the FP64 floor of 2 issue slots per exact update),
-// with two resident CTAs the flush cost per flip falls 12.2 K -> 11.1 K clocks and the slice phase 2.04 -> 1.93 ms.
+// value it loads - half the shared-memory traffic per update - while the two thread halves split the rows.
+//
+// The flush is the FP64-pipe-bound half of the slice phase (exact arithmetic: one DMUL and one DADD per element and update,
+// 2 x 2 x 256^2 x 24 / 64 lanes = 98 K clocks per flush), so its inner loop is written to keep that pipe fed:
+//   * the history is zero-padded to a multiple of 8 updates (e = c = +0 leaves every element unchanged bit for bit in both
+//     arithmetics: g - RN(0 * 0) = g, fma(-0, 0, g) = g), so the update loop has no per-update branch and the compiler
+//     schedules the shared-memory loads of e ahead of the multiply-subtract chains of the previous update (the r01 version
+//     had one basic block per update: every update started with an exposed LDS latency and ended with an exposed
+//     DMUL -> DADD latency; alone on an SM it ran at 0.60 of the pipe floor, two co-resident CTAs at 0.74);
+//   * the c history is read from tensor memory four updates at a time, the next four in flight while the current four are
+//     applied (tcgen05.ld without a memory clobber; the wait carries the destination registers as operands so that no use
+//     is scheduled above it);
+//   * no register double buffer for G: a warp's 8-row chunk carries 24 x 32 FP64 instructions = 1.5 K pipe clocks, more
+//     than the latency of its next loads, and the other warps of the sub-partition fill the gap.
+// Same operations per element in the same order as the reference loop (lqmc.py:328-331): still bit-identical.
+struct TmemQuad { uint32_t r[16]; };      // updates m .. m+3 of the thread's two columns: r[0..7] window 0, r[8..15] window 1
+__device__ __forceinline__ void tmem_ld_quad_issue(uint32_t taddr0, uint32_t taddr1, TmemQuad& q) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(q.r[0]), "=r"(q.r[1]), "=r"(q.r[2]), "=r"(q.r[3]), "=r"(q.r[4]), "=r"(q.r[5]), "=r"(q.r[6]), "=r"(q.r[7])
+               : "r"(taddr0));
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(q.r[8]), "=r"(q.r[9]), "=r"(q.r[10]), "=r"(q.r[11]), "=r"(q.r[12]), "=r"(q.r[13]), "=r"(q.r[14]), "=r"(q.r[15])
+               : "r"(taddr1));
+}
+__device__ __forceinline__ void tmem_ld_quad_wait(TmemQuad& q) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(q.r[0]), "+r"(q.r[1]), "+r"(q.r[2]), "+r"(q.r[3]), "+r"(q.r[4]), "+r"(q.r[5]), "+r"(q.r[6]), "+r"(q.r[7]),
+                 "+r"(q.r[8]), "+r"(q.r[9]), "+r"(q.r[10]), "+r"(q.r[11]), "+r"(q.r[12]), "+r"(q.r[13]), "+r"(q.r[14]), "+r"(q.r[15]));
+}
+#ifndef LQMC_FLUSH_ROWS
+#define LQMC_FLUSH_ROWS 4          // rows per chunk of the two-column flush; the next chunk's G is prefetched into registers
+#endif
+template <bool EXACT, int R>
+__device__ __forceinline__ void l2_flush_apply4(double (&g)[R][2], const TmemQuad& c, const double* __restrict__ ur, int NP) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const double c0 = __hiloint2double((int)c.r[2 * q + 1], (int)c.r[2 * q]);
+    const double c1 = __hiloint2double((int)c.r[8 + 2 * q + 1], (int)c.r[8 + 2 * q]);
+#pragma unroll
+    for (int r = 0; r < R; r += 2) {
+      const double2 e = *reinterpret_cast<const double2*>(ur + (size_t)q * NP + r);
+      g[r][0] = rank1<EXACT>(g[r][0], e.x, c0);
+      g[r][1] = rank1<EXACT>(g[r][1], e.x, c1);
+      g[r + 1][0] = rank1<EXACT>(g[r + 1][0], e.y, c0);
+      g[r + 1][1] = rank1<EXACT>(g[r + 1][1], e.y, c1);
+    }
+  }
+}
+
+// __noinline__: the build loop around the call keeps its own register allocation.
+// Column window: a flip needs column `is` of G0, a 256-line strided gather (2 K clocks of memory-system back-pressure per flip
+// with every SM doing it, profiles/r02_cfg4_summary.md).  The flush has every element in registers anyway, so the threads that
+// own the L2_COLWIN columns after the flush point (the sites the next 24 flips will come from) also store their values
+// transposed into the idle second matrix buffer, Tc[spin][c][r] = G0[r][c]: 32 contiguous bytes per thread and chunk, + 12 % flush
+// traffic, and the builder's column becomes one coalesced 2 KB read.
+constexpr int L2_COLWIN = 64;
 template <bool EXACT>
-__device__ void l2_flush_tmem2(double* __restrict__ Gc, int nd, const double* __restrict__ U3, uint32_t tm_base) {
-  constexpr int NP = 256;
+__device__ __noinline__ void l2_flush_tmem2(double* __restrict__ Gc, int nd, double* __restrict__ U3, uint32_t tm_base,
+                                            double* __restrict__ Tc, int wlo) {
+  constexpr int NP = 256, R = LQMC_FLUSH_ROWS;
   const int tid = threadIdx.x, warp = tid >> 5;
   const int jj = tid & 127, rbase = (tid >> 7) * (NP / 2);
   const uint32_t tm_lane = tm_base + ((uint32_t)(32 * (warp & 3)) << 16);
+  const int nd8 = (nd + 7) & ~7;
+  if (nd8 != nd) {                                   // zero-pad: thread t owns entry t of every e vector and the c history of column t
+    const uint32_t tm_my = tm_lane + (uint32_t)((warp >> 2) * 4 * L2_KDT);
+    for (int m = nd; m < nd8; ++m)
+#pragma unroll
+      for (int spin = 0; spin < 2; ++spin) {
+        U3[((size_t)spin * L2_KDT + m) * NP + tid] = 0.0;
+        tmem_st_f64(tm_my + 2 * (spin * L2_KDT + m), 0.0);
+      }
+    tmem_wait_st();
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+  }
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  for (int spin = 0; spin < 2; ++spin) {
-    double* const col = Gc + (size_t)spin * NP * NP + (size_t)rbase * NP + jj;
-    const double* const Us = U3 + (size_t)spin * L2_KDT * NP + rbase;
+  // the two spins are one walk of 2 x 128 / R chunks: the prefetch of the next chunk runs across the spin boundary
+  constexpr int CH = NP / 2 / R;                     // chunks per spin
+  auto chunk_ptr = [&](int ch) -> double* {
+    const int spin = ch / CH, r0 = (ch % CH) * R;    // CH is a power of two
+    return Gc + (size_t)spin * NP * NP + (size_t)(rbase + r0) * NP + jj;
+  };
+  double nxt[R][2];
+  {
+    const double* c0 = chunk_ptr(0);
+#pragma unroll
+    for (int r = 0; r < R; ++r) { nxt[r][0] = c0[(size_t)r * NP]; nxt[r][1] = c0[(size_t)r * NP + 128]; }
+  }
+  TmemQuad ca, cb;
+  tmem_ld_quad_issue(tm_lane, tm_lane + 4 * L2_KDT, ca);
+  for (int ch = 0; ch < 2 * CH; ++ch) {
+    const int spin = ch / CH, r0 = (ch % CH) * R;
+    double* const col = chunk_ptr(ch);
+    const double* const Us = U3 + (size_t)spin * L2_KDT * NP + rbase + r0;
     const uint32_t tm0 = tm_lane + 2 * (spin * L2_KDT), tm1 = tm0 + 4 * L2_KDT;
-    double nxt[8][2];
+    // history of the chunk after this one starts at update 0 of (possibly) the other spin
+    const int spin_n = (ch + 1) / CH < 2 ? (ch + 1) / CH : 1;
+    const uint32_t tn0 = tm_lane + 2 * (spin_n * L2_KDT), tn1 = tn0 + 4 * L2_KDT;
+    double g[R][2];
 #pragma unroll
-    for (int r = 0; r < 8; ++r) { nxt[r][0] = col[(size_t)r * NP]; nxt[r][1] = col[(size_t)r * NP + 128]; }
-    for (int r0 = 0; r0 < NP / 2; r0 += 8) {
-      double g[8][2];
+    for (int r = 0; r < R; ++r) { g[r][0] = nxt[r][0]; g[r][1] = nxt[r][1]; }
+    if (ch + 1 < 2 * CH) {
+      const double* cn = chunk_ptr(ch + 1);
 #pragma unroll
-      for (int r = 0; r < 8; ++r) { g[r][0] = nxt[r][0]; g[r][1] = nxt[r][1]; }
-      if (r0 + 8 < NP / 2) {
+      for (int r = 0; r < R; ++r) { nxt[r][0] = cn[(size_t)r * NP]; nxt[r][1] = cn[(size_t)r * NP + 128]; }
+    }
+    for (int m0 = 0; m0 < nd8; m0 += 8) {
+      const bool last = m0 + 8 >= nd8;
+      tmem_ld_quad_wait(ca);
+      tmem_ld_quad_issue(tm0 + 2 * (m0 + 4), tm1 + 2 * (m0 + 4), cb);
+      l2_flush_apply4<EXACT, R>(g, ca, Us + (size_t)m0 * NP, NP);
+      tmem_ld_quad_wait(cb);
+      tmem_ld_quad_issue(last ? tn0 : tm0 + 2 * (m0 + 8), last ? tn1 : tm1 + 2 * (m0 + 8), ca);
+      l2_flush_apply4<EXACT, R>(g, cb, Us + (size_t)(m0 + 4) * NP, NP);
+    }
 #pragma unroll
-        for (int r = 0; r < 8; ++r) { nxt[r][0] = col[(size_t)(r0 + 8 + r) * NP]; nxt[r][1] = col[(size_t)(r0 + 8 + r) * NP + 128]; }
+    for (int r = 0; r < R; ++r) { col[(size_t)r * NP] = g[r][0]; col[(size_t)r * NP + 128] = g[r][1]; }
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {
+      const int c = jj + 128 * cc;
+      if ((unsigned)(c - wlo) < (unsigned)L2_COLWIN) {
+        double* dst = Tc + (size_t)spin * NP * NP + (size_t)c * NP + rbase + r0;
+#pragma unroll
+        for (int r = 0; r < R; r += 2) *reinterpret_cast<double2*>(dst + r) = make_double2(g[r][cc], g[r + 1][cc]);
       }
-      for (int m0 = 0; m0 < nd; m0 += 8) {
-        double c0[8], c1[8];
-        tmem_ld_f64x8_pair(tm0 + 2 * m0, tm1 + 2 * m0, c0, c1);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          if (m0 + q < nd) {
-            const double* ur = Us + (size_t)(m0 + q) * NP + r0;
-#pragma unroll
-            for (int r = 0; r < 8; r += 2) {
-              const double2 e = *reinterpret_cast<const double2*>(ur + r);
-              g[r][0] = rank1<EXACT>(g[r][0], e.x, c0[q]);
-              g[r][1] = rank1<EXACT>(g[r][1], e.x, c1[q]);
-              g[r + 1][0] = rank1<EXACT>(g[r + 1][0], e.y, c0[q]);
-              g[r + 1][1] = rank1<EXACT>(g[r + 1][1], e.y, c1[q]);
-            }
-          }
-        }
-      }
-#pragma unroll
-      for (int r = 0; r < 8; ++r) { col[(size_t)(r0 + r) * NP] = g[r][0]; col[(size_t)(r0 + r) * NP + 128] = g[r][1]; }
     }
   }
+  tmem_ld_quad_wait(ca);                               // drain the last (unused) history prefetch
   __syncthreads();
 }
 
+// The build of one accepted flip (row and column of the current G, Sherman-Morrison vectors) is a chain of dependent
+// latencies - the FP64 work in it is small - and with the flush at the pipe floor it is what the co-resident CTA's flush has to
+// hide.  Three things keep the chain short (r01: 3.5 K clocks per flip alone on an SM, 6.9 K next to a flushing CTA):
+//   * G0 row / column of the next LQMC_L2_PF candidate sites are loaded into registers while the current flip is being built (the
+//     next accepted site is the very next one with probability ~0.6, within three with ~0.93), so the strided 256-sector
+//     column gather of a flip is no longer on its critical path; G0 only changes at a flush, after which the slots are reloaded;
+//   * the c history of the flipped site, which every thread needs for the column rebuild, used to be published by the warp that
+//     owns the site (tcgen05.ld, shared-memory store, one extra barrier per flip).  Now the threads of the next L2_PUB candidate
+//     sites publish their own history while they apply it (they hold it in registers at that moment anyway) into a small ring
+//     (slot = site & 7); the per-flip barrier orders it.  The owner-publish path remains for the rare longer jump;
+//   * all divisions' common reciprocal depends only on the flipped site's diagonal and is computed by every thread while the
+//     tensor-memory loads are in flight.
+#ifndef LQMC_L2_PF
+#define LQMC_L2_PF 0
+#endif
+#ifndef LQMC_L2_PFD
+#define LQMC_L2_PFD 0
+#endif
+// columns [0, L2_COLWIN) of both spins, transposed into Tc (the window of a slice's first flips); NP == 256
+__device__ __forceinline__ void l2_colwin_init(const double* __restrict__ Gc, double* __restrict__ Tc) {
+  constexpr int NP = 256;
+  const int tid = threadIdx.x;
+  // thread -> (spin, column c, 32-row block): 2 x 64 x 8 = 1024 pieces of 32 rows, four per thread; a warp reads 32 consecutive
+  // columns of one row at a time (256-byte segments) and every thread stores 32 contiguous rows (256 bytes)
+  for (int piece = tid; piece < 2 * L2_COLWIN * (NP / 32); piece += L2_THREADS) {
+    const int c = piece % L2_COLWIN, rb = (piece / L2_COLWIN) % (NP / 32), spin = piece / (L2_COLWIN * (NP / 32));
+    const double* src = Gc + (size_t)spin * NP * NP + (size_t)(32 * rb) * NP + c;
+    double* dst = Tc + (size_t)spin * NP * NP + (size_t)c * NP + 32 * rb;
+#pragma unroll 4
+    for (int r = 0; r < 32; r += 4) {
+      const double a0 = src[(size_t)r * NP], a1 = src[(size_t)(r + 1) * NP], a2 = src[(size_t)(r + 2) * NP], a3 = src[(size_t)(r + 3) * NP];
+      *reinterpret_cast<double2*>(dst + r) = make_double2(a0, a1);
+      *reinterpret_cast<double2*>(dst + r + 2) = make_double2(a2, a3);
+    }
+  }
+}
+// Two chains share an SM (2 CTAs) and one FP64 pipe.  A flush wants the whole pipe for ~100 K clocks, a build hardly any of it:
+// the pair runs fastest in anti-phase (one chain flushes while the other builds its next 24 flips), but nothing makes two
+// independent CTAs fall into that rhythm - whatever offset they start with persists, and when both flush at once both then
+// build at once with the pipe idle.  A per-SM token (global memory, indexed by %smid) serialises the flushes of an SM: a CTA
+// that finds the token taken waits for the other chain's flush to end, which locks the pair into anti-phase.  The wait is
+// bounded (a CTA of another, aborted launch can never wedge the SM) and only the holder releases.
+#ifndef LQMC_FLUSH_TOKEN
+#define LQMC_FLUSH_TOKEN 0          // measured (profiles/r02_cfg4_summary.md): cfg4 sweep 268.6 ms without, 274.1 ms with the token
+#endif
+__device__ int g_l2_flush_token[1024];
+__device__ __forceinline__ bool l2_flush_token_acquire() {
+  bool got = false;
+#if LQMC_FLUSH_TOKEN
+  if (threadIdx.x == 0) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+    const long long t0 = clock64();
+    while (true) {
+      if (atomicCAS(&g_l2_flush_token[smid & 1023], 0, 1) == 0) { got = true; break; }
+      if (clock64() - t0 > 400000) break;
+      __nanosleep(500);
+    }
+  }
+  __syncthreads();
+#endif
+  return got;
+}
+__device__ __forceinline__ void l2_flush_token_release(bool got) {
+#if LQMC_FLUSH_TOKEN
+  if (threadIdx.x == 0 && got) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+    atomicExch(&g_l2_flush_token[smid & 1023], 0);
+  }
+#endif
+}
+// Compiled as a subroutine of its own (by-value arguments, like the GEMM): inlined into the sweep kernel the flip loop shared the
+// 128-register budget with everything else that is live in the kernel and ptxas kept the prefetch slots in local memory - a
+// store of a just-issued load, i.e. the prefetch turned into a blocking load.
+struct L2SliceArgs {
+  double* Gc; double* Tc;
+  double* U; double* d; double* u; double* hist; double* ring; int8_t* h;      // shared memory (L2Smem)
+  double* tr_ratio; uint8_t* tr_acc; double* obs;
+  double f_p2, f_m2;
+  long long trace_base;
+  uint32_t tm_base;
+  int NP, N;
+};
+struct L2SliceView {                       // the members of L2Smem / SweepParams the slice path touches, under their old names
+  double* U; double* d; double* u; double* hist; double* ring; int8_t* h;
+  double* tr_ratio; uint8_t* tr_acc; double* obs_sum; double f_p2, f_m2; int n_sites;
+};
 template <bool EXACT, bool PHYS>
-__device__ void l2_propose_slice_tmem(double* __restrict__ Gc, int NP, L2Smem& sm, const SweepParams& p, long long trace_base,
-                                      int& n_accepted, uint32_t tm_base) {
+__device__ __noinline__ int l2_propose_slice_tmem_sub(const L2SliceArgs a) {
+  constexpr int PF = LQMC_L2_PF;
+  double* const Gc = a.Gc; double* const Tc = a.Tc;
+  const int NP = a.NP;
+  const long long trace_base = a.trace_base;
+  const uint32_t tm_base = a.tm_base;
+  L2SliceView sm{a.U, a.d, a.u, a.hist, a.ring, a.h, nullptr, nullptr, nullptr, 0.0, 0.0, 0};
+  L2SliceView p{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, a.tr_ratio, a.tr_acc, a.obs, a.f_p2, a.f_m2, a.N};
+  int n_accepted = 0;
+  static_assert(PF >= 0 && PF <= 3, "prefetch depth");
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = p.n_sites;
   double* const U3 = sm.U;                       // [2][L2_KDT][NP]: exactly the generic path's U / W region at KD = L2_KDT / 2
-  double* const wis = sm.hist;                   // [2][L2_KDT] c history of the site being flipped
+  double* const wis = sm.hist;                   // [2][L2_KDT] c history of the site being flipped (owner-publish path)
   const int j = tid;
   const bool act = j < NP;
+  const size_t NN = (size_t)NP * NP;
   // this thread's TMEM window: lane quarter of its warp, columns [0, 4 KDT) for warps 0-3, [4 KDT, 8 KDT) for warps 4-7
   const uint32_t tm_my = tm_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)((warp >> 2) * 4 * L2_KDT);
+  double* const myring = sm.ring + (size_t)(j & (L2_RING - 1)) * 2 * L2_KDT;
   for (int spin = 0; spin < 2; ++spin)
-    for (int q = tid; q < NP; q += L2_THREADS) sm.d[spin * NP + q] = Gc[(size_t)spin * NP * NP + (size_t)q * NP + q];
+    for (int q = tid; q < NP; q += L2_THREADS) sm.d[spin * NP + q] = Gc[(size_t)spin * NN + (size_t)q * NP + q];
+  int wlo = NP;                                  // first column of the transposed window in Tc (NP: none)
+  if (NP == 256) { l2_colwin_init(Gc, Tc); wlo = 0; }
   __syncthreads();
   int nd = 0, i0 = 0, cur = 0;
+  int pf_base = -(1 << 20);                      // prow / pcol [k] = G0 row / column of site pf_base + k (valid until the next flush)
+  int pub_base = -(1 << 20);                     // ring slots of sites pub_base + 1 .. pub_base + L2_PUB hold those sites' c history
+  double prow[PF > 0 ? PF : 1][2], pcol[PF > 0 ? PF : 1][2];
+  auto load_site = [&](int s, double (&r)[2], double (&c)[2]) {
+    if (s > NP - 1) s = NP - 1;                  // past the last site: a harmless in-bounds load (never used)
+    if (act) {
+      const bool win = (unsigned)(s - wlo) < (unsigned)L2_COLWIN;      // CTA-uniform
+      const double* cp = win ? Tc + (size_t)s * NP + j : Gc + (size_t)j * NP + s;
+      c[0] = cp[0];
+      c[1] = cp[NN];
+      r[0] = Gc[(size_t)s * NP + j];
+      r[1] = Gc[NN + (size_t)s * NP + j];
+    }
+  };
+  // register-free look-ahead: rows / window columns of the sites up to LQMC_L2_PFD ahead are pulled into L2 (prefetch.global.L2
+  // has no destination register), so that the loads of a later flip pay the L2, not the HBM latency
+  int l2_hi = 0;                                  // sites below l2_hi have been prefetched since the last flush
+  auto l2_prefetch_to = [&](int hi) {
+#if LQMC_L2_PFD > 0
+    if (hi > NP) hi = NP;
+    for (int s = l2_hi; s < hi; ++s) {
+      if (act) {
+        const bool win = (unsigned)(s - wlo) < (unsigned)L2_COLWIN;
+        const double* cp = win ? Tc + (size_t)s * NP + j : Gc + (size_t)j * NP + s;
+        const double* rp = Gc + (size_t)s * NP + j;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(rp));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + NN));
+        if (win) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(cp));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(cp + NN));
+        }
+      }
+    }
+    if (hi > l2_hi) l2_hi = hi;
+#else
+    (void)hi;
+#endif
+  };
 #ifdef LQMC_PHASE_CLOCKS
   long long tk_scan = 0, tk_build = 0, tk_flush = 0, tk0 = clock64();
+  long long tk_b1 = 0, tk_b2 = 0, tk_b0 = 0, tk_b3 = 0, tk_b4 = 0; int n_slow = 0, n_miss = 0;
+  const long long tk_begin = tk0;
   unsigned long long gt0; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt0));
 #endif
   while (i0 < N) {
@@ -808,71 +1031,159 @@ __device__ void l2_propose_slice_tmem(double* __restrict__ Gc, int NP, L2Smem& s
     const int hs = __shfl_sync(0xffffffffu, (int)h, first);
     const double fu = (hs > 0) ? p.f_p2 : p.f_m2;
     const double fd = (hs > 0) ? p.f_m2 : p.f_p2;
-    // G0 row / column of the flipped site, both spins, issued together
+    // G0 row / column of the flipped site, both spins: from the prefetch slots when the site is one of them.  The strided
+    // column gather is issued first: it is the longest latency of the flip and is not needed before the column loop below.
     double row[2] = {0.0, 0.0}, col[2] = {0.0, 0.0};
-    if (act) {
+    const int dpf = is - pf_base;                  // CTA-uniform
+    if (PF >= 1 && dpf >= 0 && dpf < PF) {
 #pragma unroll
-      for (int spin = 0; spin < 2; ++spin) {
-        const double* G = Gc + (size_t)spin * NP * NP;
-        row[spin] = G[(size_t)is * NP + j];
-        col[spin] = G[(size_t)j * NP + is];
-      }
+      for (int k = 0; k < PF; ++k)
+        if (k == dpf) { row[0] = prow[k][0]; row[1] = prow[k][1]; col[0] = pcol[k][0]; col[1] = pcol[k][1]; }
+    } else {
+      load_site(is, row, col);
+#ifdef LQMC_PHASE_CLOCKS
+      ++n_miss;
+#endif
     }
-    // the warp that owns site `is` publishes that site's c history (tcgen05.ld is warp-collective)
-    if (warp == (is >> 5)) {
-      for (int m0 = 0; m0 < nd; m0 += 8) {
-        double v0[8], v1[8];
-        tmem_ld_f64x8_pair(tm_my + 2 * m0, tm_my + 2 * (L2_KDT + m0), v0, v1);
-        if (lane == (is & 31)) {
+    if (PF >= 1) {
+      // slots for sites is + 1 .. is + PF: keep what is already there (shifted), load the rest
 #pragma unroll
-          for (int q = 0; q < 8; ++q) { wis[m0 + q] = v0[q]; wis[L2_KDT + m0 + q] = v1[q]; }
-        }
+      for (int k = 0; k < PF; ++k) {
+        bool have = false;
+#pragma unroll
+        for (int k2 = k + 1; k2 < PF; ++k2)
+          if (dpf >= 0 && k2 == k + 1 + dpf) { prow[k][0] = prow[k2][0]; prow[k][1] = prow[k2][1]; pcol[k][0] = pcol[k2][0]; pcol[k][1] = pcol[k2][1]; have = true; }
+        if (!have) load_site(is + 1 + k, prow[k], pcol[k]);
       }
+      pf_base = is + 1;
     }
-    __syncthreads();
-    if (act) {
-      for (int m0 = 0; m0 < nd; m0 += 8) {
-        double wj[2][8];
-        tmem_ld_f64x8_pair(tm_my + 2 * m0, tm_my + 2 * (L2_KDT + m0), wj[0], wj[1]);
+    if (l2_hi < is + 1) l2_hi = is + 1;
+    l2_prefetch_to(is + 1 + LQMC_L2_PFD);
+    // c history of the flipped site: in the ring if the site was one of the last flip's next candidates, else the warp that
+    // owns the site publishes it (tcgen05.ld is warp-collective) at the price of one more barrier
+    const int dpub = is - pub_base;
+    const double* wsrc = sm.ring + (size_t)(is & (L2_RING - 1)) * 2 * L2_KDT;
+    if (nd > 0 && !(dpub >= 1 && dpub <= L2_PUB)) {
+      if (warp == (is >> 5)) {
+        for (int m0 = 0; m0 < nd; m0 += 8) {
+          double v0[8], v1[8];
+          tmem_ld_f64x8_pair(tm_my + 2 * m0, tm_my + 2 * (L2_KDT + m0), v0, v1);
+          if (lane == (is & 31)) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int m = m0 + q;
-          if (m < nd) {
-#pragma unroll
-            for (int spin = 0; spin < 2; ++spin) {
-              const double* Um = U3 + ((size_t)spin * L2_KDT + m) * NP;
-              row[spin] = rank1<EXACT>(row[spin], Um[is], wj[spin][q]);
-              col[spin] = rank1<EXACT>(col[spin], Um[j], wis[spin * L2_KDT + m]);
-            }
+            for (int q = 0; q < 8; ++q) { wis[m0 + q] = v0[q]; wis[L2_KDT + m0 + q] = v1[q]; }
           }
         }
       }
+      __syncthreads();
+      wsrc = wis;
+#ifdef LQMC_PHASE_CLOCKS
+      ++n_slow;
+#endif
+    }
+    const int dj = j - is;
+    const bool pubme = act && dj >= 1 && dj <= L2_PUB;
+#ifdef LQMC_PHASE_CLOCKS
+    { const long long tk1 = clock64(); tk_b1 += tk1 - tk0; }
+#endif
+    if (act) {
+      // Row rebuild: own c history from tensor memory (four updates of both spins per load: r[0..7] up, r[8..15] down) times
+      // e_m[is] (broadcast).  No per-update branch - the loads of a quad are issued together and the four multiplies are
+      // independent; updates past nd are computed on stale operands and discarded by a select.
+      for (int m0 = 0; m0 < nd; m0 += 4) {
+        TmemQuad wq;
+        tmem_ld_quad_issue(tm_my + 2 * m0, tm_my + 2 * (L2_KDT + m0), wq);
+        double ui[2][4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+          for (int spin = 0; spin < 2; ++spin) ui[spin][q] = U3[((size_t)spin * L2_KDT + m0 + q) * NP + is];
+        tmem_ld_quad_wait(wq);
+        double wj[2][4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          wj[0][q] = __hiloint2double((int)wq.r[2 * q + 1], (int)wq.r[2 * q]);
+          wj[1][q] = __hiloint2double((int)wq.r[8 + 2 * q + 1], (int)wq.r[8 + 2 * q]);
+        }
+        if (pubme) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) { myring[m0 + q] = wj[0][q]; myring[L2_KDT + m0 + q] = wj[1][q]; }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const bool valid = m0 + q < nd;
+#pragma unroll
+          for (int spin = 0; spin < 2; ++spin) {
+            const double r = rank1<EXACT>(row[spin], ui[spin][q], wj[spin][q]);
+            row[spin] = valid ? r : row[spin];
+          }
+        }
+      }
+      // c vectors need the row only: park them in tensor memory (and the ring) while the column is still being rebuilt
+      double cv[2];
+#pragma unroll
+      for (int spin = 0; spin < 2; ++spin) {
+        if (!PHYS) {
+          const double gamma = spin ? fu : fd;            // exp(-arg)-1 for up, exp(+arg)-1 for down (lqmc.py:320-323)
+          cv[spin] = __dmul_rn(-gamma, row[spin]);
+          if (j == is) cv[spin] = __dadd_rn(cv[spin], gamma);
+        } else {
+          cv[spin] = row[spin];
+        }
+        tmem_st_f64(tm_my + 2 * (spin * L2_KDT + nd), cv[spin]);
+        if (pubme) myring[spin * L2_KDT + nd] = cv[spin];
+      }
+      // Column rebuild: e_m[j] (own entry) times the flipped site's c history (ring / owner-published, broadcast)
+      for (int m0 = 0; m0 < nd; m0 += 4) {
+        double uj[2][4], ws[2][4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+          for (int spin = 0; spin < 2; ++spin) {
+            uj[spin][q] = U3[((size_t)spin * L2_KDT + m0 + q) * NP + j];
+            ws[spin][q] = wsrc[spin * L2_KDT + m0 + q];
+          }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const bool valid = m0 + q < nd;
+#pragma unroll
+          for (int spin = 0; spin < 2; ++spin) {
+            const double r = rank1<EXACT>(col[spin], uj[spin][q], ws[spin][q]);
+            col[spin] = valid ? r : col[spin];
+          }
+        }
+      }
+#ifdef LQMC_PHASE_CLOCKS
+      { double chk = row[0] + col[0] + row[1] + col[1]; if (chk == 1.2345e300) tk_b2 -= 1; const long long tk1 = clock64(); tk_b2 += tk1 - tk0; }
+#endif
 #pragma unroll
       for (int spin = 0; spin < 2; ++spin) {
         const double gs = spin ? gd : gu;
-        double e, c;
+        double e;
         if (!PHYS) {
-          const double gamma = spin ? fu : fd;            // exp(-arg)-1 for up, exp(+arg)-1 for down (lqmc.py:320-323)
+          const double gamma = spin ? fu : fd;
           const double ci = __dadd_rn(__dmul_rn(-gamma, gs), gamma);
           const double den = __dadd_rn(1.0, ci);
           const double r = __drcp_rn(den);
-          c = __dmul_rn(-gamma, row[spin]);
-          if (j == is) c = __dadd_rn(c, gamma);
           e = EXACT ? div_shared_rcp(col[spin], den, r, div_safe(den)) : col[spin] * r;
         } else {
           const double delta = spin ? fd : fu;
           const double rr = __dadd_rn(1.0, __dmul_rn(__dsub_rn(1.0, gs), delta));
           const double fac = delta / rr;
           e = ((j == is) ? (1.0 - col[spin]) : -col[spin]) * fac;
-          c = row[spin];
         }
         U3[((size_t)spin * L2_KDT + nd) * NP + j] = e;
-        tmem_st_f64(tm_my + 2 * (spin * L2_KDT + nd), c);
-        dnxt[spin * NP + j] = rank1<EXACT>(dcur[spin * NP + j], e, c);
+#ifdef LQMC_PHASE_CLOCKS
+        if (spin == 1) { if (e + cv[1] == 1.2345e300) tk_b3 -= 1; const long long tk1 = clock64(); tk_b3 += tk1 - tk0; }
+#endif
+        dnxt[spin * NP + j] = rank1<EXACT>(dcur[spin * NP + j], e, cv[spin]);
       }
       tmem_wait_st();
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");    // the two-column flush reads the partner warp's window
+#ifdef LQMC_PHASE_CLOCKS
+      { const long long tk1 = clock64(); tk_b4 += tk1 - tk0; }
+#endif
     }
+    pub_base = is;
     ++n_accepted;
     ++nd;
     cur ^= 1;
@@ -882,8 +1193,14 @@ __device__ void l2_propose_slice_tmem(double* __restrict__ Gc, int NP, L2Smem& s
     { const long long tk1 = clock64(); tk_build += tk1 - tk0; tk0 = tk1; }
 #endif
     if (nd == L2_KDT) {
-      if (NP == 256) l2_flush_tmem2<EXACT>(Gc, nd, U3, tm_base); else l2_flush_tmem<EXACT>(Gc, NP, nd, U3, tm_my);
+      const bool tok = l2_flush_token_acquire();
+      if (NP == 256) { wlo = is + 1; l2_flush_tmem2<EXACT>(Gc, nd, U3, tm_base, Tc, wlo); } else l2_flush_tmem<EXACT>(Gc, NP, nd, U3, tm_my);
+      l2_flush_token_release(tok);
       nd = 0;
+      if (PF > 0) {                               // G0 changed: reload the slots of the next candidates
+#pragma unroll
+        for (int k = 0; k < PF; ++k) load_site(is + 1 + k, prow[k], pcol[k]);
+      }
     }
 #ifdef LQMC_PHASE_CLOCKS
     { const long long tk1 = clock64(); tk_flush += tk1 - tk0; tk0 = tk1; }
@@ -891,15 +1208,30 @@ __device__ void l2_propose_slice_tmem(double* __restrict__ Gc, int NP, L2Smem& s
     i0 = is + 1;
   }
   if (nd > 0) {
-    if (NP == 256) l2_flush_tmem2<EXACT>(Gc, nd, U3, tm_base); else l2_flush_tmem<EXACT>(Gc, NP, nd, U3, tm_my);
+    const bool tok = l2_flush_token_acquire();
+    if (NP == 256) l2_flush_tmem2<EXACT>(Gc, nd, U3, tm_base, Tc, NP); else l2_flush_tmem<EXACT>(Gc, NP, nd, U3, tm_my);
+    l2_flush_token_release(tok);
   }
 #ifdef LQMC_PHASE_CLOCKS
   { const long long tk1 = clock64(); tk_flush += tk1 - tk0;
     if (tid == 0) { double* ob = p.obs_sum + (size_t)blockIdx.x * 3 * N; ob[0] = (double)tk_scan; ob[1] = (double)tk_build; ob[2] = (double)tk_flush; ob[3] = (double)n_accepted;
+      ob[4] = (double)tk_b1; ob[5] = (double)tk_b2; ob[6] = (double)n_slow; ob[7] = (double)n_miss;
       unsigned smid; asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
       unsigned long long gt1; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt1));
-      ob[4] = (double)smid; ob[5] = (double)(gt0 & 0xffffffffffffull); ob[6] = (double)(gt1 & 0xffffffffffffull); } }
+      ob[8] = (double)(gt0 & 0xffffffffffffull); ob[9] = (double)(gt1 & 0xffffffffffffull); ob[10] = (double)smid; ob[11] = (double)(tk1 - tk_begin);
+      ob[12] = (double)tk_b0; ob[13] = (double)tk_b3; ob[14] = (double)tk_b4; } }
 #endif
+  return n_accepted;
+}
+
+template <bool EXACT, bool PHYS>
+__device__ __forceinline__ void l2_propose_slice_tmem(double* __restrict__ Gc, double* __restrict__ Tc, int NP, L2Smem& sm, const SweepParams& p,
+                                                      long long trace_base, int& n_accepted, uint32_t tm_base) {
+  L2SliceArgs a;
+  a.Gc = Gc; a.Tc = Tc; a.U = sm.U; a.d = sm.d; a.u = sm.u; a.hist = sm.hist; a.ring = sm.ring; a.h = sm.h;
+  a.tr_ratio = p.tr_ratio; a.tr_acc = p.tr_acc; a.obs = p.obs_sum;
+  a.f_p2 = p.f_p2; a.f_m2 = p.f_m2; a.trace_base = trace_base; a.tm_base = tm_base; a.NP = NP; a.N = p.n_sites;
+  n_accepted += l2_propose_slice_tmem_sub<EXACT, PHYS>(a);
 }
 
 // ---- 256 < NP <= 640: the tensor-memory slice path with several columns per thread ------------------------------------------
@@ -1361,7 +1693,7 @@ __global__ void __launch_bounds__(L2_THREADS, TMEM >= 2 ? 1 : 2) sweep_l2_kernel
                     : lqmc_philox_uniform(p.seed, (uint64_t)(p.chain0 + chain), (uint64_t)(p.sweep0 + sweep), (uint32_t)(step * N + j));
           sm.u[j] = u;
         }
-        if (TMEM == 1) l2_propose_slice_tmem<EXACT, PHYS>(Gc, NP, sm, p, base, n_accepted, tm_base);
+        if (TMEM == 1) l2_propose_slice_tmem<EXACT, PHYS>(Gc, Tc, NP, sm, p, base, n_accepted, tm_base);
         else if (TMEM == 2) l2_propose_slice_tmemx<EXACT, PHYS, 2, 24>(Gc, NP, sm, p, base, n_accepted, tm_base);
         else if (TMEM == 3) l2_propose_slice_tmemx<EXACT, PHYS, 3, 16>(Gc, NP, sm, p, base, n_accepted, tm_base);
         else l2_propose_slice<EXACT, PHYS, L2_MAXQ>(Gc, NP, KD, sm, p, base, n_accepted);
@@ -1405,8 +1737,8 @@ inline int l2_alloc(L2Workspace& w, int n_sites, int np, int n_slices, int n_cha
     snprintf(err, errlen, "cudaMalloc of the %zu-byte GEMM workspace failed", bytes);
     return 4;
   }
-  // two CTAs per SM (about 113 KiB each) up to NP = 384, one above
-  const size_t budget = (np <= 384) ? 110 * 1024 : 220 * 1024;
+  // two CTAs per SM up to NP = 384 (228 KiB per SM, 1 KiB reserved per CTA: 113 KiB each), one above
+  const size_t budget = (np <= 384) ? 113 * 1024 : 220 * 1024;
   int kd = 1;
   while (kd < 64 && l2_smem_bytes(np, kd + 1) <= budget) ++kd;
   if (const char* env = getenv("LQMC_L2_KD")) { const int v = atoi(env); if (v >= 1 && v <= kd) kd = v; }   // experiments

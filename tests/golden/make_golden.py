@@ -278,7 +278,156 @@ def case_det(lqmc):
              fields=np.stack(fields), gf=np.asarray(gf))
 
 
-CASES = dict(cfg1=case_cfg1, small=case_small, cfg2=case_cfg2, cfg3=case_cfg3, cfg4=case_cfg4, u0=case_u0,
+def subsample(g, rows, cols):
+    """The parts of a Green's function a fixture keeps when the full matrix would be megabytes: `rows`, `cols` and the
+    diagonal.  (The full-matrix comparison is GPU vs oracle in the test; the oracle is pinned on these parts, on every
+    ratio - each depends on the whole update history through the diagonal - and on every decision.)"""
+    return g[rows, :].copy(), g[:, cols].copy(), np.diag(g).copy()
+
+
+class Stop(Exception):
+    pass
+
+
+def case_cfg4mid(lqmc):
+    """16x16 (ideal periodic K, H10), U=4, beta=8, L=80: the reference's own free-running sweep from slice 79 down to
+    slice 10 (about 25 min of the interpreted loop), recording the two mid-sweep slices 44 and 10 where |G| ~ 1e2 and a
+    third of the ratios are negative.  Kept: G after the proposals of slices 45 and 11 (the inputs: the
+    wrap to 44 / 10 is replayed with the same NumPy calls, lqmc.py:338-345), every ratio / decision / uniform of slices
+    44 and 10, the field columns involved, and rows / columns / diagonal of G after the proposals of 44 and 10."""
+    sys.path.insert(0, os.path.join(HERE, "..", ".."))
+    from oracle import sweep_oracle as so
+    ham = so.ideal_square_kinetic(16, t=1.0, mu=2.0)
+    model = IdealModel(ham, u=4)
+    lt, n = 80, 256
+    solver = make_solver(lqmc, model, 8.0, lt, seed=43)
+    field_in = solver.config.config.copy()
+    state = np.random.get_state()
+    uniforms = np.random.rand(lt * n).reshape(lt, n)
+    np.random.set_state(state)
+    want = (45, 44, 11, 10)
+    ratios = np.empty((lt, n))
+    accs = np.zeros((lt, n), dtype=bool)
+    snaps = {}
+
+    def hook(i, l):
+        step = lt - 1 - l
+        ratios[step, i] = solver.ratio
+        accs[step, i] = solver.acc
+        if i == n - 1:
+            if l in want:
+                loc = sys._getframe(1).f_locals
+                snaps[l] = (loc["gf_up"].copy(), loc["gf_dn"].copy())
+            print(f"cfg4mid: slice {l} done, accept so far {accs[:step + 1].mean():.3f}", flush=True)
+            if l == min(want):
+                raise Stop
+
+    solver._debug = hook
+    t0 = time.time()
+    try:
+        solver._update_step()
+    except Stop:
+        pass
+    print(f"cfg4mid: reference slices 79..10 took {time.time() - t0:.1f} s")
+    field_out = solver.config.config.copy()
+    rows = np.arange(0, n, 16)
+    cols = np.arange(5, n, 16)
+    arrays = dict(ham=ham, u=4.0, beta=8.0, lamb=solver.lamb, exp_k=solver.exp_k, rows=rows, cols=cols,
+                  field0=field_in, field1=field_out)
+    for l in (44, 10):
+        step = lt - 1 - l
+        # self-check: replaying wrap + slice with the same NumPy calls reproduces the reference bit for bit
+        h = field_out.copy()
+        h[:, l] = field_in[:, l]
+        gu, gd = so.wrap(snaps[l + 1][0], snaps[l + 1][1], h, l + 1, solver.exp_k, solver.lamb)
+        pre_max = max(np.abs(gu).max(), np.abs(gd).max())
+        r, a = so.slice_proposals(gu, gd, h, l, solver.lamb, uniforms[step])
+        assert np.array_equal(a, accs[step]) and np.array_equal(r, ratios[step])
+        assert np.array_equal(gu, snaps[l][0]) and np.array_equal(gd, snaps[l][1]) and np.array_equal(h[:, l], field_out[:, l])
+        print(f"cfg4mid: slice {l}: max|G| before {pre_max:.3e}, negative ratios {np.mean(ratios[step] < 0):.2f}, "
+              f"accept {accs[step].mean():.2f}, max|ratio| {np.abs(ratios[step]).max():.3e}")
+        arrays.update({f"in{l}_up": snaps[l + 1][0], f"in{l}_dn": snaps[l + 1][1],
+                       f"uniforms{l}": uniforms[step], f"ratios{l}": ratios[step], f"accs{l}": accs[step]})
+        for tag, g in (("up", snaps[l][0]), ("dn", snaps[l][1])):
+            gr, gc, gdg = subsample(g, rows, cols)
+            arrays.update({f"post{l}_{tag}_rows": gr, f"post{l}_{tag}_cols": gc, f"post{l}_{tag}_diag": gdg})
+    save("cfg4_16x16_mid", **arrays)
+
+
+def case_cfg5(lqmc):
+    """24x24 square (N = 576, built by the reference's own lattice builder), U=6, beta=10, L=100:
+    proposals(99) -> wrap -> proposals(98) of the reference's `_update_step`, teacher-forced from a well-scaled G.
+    The reference always starts a sweep from `np.linalg.inv(get_m(0, sigma))` (lqmc.py:303-307), which at beta = 10 is
+    pure round-off (max|G| ~ 1e-24).  To run its proposals and wrap on an O(1) Green's function without
+    touching reference code, `np.linalg.inv` is wrapped for the two sweep-start calls only and hands back a prepared G0:
+    float32-rounded `inv(I + B_99 ... B_90)` (a short, well-conditioned product; float32 values keep the fixture small).
+    Everything after that - ratios, decisions, rank-1 loops, the wrap's own `inv(b)` - is the unmodified reference."""
+    model = lqmc.HubbardModel(u=6, t=1)
+    t0 = time.time()
+    model.build_square(24)
+    print(f"cfg5: reference lattice builder took {time.time() - t0:.1f} s")
+    lt, n = 100, 576
+    solver = make_solver(lqmc, model, 10.0, lt, seed=53)
+    field_in = solver.config.config.copy()
+    g0 = []
+    for sigma in (+1, -1):
+        prod = 1
+        for l in range(lt - 1, lt - 11, -1):
+            prod = np.dot(prod, np.dot(solver.exp_k, solver.get_exp_v(l, sigma)))
+        g0.append(np.linalg.inv(np.eye(n) + prod).astype(np.float32))
+    state = np.random.get_state()
+    uniforms = np.random.rand(2 * n).reshape(2, n)
+    np.random.set_state(state)
+    ratios = np.empty((2, n))
+    accs = np.zeros((2, n), dtype=bool)
+    snaps = {}
+
+    def hook(i, l):
+        step = lt - 1 - l
+        ratios[step, i] = solver.ratio
+        accs[step, i] = solver.acc
+        if i == n - 1:
+            loc = sys._getframe(1).f_locals
+            snaps[l] = (loc["gf_up"].copy(), loc["gf_dn"].copy())
+            print(f"cfg5: slice {l} done after {time.time() - t0:.0f} s", flush=True)
+            if l == lt - 2:
+                raise Stop
+
+    solver._debug = hook
+    real_inv = np.linalg.inv
+    pending = [g0[0].astype(np.float64), g0[1].astype(np.float64)]
+
+    def inv_once(a):
+        if pending and a.shape == (n, n):
+            return pending.pop(0).copy()
+        return real_inv(a)
+
+    real_get_m = solver.get_m
+    solver.get_m = lambda l0, sigma: np.eye(n)            # the product is not needed: its inverse is replaced
+    np.linalg.inv = inv_once
+    t0 = time.time()
+    try:
+        solver._update_step()
+    except Stop:
+        pass
+    finally:
+        np.linalg.inv = real_inv
+        solver.get_m = real_get_m
+    assert not pending
+    print(f"cfg5: two reference slices took {time.time() - t0:.1f} s, accept {accs.mean():.3f}, "
+          f"max|G| after 99: {np.abs(snaps[99][0]).max():.3e}")
+    rows = np.arange(3, n, 36)
+    cols = np.arange(7, n, 36)
+    arrays = dict(ham=model.ham_kinetic(), u=6.0, beta=10.0, lamb=solver.lamb, exp_k=solver.exp_k, rows=rows, cols=cols,
+                  g0_up=g0[0], g0_dn=g0[1], field0=field_in, field1=solver.config.config.copy(), uniforms=uniforms, ratios=ratios, accs=accs)
+    for l in (99, 98):
+        for tag, g in (("up", snaps[l][0]), ("dn", snaps[l][1])):
+            gr, gc, gdg = subsample(g, rows, cols)
+            arrays.update({f"post{l}_{tag}_rows": gr, f"post{l}_{tag}_cols": gc, f"post{l}_{tag}_diag": gdg})
+    save("cfg5_24x24_slices", **arrays)
+
+
+CASES = dict(cfg4mid=case_cfg4mid, cfg5=case_cfg5, cfg1=case_cfg1, small=case_small, cfg2=case_cfg2, cfg3=case_cfg3, cfg4=case_cfg4, u0=case_u0,
              lattice=case_lattice, det=case_det)
 
 if __name__ == "__main__":
