@@ -46,7 +46,9 @@ struct lqmc_engine {
   bool family_reg = true;
   double lamb = 0;
   double hs[4] = {1, 1, 0, 0};
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;       // non-blocking: every engine-side memset / copy below is issued ON it, never on the legacy stream
+  cudaEvent_t foreignDone = nullptr;   // recorded on a caller-owned stream after lqmc_sweep_async queued work there
+  bool foreignPending = false;
   // device state
   double *dE = nullptr, *dEt = nullptr, *dEi = nullptr, *dEit = nullptr;
   int8_t* dField = nullptr;
@@ -126,6 +128,22 @@ __global__ void field_to_host_kernel(const int8_t* __restrict__ dev, int8_t* __r
     }
     __syncthreads();
   }
+}
+
+// Everything this engine has queued: its own stream, and the caller's stream if lqmc_sweep_async was given one (an event
+// recorded there at submit time - valid even if the caller has destroyed the stream since).
+int drain(lqmc_engine* e) {
+  if (e->foreignPending) {
+    CU(cudaEventSynchronize(e->foreignDone));
+    e->foreignPending = false;
+  }
+  CU(cudaStreamSynchronize(e->stream));
+  return LQMC_OK;
+}
+// Later work on the engine's stream must not overtake sweeps still running on a caller's stream.
+int order_after_foreign(lqmc_engine* e) {
+  if (e->foreignPending) CU(cudaStreamWaitEvent(e->stream, e->foreignDone, 0));
+  return LQMC_OK;
 }
 
 size_t field_bytes(const lqmc_engine* e) { return (size_t)e->C * e->L * e->NP; }
@@ -234,9 +252,16 @@ int set_smem(K kernel, size_t bytes) {
   return LQMC_OK;
 }
 
+void stab_free(lqmc_engine* e);
+int stab_init_impl(lqmc_engine* e);
 int stab_init(lqmc_engine* e) {
+  if (e->st.ready) return LQMC_OK;
+  const int rc = stab_init_impl(e);
+  if (rc) stab_free(e);          // a failed allocation part-way leaves nothing behind (stab_free resets the struct)
+  return rc;
+}
+int stab_init_impl(lqmc_engine* e) {
   auto& st = e->st;
-  if (st.ready) return LQMC_OK;
   CU(cudaSetDevice(e->device));
   st.NPs = lqmc::st_padded_size(e->N);
   if (e->N > 64 && st.NPs != e->NP)
@@ -580,6 +605,7 @@ int lqmc_create(lqmc_engine** out, int device, int n_sites, int n_slices, int n_
   const int NP = e->NP, N = e->N;
   auto cleanup = [&](int code) { lqmc_destroy(e); return code; };
   if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) return cleanup(fail(LQMC_ERR_CUDA, "cudaStreamCreate failed"));
+  if (cudaEventCreateWithFlags(&e->foreignDone, cudaEventDisableTiming) != cudaSuccess) return cleanup(fail(LQMC_ERR_CUDA, "cudaEventCreate failed"));
   // identity-padded operator matrices and their transposes
   std::vector<double> m((size_t)NP * NP), mt((size_t)NP * NP);
   double** dst[4] = {&e->dE, &e->dEt, &e->dEi, &e->dEit};
@@ -608,14 +634,16 @@ int lqmc_create(lqmc_engine** out, int device, int n_sites, int n_slices, int n_
     return cleanup(fail(LQMC_ERR_NOMEM, "cudaMalloc of chain state failed (%d chains, N=%d)", e->C, N));
   if (cudaMallocHost(&e->hostField, field_bytes(e)) != cudaSuccess || cudaMallocHost(&e->hostG, nG * sizeof(double)) != cudaSuccess)
     return cleanup(fail(LQMC_ERR_NOMEM, "cudaMallocHost of the staging buffers failed"));
-  cudaMemset(e->dField, 1, field_bytes(e));
-  cudaMemset(e->dG, 0, nG * sizeof(double));
+  if (cudaMemsetAsync(e->dField, 1, field_bytes(e), e->stream) != cudaSuccess ||
+      cudaMemsetAsync(e->dG, 0, nG * sizeof(double), e->stream) != cudaSuccess)
+    return cleanup(fail(LQMC_ERR_CUDA, "initialising the chain state failed"));
   if (!e->family_reg) {
     int rc = lqmc::l2_alloc(e->l2, N, NP, e->L, e->C, g_err, sizeof(g_err));
     if (rc) return cleanup(rc);
   }
   int rc = lqmc_reset_measurements(e);
   if (rc) return cleanup(rc);
+  if (cudaStreamSynchronize(e->stream) != cudaSuccess) return cleanup(fail(LQMC_ERR_CUDA, "engine initialisation failed"));
   *out = e;
   return LQMC_OK;
 }
@@ -630,6 +658,7 @@ void lqmc_destroy(lqmc_engine* e) {
   stab_free(e);
   if (e->hostField) cudaFreeHost(e->hostField);
   if (e->hostG) cudaFreeHost(e->hostG);
+  if (e->foreignDone) cudaEventDestroy(e->foreignDone);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
 }
@@ -637,6 +666,7 @@ void lqmc_destroy(lqmc_engine* e) {
 int lqmc_set_field(lqmc_engine* e, const int8_t* field) {
   if (!e || !field) return fail(LQMC_ERR_INVALID, "engine or field is NULL");
   CU(cudaSetDevice(e->device));
+  { int rc = order_after_foreign(e); if (rc) return rc; }
   const int N = e->N, L = e->L, NP = e->NP;
   // raw upload, layout conversion and the +-1 check on the device (a scalar host loop over C*N*L bytes cost more than the copy)
   const size_t raw_bytes = (size_t)e->C * N * L;
@@ -659,6 +689,7 @@ int lqmc_set_field(lqmc_engine* e, const int8_t* field) {
 int lqmc_get_field(lqmc_engine* e, int8_t* field) {
   if (!e || !field) return fail(LQMC_ERR_INVALID, "engine or field is NULL");
   CU(cudaSetDevice(e->device));
+  { int rc = order_after_foreign(e); if (rc) return rc; }
   const int N = e->N, L = e->L, NP = e->NP;
   const size_t raw_bytes = (size_t)e->C * N * L;
   field_to_host_kernel<<<dim3((L + 31) / 32, e->C), dim3(32, 8), 0, e->stream>>>(e->dField, e->dFieldRaw, N, L, NP);
@@ -672,6 +703,7 @@ int lqmc_get_field(lqmc_engine* e, int8_t* field) {
 int lqmc_set_g(lqmc_engine* e, const double* g) {
   if (!e || !g) return fail(LQMC_ERR_INVALID, "engine or g is NULL");
   CU(cudaSetDevice(e->device));
+  { int rc = order_after_foreign(e); if (rc) return rc; }
   const int N = e->N, NP = e->NP;
   const size_t mats = (size_t)e->C * 2;
   if (N != NP) {
@@ -693,6 +725,7 @@ int lqmc_set_g(lqmc_engine* e, const double* g) {
 int lqmc_get_g(lqmc_engine* e, double* g) {
   if (!e || !g) return fail(LQMC_ERR_INVALID, "engine or g is NULL");
   CU(cudaSetDevice(e->device));
+  { int rc = order_after_foreign(e); if (rc) return rc; }
   const int N = e->N, NP = e->NP;
   const size_t mats = (size_t)e->C * 2;
   if (N != NP) {
@@ -774,28 +807,32 @@ int lqmc_sweep_async(lqmc_engine* e, int n_sweeps, const double* d_uniforms, uin
   if (n_sweeps < 0) return fail(LQMC_ERR_INVALID, "n_sweeps = %d is negative", n_sweeps);
   if (n_sweeps == 0) return LQMC_OK;
   cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
+  const bool foreign = (s != e->stream);
+  CU(cudaSetDevice(e->device));
+  if (!foreign) { int rc0 = order_after_foreign(e); if (rc0) return rc0; }
   const bool phys = (e->flags & LQMC_MODE_PHYSICS) != 0;
+  int rc;
   if (phys && e->stab_every > 0) {
     // stabilised schedule (stab.cuh): G is rebuilt from the field by QR/UDV at the top of every segment of stab_every
     // slices and propagated by wraps inside it
-    CU(cudaSetDevice(e->device));
-    return stab_sweeps(e, n_sweeps, d_uniforms, seed, measure != 0, s);
+    rc = stab_sweeps(e, n_sweeps, d_uniforms, seed, measure != 0, s);
+  } else {
+    RunSpec r;
+    r.n_sweeps = n_sweeps; r.step_lo = 0; r.step_hi = e->L; r.recompute = true; r.propose = true; r.wrap = true;
+    r.measure = measure != 0; r.l0 = phys ? e->L - 1 : 0; r.d_uniforms = d_uniforms; r.seed = seed;
+    rc = run(e, r, s);
+    if (!rc) e->sweep_counter += n_sweeps;
   }
-  RunSpec r;
-  r.n_sweeps = n_sweeps; r.step_lo = 0; r.step_hi = e->L; r.recompute = true; r.propose = true; r.wrap = true;
-  r.measure = measure != 0; r.l0 = phys ? e->L - 1 : 0; r.d_uniforms = d_uniforms; r.seed = seed;
-  int rc = run(e, r, s);
-  if (rc) return rc;
-  e->sweep_counter += n_sweeps;
-  return LQMC_OK;
+  if (foreign) {            // whatever was queued (even a partial schedule on failure) must be waited for by the getters
+    if (cudaEventRecord(e->foreignDone, s) == cudaSuccess) e->foreignPending = true;
+  }
+  return rc;
 }
 
 int lqmc_sync(lqmc_engine* e) {
   if (!e) return fail(LQMC_ERR_INVALID, "engine is NULL");
   CU(cudaSetDevice(e->device));
-  CU(cudaStreamSynchronize(e->stream));
-  CU(cudaDeviceSynchronize());
-  return LQMC_OK;
+  return drain(e);
 }
 
 int lqmc_sweep(lqmc_engine* e, int n_sweeps, const double* uniforms, uint64_t seed, int measure) {
@@ -880,8 +917,9 @@ int lqmc_get_det(lqmc_engine* e, double* det_old) {
   if (!e || !det_old) return fail(LQMC_ERR_INVALID, "engine or det_old is NULL");
   if (!e->dDetOld) return fail(LQMC_ERR_INVALID, "no det-mode sweep has run on this engine");
   CU(cudaSetDevice(e->device));
+  { int rc = drain(e); if (rc) return rc; }
+  CU(cudaMemcpyAsync(det_old, e->dDetOld, (size_t)e->C * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
   CU(cudaStreamSynchronize(e->stream));
-  CU(cudaMemcpy(det_old, e->dDetOld, (size_t)e->C * sizeof(double), cudaMemcpyDeviceToHost));
   return LQMC_OK;
 }
 
@@ -889,20 +927,23 @@ int lqmc_get_trace(lqmc_engine* e, uint8_t* acc, double* ratio) {
   if (!e) return fail(LQMC_ERR_INVALID, "engine is NULL");
   if (!(e->flags & LQMC_TRACE)) return fail(LQMC_ERR_INVALID, "engine was created without LQMC_TRACE");
   CU(cudaSetDevice(e->device));
-  if (acc) CU(cudaMemcpy(acc, e->dTrAcc, e->trCount, cudaMemcpyDeviceToHost));
-  if (ratio) CU(cudaMemcpy(ratio, e->dTrRatio, e->trCount * sizeof(double), cudaMemcpyDeviceToHost));
+  { int rc = drain(e); if (rc) return rc; }                 // the sweep that writes the trace may still be in flight (lqmc_sweep_submit)
+  if (acc) CU(cudaMemcpyAsync(acc, e->dTrAcc, e->trCount, cudaMemcpyDeviceToHost, e->stream));
+  if (ratio) CU(cudaMemcpyAsync(ratio, e->dTrRatio, e->trCount * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
   return LQMC_OK;
 }
 
 int lqmc_get_measurements(lqmc_engine* e, double* g_sum, double* obs_sum, int64_t* n_meas, int64_t* n_accepted) {
   if (!e) return fail(LQMC_ERR_INVALID, "engine is NULL");
   CU(cudaSetDevice(e->device));
-  CU(cudaStreamSynchronize(e->stream));
+  { int rc = drain(e); if (rc) return rc; }
   const size_t C = e->C, N = e->N;
-  if (g_sum) CU(cudaMemcpy(g_sum, e->dGsum, C * 2 * N * N * sizeof(double), cudaMemcpyDeviceToHost));
-  if (obs_sum) CU(cudaMemcpy(obs_sum, e->dObs, C * 3 * N * sizeof(double), cudaMemcpyDeviceToHost));
-  if (n_meas) CU(cudaMemcpy(n_meas, e->dNmeas, C * sizeof(long long), cudaMemcpyDeviceToHost));
-  if (n_accepted) CU(cudaMemcpy(n_accepted, e->dNacc, C * sizeof(long long), cudaMemcpyDeviceToHost));
+  if (g_sum) CU(cudaMemcpyAsync(g_sum, e->dGsum, C * 2 * N * N * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  if (obs_sum) CU(cudaMemcpyAsync(obs_sum, e->dObs, C * 3 * N * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  if (n_meas) CU(cudaMemcpyAsync(n_meas, e->dNmeas, C * sizeof(long long), cudaMemcpyDeviceToHost, e->stream));
+  if (n_accepted) CU(cudaMemcpyAsync(n_accepted, e->dNacc, C * sizeof(long long), cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
   return LQMC_OK;
 }
 
@@ -910,12 +951,13 @@ int lqmc_set_measurements(lqmc_engine* e, const double* g_sum, const double* obs
                           const int64_t* n_accepted) {
   if (!e) return fail(LQMC_ERR_INVALID, "engine is NULL");
   CU(cudaSetDevice(e->device));
-  CU(cudaStreamSynchronize(e->stream));
+  { int rc = drain(e); if (rc) return rc; }
   const size_t C = e->C, N = e->N;
-  if (g_sum) CU(cudaMemcpy(e->dGsum, g_sum, C * 2 * N * N * sizeof(double), cudaMemcpyHostToDevice));
-  if (obs_sum) CU(cudaMemcpy(e->dObs, obs_sum, C * 3 * N * sizeof(double), cudaMemcpyHostToDevice));
-  if (n_meas) CU(cudaMemcpy(e->dNmeas, n_meas, C * sizeof(long long), cudaMemcpyHostToDevice));
-  if (n_accepted) CU(cudaMemcpy(e->dNacc, n_accepted, C * sizeof(long long), cudaMemcpyHostToDevice));
+  if (g_sum) CU(cudaMemcpyAsync(e->dGsum, g_sum, C * 2 * N * N * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+  if (obs_sum) CU(cudaMemcpyAsync(e->dObs, obs_sum, C * 3 * N * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+  if (n_meas) CU(cudaMemcpyAsync(e->dNmeas, n_meas, C * sizeof(long long), cudaMemcpyHostToDevice, e->stream));
+  if (n_accepted) CU(cudaMemcpyAsync(e->dNacc, n_accepted, C * sizeof(long long), cudaMemcpyHostToDevice, e->stream));
+  CU(cudaStreamSynchronize(e->stream));        // the caller's buffers are pageable: do not return before they have been read
   return LQMC_OK;
 }
 
@@ -923,10 +965,12 @@ int lqmc_reset_measurements(lqmc_engine* e) {
   if (!e) return fail(LQMC_ERR_INVALID, "engine is NULL");
   CU(cudaSetDevice(e->device));
   const size_t C = e->C, N = e->N;
-  CU(cudaMemset(e->dGsum, 0, C * 2 * N * N * sizeof(double)));
-  CU(cudaMemset(e->dObs, 0, C * 3 * N * sizeof(double)));
-  CU(cudaMemset(e->dNmeas, 0, C * sizeof(long long)));
-  CU(cudaMemset(e->dNacc, 0, C * sizeof(long long)));
+  // on the engine's stream: ordered after sweeps still in flight there (lqmc_sweep_submit) and before the next one queued
+  { int rc = order_after_foreign(e); if (rc) return rc; }
+  CU(cudaMemsetAsync(e->dGsum, 0, C * 2 * N * N * sizeof(double), e->stream));
+  CU(cudaMemsetAsync(e->dObs, 0, C * 3 * N * sizeof(double), e->stream));
+  CU(cudaMemsetAsync(e->dNmeas, 0, C * sizeof(long long), e->stream));
+  CU(cudaMemsetAsync(e->dNacc, 0, C * sizeof(long long), e->stream));
   return LQMC_OK;
 }
 

@@ -1674,7 +1674,14 @@ __global__ void __launch_bounds__(L2_THREADS, TMEM >= 2 ? 1 : 2) sweep_l2_kernel
   __syncthreads();
 
   for (int sweep = 0; sweep < p.n_sweeps; ++sweep) {
+#ifdef LQMC_PHASE_CLOCKS
+    long long kt_rec = 0, kt_slice = 0, kt_wrap = 0, kt0 = clock64();
+#define LQMC_KT(acc) { const long long kt1 = clock64(); acc += kt1 - kt0; kt0 = kt1; }
+#else
+#define LQMC_KT(acc)
+#endif
     if (p.do_recompute) l2_recompute(Gc, Tc, NP, KD, field, p.recompute_l0, p, sm, piv);
+    LQMC_KT(kt_rec)
     for (int step = p.step_lo; step < p.step_hi; ++step) {
       const int l = L - 1 - step;
       const long long base = (((long long)chain * p.buf_sweeps + p.buf_sweep0 + sweep) * p.buf_steps + (step - p.buf_step0)) * N;
@@ -1693,18 +1700,24 @@ __global__ void __launch_bounds__(L2_THREADS, TMEM >= 2 ? 1 : 2) sweep_l2_kernel
                     : lqmc_philox_uniform(p.seed, (uint64_t)(p.chain0 + chain), (uint64_t)(p.sweep0 + sweep), (uint32_t)(step * N + j));
           sm.u[j] = u;
         }
+        LQMC_KT(kt_wrap)
         if (TMEM == 1) l2_propose_slice_tmem<EXACT, PHYS>(Gc, Tc, NP, sm, p, base, n_accepted, tm_base);
         else if (TMEM == 2) l2_propose_slice_tmemx<EXACT, PHYS, 2, 24>(Gc, NP, sm, p, base, n_accepted, tm_base);
         else if (TMEM == 3) l2_propose_slice_tmemx<EXACT, PHYS, 3, 16>(Gc, NP, sm, p, base, n_accepted, tm_base);
         else l2_propose_slice<EXACT, PHYS, L2_MAXQ>(Gc, NP, KD, sm, p, base, n_accepted);
         __syncthreads();
         for (int j = tid; j < NP; j += L2_THREADS) field[(size_t)l * NP + j] = sm.h[j];
+        LQMC_KT(kt_slice)
       }
       if (p.do_wrap && l > 0 && !(p.skip_last_wrap && step == p.step_hi - 1)) {
         __syncthreads();
         l2_wrap<PHYS>(Gc, Tc, NP, field + (size_t)(l - 1) * NP, p, sm);
+        LQMC_KT(kt_wrap)
       }
     }
+#ifdef LQMC_PHASE_CLOCKS
+    if (tid == 0 && p.do_recompute) { double* ob = p.obs_sum + (size_t)chain * 3 * N; ob[16] = (double)kt_rec; ob[17] = (double)kt_slice; ob[18] = (double)kt_wrap; }
+#endif
     if (p.measure) {
       __syncthreads();
       for (int spin = 0; spin < 2; ++spin) {

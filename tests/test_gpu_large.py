@@ -186,3 +186,99 @@ def test_cfg5_slice_is_bit_exact_at_full_size():
     assert np.array_equal(h_out, h)
     wu, wd = so.wrap(gu, gd, h, lt - 1, exp_k, lamb)
     assert _close(w[0], wu) and _close(w[1], wd)
+
+
+# ------------------------------------------------------------------------------------------------
+# reference-held evidence from the middle of the headline sweep and at the 24x24 size (round 2)
+# ------------------------------------------------------------------------------------------------
+
+def _sub_equal(gmat, g, key):
+    """Rows / columns / diagonal of a Green's function against the parts a large fixture keeps."""
+    return (np.array_equal(gmat[g["rows"], :], g[key + "_rows"]) and np.array_equal(gmat[:, g["cols"]], g[key + "_cols"])
+            and np.array_equal(np.diag(gmat), g[key + "_diag"]))
+
+
+def _sub_close(gmat, g, key, rtol):
+    scale = max(np.abs(g[key + "_rows"]).max(), np.abs(g[key + "_cols"]).max())
+    err = max(np.abs(gmat[g["rows"], :] - g[key + "_rows"]).max(), np.abs(gmat[:, g["cols"]] - g[key + "_cols"]).max(),
+              np.abs(np.diag(gmat) - g[key + "_diag"]).max())
+    return err <= rtol * scale
+
+
+@pytest.mark.parametrize("l", [44, 10])
+def test_cfg4_mid_sweep_reference_slices(golden, l):
+    """BASELINE configs[3], slices 44 and 10 of the REFERENCE's own free-running sweep (|G| ~ 1e3, 40 % of the ratios
+    negative, |ratio| up to 3e5 - SURVEY.md B.3): from the reference's G after the proposals of slice l+1, wrap on the GPU,
+    then the proposals of slice l.  Decisions identical to the reference; with the wrap teacher-forced (same NumPy calls as
+    lqmc.py:338-345) ratios, decisions and G bit for bit."""
+    g = golden("cfg4_16x16_mid")
+    n, lt = g["field0"].shape
+    lamb = float(g["lamb"])
+    step = lt - 1 - l
+    h = g["field1"].copy()
+    h[:, :l + 1] = g["field0"][:, :l + 1]                 # slices above l already updated, l and below untouched
+    uni = g[f"uniforms{l}"]
+    with _engine(g["exp_k"], lamb, lt, trace=True) as eng:
+        eng.set_field(h[None])
+        eng.set_g(np.stack([g[f"in{l}_up"], g[f"in{l}_dn"]])[None])
+        eng.wrap(l + 1)
+        w = eng.get_g()[0]
+        wu, wd = so.wrap(g[f"in{l}_up"], g[f"in{l}_dn"], h, l + 1, g["exp_k"], lamb)
+        assert _close(w[0], wu) and _close(w[1], wd)
+        # free-running from the GPU's own wrap: same decisions as the reference, G close
+        eng.slice(l, uni[None])
+        acc, ratio = eng.get_trace()
+        assert np.array_equal(acc[0, 0, 0], g[f"accs{l}"])
+        out = eng.get_g()[0]
+        assert _sub_close(out[0], g, f"post{l}_up", 1e-8) and _sub_close(out[1], g, f"post{l}_dn", 1e-8)
+        assert np.array_equal(eng.get_field()[0][:, l], g["field1"][:, l])
+        # teacher-forced wrap: bit for bit against the NumPy restatement on the same inputs
+        eng.set_field(h[None])
+        eng.set_g(np.stack([wu, wd])[None])
+        eng.slice(l, uni[None])
+        acc, ratio = eng.get_trace()
+        out = eng.get_g()[0]
+    ho = h.copy()
+    r_o, a_o = so.slice_proposals(wu, wd, ho, l, lamb, uni)
+    assert np.array_equal(acc[0, 0, 0], a_o) and np.array_equal(ratio[0, 0, 0], r_o)
+    assert np.array_equal(out[0], wu) and np.array_equal(out[1], wd)          # full matrices
+    assert np.array_equal(a_o, g[f"accs{l}"])
+    if np.array_equal(r_o, g[f"ratios{l}"]):
+        # this host's BLAS reproduces the fixture's wrap (always true where the fixture was made): then the CUDA slice equals
+        # the REFERENCE's recorded slice bit for bit as well
+        assert _sub_equal(out[0], g, f"post{l}_up") and _sub_equal(out[1], g, f"post{l}_dn")
+    else:
+        assert np.allclose(r_o, g[f"ratios{l}"], rtol=1e-8, atol=0)
+        assert _sub_close(out[0], g, f"post{l}_up", 1e-8) and _sub_close(out[1], g, f"post{l}_dn", 1e-8)
+
+
+def test_cfg5_reference_slices(golden):
+    """BASELINE configs[4] (24x24 built by the reference's own lattice code, N = 576, U=6, beta=10, L=100): proposals(99),
+    wrap, proposals(98) of the reference's `_update_step` from a well-scaled G0 (tests/golden/make_golden.py: case_cfg5).
+    Slice 99 bit for bit (ratios, decisions, G on the recorded rows / columns / diagonal, full G against the oracle);
+    slice 98 after the GPU's own wrap: same decisions, G within 1e-9."""
+    g = golden("cfg5_24x24_slices")
+    n, lt = g["field0"].shape
+    assert n == 576
+    lamb = float(g["lamb"])
+    g0 = np.stack([g["g0_up"].astype(np.float64), g["g0_dn"].astype(np.float64)])
+    with _engine(g["exp_k"], lamb, lt, trace=True) as eng:
+        eng.set_field(g["field0"][None])
+        eng.set_g(g0[None])
+        eng.slice(99, g["uniforms"][0][None])
+        acc, ratio = eng.get_trace()
+        assert np.array_equal(acc[0, 0, 0], g["accs"][0]) and np.array_equal(ratio[0, 0, 0], g["ratios"][0])
+        out = eng.get_g()[0]
+        assert _sub_equal(out[0], g, "post99_up") and _sub_equal(out[1], g, "post99_dn")
+        gu, gd = g0[0].copy(), g0[1].copy()
+        h = g["field0"].copy()
+        so.slice_proposals(gu, gd, h, 99, lamb, g["uniforms"][0])
+        assert np.array_equal(out[0], gu) and np.array_equal(out[1], gd)
+        assert np.array_equal(eng.get_field()[0], h)
+        eng.wrap(99)
+        eng.slice(98, g["uniforms"][1][None])
+        acc, _ = eng.get_trace()
+        assert np.array_equal(acc[0, 0, 0], g["accs"][1])
+        out = eng.get_g()[0]
+        assert _sub_close(out[0], g, "post98_up", 1e-9) and _sub_close(out[1], g, "post98_dn", 1e-9)
+        assert np.array_equal(eng.get_field()[0], g["field1"])

@@ -197,6 +197,50 @@ def test_cfg2_full_sweep_teacher_forced_from_reference_g0(golden):
     assert _close(out[0], g["gf_up"], 1e-5) and _close(out[1], g["gf_dn"], 1e-5)
 
 
+def test_cfg3_full_sweep_per_slice_teacher_forced(golden):
+    """BASELINE configs[2] (ring N=64, U=8, beta=8, L=80): every slice of the reference's recorded sweep, teacher-forced.
+    A free-running sweep cannot be compared here (a 1e-15 perturbation flips a decision at proposal ~2400),
+    so each slice starts from the pre-slice G of the reference's own trajectory - replayed by the oracle, which
+    tests/test_oracle_golden.py pins bit for bit on this very fixture - and its 64 ratios and decisions are compared with the
+    numbers the reference recorded, its G with the replay: all bit for bit (EXACT arithmetic)."""
+    g = golden("cfg3_ring64_sweep")
+    n, lt = g["field0"].shape
+    lamb = float(g["lamb"])
+    h = g["field0"].copy()
+    gu, gd = g["g0_up"].copy(), g["g0_dn"].copy()
+    left_reference_at = None          # the replay's wraps go through this host's BLAS: another OpenBLAS kernel may leave the trajectory
+    with _engine(g["exp_k"], lamb, lt, trace=True) as eng:
+        for step in range(lt):
+            l = lt - 1 - step
+            eng.set_field(h[None])
+            eng.set_g(np.stack([gu, gd])[None])
+            eng.slice(l, g["uniforms"][step][None])
+            acc, ratio = eng.get_trace()
+            out = eng.get_g()[0]
+            r, a = so.slice_proposals(gu, gd, h, l, lamb, g["uniforms"][step])
+            # the CUDA path against the NumPy restatement on the same inputs: always bit for bit
+            assert np.array_equal(acc[0, 0, 0], a), f"accept/reject differs at slice {l}"
+            assert np.array_equal(ratio[0, 0, 0], r), f"ratios differ at slice {l}"
+            assert np.array_equal(out[0], gu) and np.array_equal(out[1], gd), f"G differs after slice {l}"
+            assert np.array_equal(eng.get_field()[0], h)
+            # and, as long as the replay is on the recorded trajectory, against the reference's own numbers
+            if left_reference_at is None:
+                if np.array_equal(a, g["accs"][step]) and np.array_equal(r, g["ratios"][step]):
+                    if f"post{l}_up" in g:
+                        assert np.array_equal(gu, g[f"post{l}_up"]) and np.array_equal(gd, g[f"post{l}_dn"])
+                else:
+                    left_reference_at = l
+            if l > 0:
+                gu, gd = so.wrap(gu, gd, h, l, g["exp_k"], lamb)
+    if left_reference_at is None:
+        assert np.array_equal(h, g["field1"])
+        assert np.array_equal(gu, g["gf_up"]) and np.array_equal(gd, g["gf_dn"])
+    else:
+        # only legitimate on a host whose BLAS rounds the wrap differently from the fixture's: never before the first wrap,
+        # and the decisions of the slices that were on the trajectory have been compared with the reference's
+        assert left_reference_at < lt - 1, "slice L-1 needs no wrap: it must reproduce the reference bit for bit"
+
+
 # ------------------------------------------------------------------------------------------------
 # batch semantics
 # ------------------------------------------------------------------------------------------------

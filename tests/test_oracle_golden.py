@@ -168,3 +168,43 @@ def test_det_mode_golden(golden, name):
         assert _bitwise_or_close(ratios, g["ratios"][warm + s], 1e-10)
     assert np.array_equal(h, g["fields"][-1])
     assert _bitwise_or_close(gf, g["gf"], 1e-10)
+
+
+@pytest.mark.parametrize("l", [44, 10])
+def test_cfg4_mid_sweep_slices(golden, l):
+    """Slices 44 and 10 of the reference's own 16x16 sweep (make_golden.py: case_cfg4mid): wrap + proposals replayed from the
+    reference's G after slice l+1 reproduce its ratios, decisions and the recorded parts of G."""
+    g = golden("cfg4_16x16_mid")
+    lamb = float(g["lamb"])
+    h = g["field1"].copy()
+    h[:, :l + 1] = g["field0"][:, :l + 1]
+    gu, gd = so.wrap(g[f"in{l}_up"], g[f"in{l}_dn"], h, l + 1, g["exp_k"], lamb)
+    r, a = so.slice_proposals(gu, gd, h, l, lamb, g[f"uniforms{l}"])
+    assert np.array_equal(a, g[f"accs{l}"])
+    assert _bitwise_or_close(r, g[f"ratios{l}"], 1e-8)
+    assert np.array_equal(h[:, l], g["field1"][:, l])
+    for tag, mat in (("up", gu), ("dn", gd)):
+        assert _bitwise_or_close(mat[g["rows"], :], g[f"post{l}_{tag}_rows"], 1e-8)
+        assert _bitwise_or_close(mat[:, g["cols"]], g[f"post{l}_{tag}_cols"], 1e-8)
+        assert _bitwise_or_close(np.diag(mat), g[f"post{l}_{tag}_diag"], 1e-8)
+    assert (g[f"ratios{l}"] < 0).mean() > 0.3 and max(np.abs(g[f"in{l}_up"]).max(), np.abs(g[f"in{l}_dn"]).max()) > 1e2
+
+
+def test_cfg5_slices(golden):
+    """24x24 (N = 576, the reference's own lattice): slice 99 needs no BLAS - the replay must be bit-identical to the reference;
+    slice 98 follows the wrap."""
+    g = golden("cfg5_24x24_slices")
+    lamb = float(g["lamb"])
+    h = g["field0"].copy()
+    gu, gd = g["g0_up"].astype(np.float64), g["g0_dn"].astype(np.float64)
+    r, a = so.slice_proposals(gu, gd, h, 99, lamb, g["uniforms"][0])
+    assert np.array_equal(a, g["accs"][0]) and np.array_equal(r, g["ratios"][0])
+    for tag, mat in (("up", gu), ("dn", gd)):
+        assert np.array_equal(mat[g["rows"], :], g[f"post99_{tag}_rows"]) and np.array_equal(mat[:, g["cols"]], g[f"post99_{tag}_cols"])
+        assert np.array_equal(np.diag(mat), g[f"post99_{tag}_diag"])
+    gu, gd = so.wrap(gu, gd, h, 99, g["exp_k"], lamb)
+    r, a = so.slice_proposals(gu, gd, h, 98, lamb, g["uniforms"][1])
+    assert np.array_equal(a, g["accs"][1]) and _bitwise_or_close(r, g["ratios"][1], 1e-9)
+    assert np.array_equal(h, g["field1"])
+    for tag, mat in (("up", gu), ("dn", gd)):
+        assert _bitwise_or_close(mat[g["rows"], :], g[f"post98_{tag}_rows"], 1e-9)
