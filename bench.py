@@ -243,30 +243,42 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
+class _DeviceArray:
+    """A raw engine buffer (lqmc_device_ptr) as a torch tensor, through the CUDA array interface - no copy."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = dict(shape=tuple(shape), typestr=typestr, data=(int(ptr), False), version=3)
+
+
+def device_observables(eng, torch, dev):
+    """The path's final reduction input, built ON THE DEVICE from the engine's accumulators (no host staging): per-chain means
+    of G (2 N^2), of n_up / n_dn / n_up n_dn per site (3 N) and their squares (for the error bars over chains), and the chain
+    count - one f64 vector, summed over ranks by ONE all_reduce.  Reference analogue: the Pipe + `np.sum(gf_data, 0) / procs`
+    of multiprocessing.py:265-267 (which has no error bars)."""
+    c, n = eng.n_chains, eng.n_sites
+    g_sum = torch.as_tensor(_DeviceArray(eng.device_ptr(2)[0], (c, 2 * n * n), "<f8"), device=dev)
+    obs = torch.as_tensor(_DeviceArray(eng.device_ptr(3)[0], (c, 3 * n), "<f8"), device=dev)
+    n_meas = torch.as_tensor(_DeviceArray(eng.device_ptr(4)[0], (c,), "<i8"), device=dev)
+    w = n_meas.clamp(min=1).to(torch.float64)[:, None]
+    g_mean = g_sum / w
+    o_mean = obs / w
+    return torch.cat([g_mean.sum(0), o_mean.sum(0), (o_mean * o_mean).sum(0),
+                      torch.tensor([float(c)], dtype=torch.float64, device=dev)])
+
+
+def measure_workload(torch, dist, dev, rank, world, local, name, mode, stab, arith, chains, steps, warmup, seed, clocks=True):
+    """Device-resident throughput of one workload on this rank's GPU: `warmup` untimed sweeps, then exactly `steps` sweeps, each
+    its own launch, timed with CUDA events on the launching stream; max over ranks.  Returns the engine (still alive) and a dict."""
     from latticeqmc_b200 import SweepEngine
-
-    rank, world, local = dist_setup(args.gpus)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
-    torch.cuda.set_device(local)
-    dev = torch.device(f"cuda:{local}")
-
-    physics = args.mode == "physics"
-    w = build_workload(args.workload, mu=0.0 if physics else None)
-    n, lt = w["n"], w["lt"]
-    chains = args.chains or w["chains"]
     from latticeqmc_b200.workloads import synthetic_fields
+    physics = mode == "physics"
+    w = build_workload(name, mu=0.0 if physics else None)
+    n, lt = w["n"], w["lt"]
     fields = synthetic_fields(n, lt, chains, seed0=rank * chains)
     eng = SweepEngine(w["exp_k"], w["lamb"], lt, n_chains=chains, exp_k_inv=w["exp_k_inv"], device=local,
-                      mode=args.mode, arith=args.arith, chain_offset=rank * chains,
-                      stab_every=args.stab if physics else 0)
+                      mode=mode, arith=arith, chain_offset=rank * chains, stab_every=stab if physics else 0)
     eng.set_field(fields)
-    stream = torch.cuda.Stream(dev)          # a real (non-default) stream: its handle goes to the C ABI, events see it
-    torch.cuda.set_stream(stream)
+    stream = torch.cuda.current_stream(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
 
     def barrier():
@@ -276,22 +288,21 @@ def run_ours(args):
         torch.cuda.synchronize(dev)
 
     def device_step():
-        eng.sweep_async(1, 0, seed=args.seed, measure=True, stream=stream.cuda_stream)
+        eng.sweep_async(1, 0, seed=seed, measure=True, stream=stream.cuda_stream)
 
-    # ---- device-resident throughput ----
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         device_step()
     barrier()
     eng.reset_measurements()
     launches0 = eng.info()["launches"]
-    sampler = ClockSampler(local)
-    if rank == 0:
+    sampler = ClockSampler(local) if (clocks and rank == 0) else None
+    if sampler:
         sampler.start()
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
     barrier()
     t_wall = time.perf_counter()
-    for k in range(args.steps):
+    for k in range(steps):
         flush.zero_()                       # L2 flush between timed iterations (not timed)
         starts[k].record(stream)
         device_step()
@@ -304,15 +315,92 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     total_ms = float(total_ms.item())
-    m = eng.get_measurements()
-    accept = float(m["n_accepted"].sum()) / (chains * args.steps * n * lt)
+    counts = torch.tensor([float(eng.get_measurements()["n_accepted"].sum()), float(chains)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(counts)
+    accepted_total, chains_total = float(counts[0].item()), int(round(float(counts[1].item())))
+    accept = accepted_total / max(1, chains_total * steps * n * lt)
+    del flush
+    res = dict(w=w, n=n, lt=lt, fields=fields, chains=chains, chains_total=chains_total, total_ms=total_ms, ms_per_step=total_ms / steps,
+               accept=accept, launches=int(launches), wall_s=t_wall, clocks=sampler.stop() if sampler else None,
+               family=eng.info()["family"], physics=physics, stab=stab if physics else 0, barrier=barrier)
+    res["value"] = chains_total * n * lt * steps / (total_ms * 1e-3)
+    res["flops_per_step_all_ranks"] = (flops_per_sweep_physics(n, lt, accept, stab) if physics and stab
+                                       else flops_per_sweep(n, lt, accept)) * chains_total
+    return eng, res
+
+
+def roofline_block(res, world, peaks, name, mode):
+    """FP64-pipe roofline of the sweep kernel: ALGORITHMIC flops of the step / live event time / GPUs, against the measured DFMA
+    peak of this pool's B200 (tools/fp64_peak.cu; MEASURED_PEAKS.json has no FP64 figure) and the 40 TFLOP/s datasheet figure."""
+    per_gpu_flops = res["flops_per_step_all_ranks"] / world
+    achieved = per_gpu_flops / (res["ms_per_step"] * 1e-3) * 1e-12
+    parity = mode == "parity"
+    traffic = load_traffic(name) if parity else None
+    return dict(bound="tensor", pipe="FP64 (DFMA and DMMA issue to the same pipe on sm_100a; no tcgen05 f64 kind)",
+                achieved=achieved, peak=peaks["fp64_tflops"], unit="TFLOP/s", frac=achieved / peaks["fp64_tflops"],
+                frac_vs_datasheet=achieved / 40.0, datasheet_peak=40.0,
+                traffic=traffic,
+                traffic_source=("profiles/traffic.json: dram__bytes_read + dram__bytes_write of one launch from the committed ncu --set full "
+                                "capture of this workload (static, not re-measured in this run)") if traffic else None,
+                peak_source=peaks["source"],
+                kernel="sweep_reg_kernel" if res["family"] == "reg" else "sweep_l2_kernel",
+                flops_per_launch=per_gpu_flops if not (res["physics"] and res["stab"]) else None,
+                flops_per_step_per_gpu=per_gpu_flops,
+                hbm=hbm_leg(name, res["ms_per_step"], peaks) if parity else None)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    rank, world, local = dist_setup(args.gpus)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    stream = torch.cuda.Stream(dev)          # a real (non-default) stream: its handle goes to the C ABI, events see it
+    torch.cuda.set_stream(stream)
+    peaks = load_peaks()
+
+    physics = args.mode == "physics"
+    base_chains = args.chains or WORKLOADS[args.workload][5]
+    if args.scaling == "strong":
+        # a FIXED job (the workload's chain count) split over the ranks, like the reference's ParallelProcessManager splits a
+        # fixed number of sweeps over its processes (multiprocessing.py:260-267); remainder chains go to the low ranks
+        chains = base_chains // world + (1 if rank < base_chains % world else 0)
+    else:
+        chains = base_chains
+    eng, res = measure_workload(torch, dist, dev, rank, world, local, args.workload, args.mode, args.stab, args.arith, chains,
+                                args.steps, args.warmup, args.seed)
+    w, n, lt, fields, barrier = res["w"], res["n"], res["lt"], res["fields"], res["barrier"]
+    accept = res["accept"]
+
+    # ---- the only collective of the path: observables + error-bar sums, from the device accumulators, after the sweeps ----
+    torch.cuda.synchronize(dev)
+    a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    a.record(stream)
+    vec = device_observables(eng, torch, dev)
+    b.record(stream)
+    if world > 1:
+        dist.all_reduce(vec)
+    c.record(stream)
+    torch.cuda.synchronize(dev)
+    reduce_build_ms, reduce_ms = a.elapsed_time(b), (b.elapsed_time(c) if world > 1 else None)
+    n_chains_all = float(vec[-1].item())
+    o_mean = (vec[2 * n * n:2 * n * n + 3 * n] / n_chains_all).cpu().numpy().reshape(3, n)
+    o_sq = (vec[2 * n * n + 3 * n:2 * n * n + 6 * n] / n_chains_all).cpu().numpy().reshape(3, n)
+    o_err = np.sqrt(np.maximum(o_sq - o_mean ** 2, 0.0) / max(n_chains_all - 1, 1))
+    observables = dict(n_up=float(o_mean[0].mean()), n_dn=float(o_mean[1].mean()), docc=float(o_mean[2].mean()),
+                       docc_stderr_over_chains=float(np.sqrt((o_err[2] ** 2).mean() / n)),
+                       reduced_doubles=int(vec.numel()), chains=int(n_chains_all))
 
     # ---- end to end through the host-buffer API ----
     pin_field = torch.from_numpy(fields.copy()).pin_memory()
     pin_uni = torch.empty((chains, 1, lt, n), dtype=torch.float64).pin_memory()
     pin_uni.copy_(torch.from_numpy(np.random.RandomState(7 + rank).rand(chains, 1, lt, n)))
     f_np, u_np = pin_field.numpy(), pin_uni.numpy()
-
     pin_g = torch.empty((chains, 2, n, n), dtype=torch.float64).pin_memory()
     g_np = pin_g.numpy()
 
@@ -322,7 +410,7 @@ def run_ours(args):
         eng.get_field(out=f_np)                      # D2H: field, becomes the next step's input
         return eng.get_g(out=g_np)                   # D2H: (gf_up, gf_dn) of every chain, into pinned memory
 
-    for _ in range(max(1, args.warmup)):
+    for _ in range(max(1, min(args.warmup, 2))):
         host_step()
     barrier()
     t0 = time.perf_counter()
@@ -333,56 +421,70 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_s = float(e2e_s.item())
-    clocks = sampler.stop() if rank == 0 else None
-
-    # ---- the only collective of the path: observables, after the sweeps ----
-    reduce_ms = None
+    io = torch.tensor([float(fields.nbytes + pin_uni.numel() * 8), float(fields.nbytes + chains * 2 * n * n * 8)],
+                      dtype=torch.float64, device=dev)
     if world > 1:
-        gsum = torch.from_numpy(m["g_sum"].sum(0)).to(dev)
-        torch.cuda.synchronize(dev)
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(); dist.all_reduce(gsum); b.record(); torch.cuda.synchronize(dev)
-        reduce_ms = a.elapsed_time(b)
+        dist.all_reduce(io)
+    h2d_bytes, d2h_bytes = int(io[0].item()), int(io[1].item())
+    eng.close()
+    del pin_field, pin_uni, pin_g
+    torch.cuda.empty_cache()
+
+    # ---- the other BASELINE.json configurations, measured in the same run (short: they are context for the headline) ----
+    extra = {}
+    if args.configs and args.workload == "cfg4" and args.mode == "parity" and args.scaling == "weak":
+        plan = [("cfg2", "parity", 0, 3, 5), ("cfg3", "physics", 10, 3, 3), ("cfg5", "physics", 8, 1, 2)]
+        for name, mode, stab, wu, st in plan:
+            try:
+                e2, r2 = measure_workload(torch, dist, dev, rank, world, local, name, mode, stab, "exact", WORKLOADS[name][5], st, wu,
+                                          args.seed, clocks=True)
+                e2.close()
+                torch.cuda.empty_cache()
+                rf = roofline_block(r2, world, peaks, name, mode)
+                extra[name] = dict(description=WORKLOADS[name][6], mode=mode, stab_every=stab, arith="exact", chains_per_gpu=r2["chains"],
+                                   steps=st, warmup=wu, value=r2["value"], unit=UNIT, ms_per_step=r2["ms_per_step"],
+                                   accept_rate=r2["accept"], roofline_frac=rf["frac"], roofline_achieved_tflops=rf["achieved"],
+                                   gpu_launches=r2["launches"], clocks=r2["clocks"])
+            except Exception as exc:          # a context line must never take the headline down with it
+                extra[name] = dict(error=f"{type(exc).__name__}: {exc}")
 
     if rank == 0:
-        proposals_per_step = world * chains * n * lt
-        value = proposals_per_step * args.steps / (total_ms * 1e-3)
-        e2e_value = proposals_per_step * args.steps / e2e_s
-        flops = (flops_per_sweep_physics(n, lt, accept, args.stab) if physics and args.stab
-                 else flops_per_sweep(n, lt, accept)) * chains            # per step (one rank)
-        kernel_ms = total_ms / args.steps
-        peaks = load_peaks()
-        achieved = flops / (kernel_ms * 1e-3) * 1e-12
-        info = eng.info()
+        chains_total = res["chains_total"]
+        value = res["value"]
+        e2e_value = chains_total * n * lt * args.steps / e2e_s
         line = dict(
             metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
-            ms_per_step=kernel_ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
+            ms_per_step=res["ms_per_step"], higher_is_better=True, scaling=args.scaling, vs_baseline=None, dtype="f64", data="synthetic",
             config=dict(workload=args.workload, description=w["text"], n_sites=n, n_slices=lt, chains_per_gpu=chains,
-                        chains_total=world * chains, mode=args.mode, stab_every=args.stab if physics else 0,
+                        chains_total=chains_total, mode=args.mode, stab_every=args.stab if physics else 0,
                         arith=args.arith, rng="device philox4x32-10",
-                        kernel_family=info["family"], l2="flushed between timed steps (256 MiB memset, untimed)",
-                        parallelism=f"chains sharded over {world} GPU(s), no collective in the sweep"),
+                        kernel_family=res["family"], l2="flushed between timed steps (256 MiB memset, untimed)",
+                        parallelism=(f"{chains_total} chains sharded over {world} GPU(s) "
+                                     f"({'fixed total, split' if args.scaling == 'strong' else 'fixed per GPU'}), no collective in the sweep")),
             accept_rate=accept, accepted_flips_per_s=value * accept,
-            roofline=dict(bound="tensor", pipe="FP64 (DFMA and DMMA issue to the same pipe on sm_100a; no tcgen05 f64 kind)",
-                          achieved=achieved, peak=peaks["fp64_tflops"], unit="TFLOP/s", frac=achieved / peaks["fp64_tflops"],
-                          traffic=None if physics else load_traffic(args.workload), peak_source=peaks["source"],
-                          kernel="sweep_reg_kernel" if info["family"] == "reg" else "sweep_l2_kernel",
-                          flops_per_launch=flops, hbm=None if physics else hbm_leg(args.workload, kernel_ms, peaks)),
-            e2e=dict(value=e2e_value, unit=UNIT,
-                     h2d_bytes_per_step=int(world * (fields.nbytes + pin_uni.numel() * 8)),
-                     d2h_bytes_per_step=int(world * (fields.nbytes + chains * 2 * n * n * 8)),
+            roofline=roofline_block(res, world, peaks, args.workload, args.mode),
+            e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=d2h_bytes,
                      ms_per_step=1e3 * e2e_s / args.steps),
-            gpu_launches=int(launches), clocks=clocks, wall_s_timed_region=t_wall, observable_allreduce_ms=reduce_ms,
+            gpu_launches=res["launches"], clocks=res["clocks"], wall_s_timed_region=res["wall_s"],
+            observable_allreduce_ms=reduce_ms,
+            observable_reduction=dict(device_build_ms=reduce_build_ms, allreduce_ms=reduce_ms, doubles=observables["reduced_doubles"],
+                                      source="engine accumulators through lqmc_device_ptr (no host staging); G sums, per-site n_up / n_dn / "
+                                             "n_up n_dn sums and their squares over chains, chain count",
+                                      n_up=observables["n_up"], n_dn=observables["n_dn"], docc=observables["docc"],
+                                      docc_stderr_over_chains=observables["docc_stderr_over_chains"]),
         )
+        if extra:
+            line["configs"] = extra
         if not args.no_cpu and world == 1:
             base = cpu_baseline(args.workload, args.cpu_budget, literal=True)
             vec = cpu_baseline(args.workload, min(args.cpu_budget, 5.0), literal=False)
             base["vectorised_port_value"] = vec["value"]
+            base["calibration"] = ("tests/test_cpu_arm_calibration.py: seconds per proposal of this port within 15 % of the unmodified "
+                                   "reference's _update_step on BASELINE configs[1] (build container)")
             line["cpu_baseline"] = base
         else:
             line["cpu_baseline"] = None
         print(json.dumps(line))
-    eng.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -437,6 +539,10 @@ def main():
     ap.add_argument("--seed", type=int, default=20260101)
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: the workload's chain count on EVERY GPU; strong: that chain count in total, split over the GPUs")
+    ap.add_argument("--no-configs", dest="configs", action="store_false",
+                    help="skip the short in-run measurements of the other BASELINE.json configurations (cfg2, cfg3, cfg5)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

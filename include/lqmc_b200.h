@@ -119,6 +119,11 @@ int lqmc_sweep_submit(lqmc_engine* e, int n_sweeps, const double* uniforms, uint
 int lqmc_sweep_det(lqmc_engine* e, int n_sweeps, const double* uniforms, uint64_t seed, int measure);
 /* old_det of every chain after the last lqmc_sweep_det (what _update_step_det returns, lqmc.py:259): f64 [chain]. */
 int lqmc_get_det(lqmc_engine* e, double* det_old);
+/* The old_det the NEXT lqmc_sweep_det starts from.  `_update_step_det(old_det)` takes it as an argument and the reference's
+ * loops carry it from sweep to sweep (lqmc.py:236-259, 264-270): det_old = f64 [chain], or NULL to carry the value the
+ * previous lqmc_sweep_det left on the device (a loop split into several calls).  One-shot; without it a call starts from
+ * det(M_up(0)) det(M_dn(0)) of the current field, as the reference's loops do before their first sweep. */
+int lqmc_set_det(lqmc_engine* e, const double* det_old);
 
 /* Per-proposal record of the last lqmc_sweep / lqmc_slice call (needs LQMC_TRACE): what the
  * reference exposes as self.ratio / self.acc and logs through _debug (lqmc.py:217-232,316-317).

@@ -49,6 +49,7 @@ struct lqmc_engine {
   cudaStream_t stream = nullptr;       // non-blocking: every engine-side memset / copy below is issued ON it, never on the legacy stream
   cudaEvent_t foreignDone = nullptr;   // recorded on a caller-owned stream after lqmc_sweep_async queued work there
   bool foreignPending = false;
+  bool detCarried = false;             // the next lqmc_sweep_det starts from the old_det already on the device (lqmc_set_det)
   // device state
   double *dE = nullptr, *dEt = nullptr, *dEi = nullptr, *dEit = nullptr;
   int8_t* dField = nullptr;
@@ -883,7 +884,7 @@ int lqmc_sweep_det(lqmc_engine* e, int n_sweeps, const double* uniforms, uint64_
   // unmeasured: all sweeps in one launch
   const int per_launch = measure ? 1 : n_sweeps;
   for (int s0 = 0; s0 < n_sweeps; s0 += per_launch) {
-    p.n_sweeps = per_launch; p.buf_sweep0 = s0; p.sweep0 = e->sweep_counter + s0; p.init_det = (s0 == 0);
+    p.n_sweeps = per_launch; p.buf_sweep0 = s0; p.sweep0 = e->sweep_counter + s0; p.init_det = (s0 == 0) && !e->detCarried;
     lqmc::sweep_det_kernel<<<e->C, lqmc::DET_THREADS, smem, s>>>(p);
     CU(cudaGetLastError());
     e->launches += 1;
@@ -895,7 +896,22 @@ int lqmc_sweep_det(lqmc_engine* e, int n_sweeps, const double* uniforms, uint64_
     }
   }
   e->sweep_counter += n_sweeps;
+  e->detCarried = false;
   CU(cudaStreamSynchronize(s));
+  return LQMC_OK;
+}
+
+int lqmc_set_det(lqmc_engine* e, const double* det_old) {
+  if (!e) return fail(LQMC_ERR_INVALID, "engine is NULL");
+  CU(cudaSetDevice(e->device));
+  if (!det_old && !e->dDetOld) return fail(LQMC_ERR_INVALID, "no det-mode sweep has run on this engine: there is no old_det to carry");
+  if (!e->dDetOld) CU(cudaMalloc(&e->dDetOld, (size_t)e->C * sizeof(double)));
+  if (det_old) {
+    { int rc = order_after_foreign(e); if (rc) return rc; }
+    CU(cudaMemcpyAsync(e->dDetOld, det_old, (size_t)e->C * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+  }
+  e->detCarried = true;
   return LQMC_OK;
 }
 

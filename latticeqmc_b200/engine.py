@@ -24,7 +24,7 @@ EXPORTS = (
     "lqmc_get_trace", "lqmc_get_measurements", "lqmc_reset_measurements", "lqmc_device_ptr", "lqmc_info",
     "lqmc_set_sweep_counter", "lqmc_set_chain_offset", "lqmc_philox_uniforms", "lqmc_last_error",
     "lqmc_version", "lqmc_selftest_division", "lqmc_recompute_stable", "lqmc_set_stabilization",
-    "lqmc_set_measurements", "lqmc_sweep_det", "lqmc_get_det", "lqmc_sweep_submit",
+    "lqmc_set_measurements", "lqmc_sweep_det", "lqmc_get_det", "lqmc_set_det", "lqmc_sweep_submit",
 )
 
 
@@ -64,6 +64,7 @@ def load_library(path=None):
     lib.lqmc_sweep.argtypes = [vp, ctypes.c_int, vp, ctypes.c_uint64, ctypes.c_int]
     lib.lqmc_sweep_det.argtypes = [vp, ctypes.c_int, vp, ctypes.c_uint64, ctypes.c_int]
     lib.lqmc_get_det.argtypes = [vp, vp]
+    lib.lqmc_set_det.argtypes = [vp, vp]
     lib.lqmc_sweep_submit.argtypes = [vp, ctypes.c_int, vp, ctypes.c_uint64, ctypes.c_int]
     lib.lqmc_sweep_async.argtypes = [vp, ctypes.c_int, vp, ctypes.c_uint64, ctypes.c_int, vp]
     lib.lqmc_sync.argtypes = [vp]
@@ -147,6 +148,8 @@ class SweepEngine:
         self.n_chains = int(n_chains)
         self.mode, self.arith, self.trace = mode, arith, bool(trace)
         self.lamb = float(lamb)
+        import hashlib
+        self._model_hash = hashlib.sha256(exp_k.tobytes()).hexdigest()[:16]          # checkpoint compatibility check
         self.device = int(device)
         hs = hs_constants(self.lamb)
         dp = ctypes.POINTER(ctypes.c_double)
@@ -253,10 +256,18 @@ class SweepEngine:
         self._check(self._lib.lqmc_sweep(self._h, int(n_sweeps), ptr, int(seed), int(bool(measure))))
         self._last_trace_shape = (self.n_chains, int(n_sweeps), self.n_slices, self.n_sites)
 
-    def sweep_det(self, n_sweeps=1, uniforms=None, seed=0, measure=False):
+    def sweep_det(self, n_sweeps=1, uniforms=None, seed=0, measure=False, old_det=None):
         """`n_sweeps` x `LatticeQMC._update_step_det` (lqmc.py:236-259) as one of the reference's det-mode loops:
-        `old_det` from `get_m(0, +-1)` at the start of the call; `measure` adds `inv(get_m(0, +-1))` after every sweep
+        `old_det` from `get_m(0, +-1)` at the start of the call (`old_det=None`), a caller-supplied value per chain, or
+        `"carry"` = the value the previous call left on the device; `measure` adds `inv(get_m(0, +-1))` after every sweep
         (lqmc.py:293-297).  `uniforms` as in `sweep`.  N <= 64."""
+        if isinstance(old_det, str):
+            if old_det != "carry":
+                raise ValueError("old_det must be None, 'carry' or per-chain values")
+            self._check(self._lib.lqmc_set_det(self._h, None))
+        elif old_det is not None:
+            d = np.ascontiguousarray(np.broadcast_to(np.asarray(old_det, dtype=np.float64), (self.n_chains,)))
+            self._check(self._lib.lqmc_set_det(self._h, d.ctypes.data))
         ptr = None
         if uniforms is not None:
             u = np.ascontiguousarray(uniforms, dtype=np.float64).reshape(self.n_chains, n_sweeps, self.n_slices, self.n_sites)
@@ -326,27 +337,47 @@ class SweepEngine:
                                                     n_acc.ctypes.data))
 
     # -- checkpoint / resume -------------------------------------------------------------------
-    def save_checkpoint(self, path, seed=0):
+    @staticmethod
+    def _checkpoint_path(path):
+        path = str(path)
+        return path if path.endswith(".npz") else path + ".npz"          # np.savez appends the suffix: do the same on load
+
+    def save_checkpoint(self, path, seed=0, numpy_rng=False):
         """Markov state of every chain as one `.npz`: HS field (int8), global sweep counter, chain offset, RNG seed and
-        the measurement accumulators.  With the device Philox stream (a pure function of seed / chain / sweep /
-        proposal) this is everything: G is rebuilt from the field at the next sweep start."""
+        the measurement accumulators, plus what identifies the simulation (lamb, a hash of exp_k, mode, arithmetic,
+        stab_every).  With the device Philox stream (a pure function of seed / chain / sweep / proposal) this is
+        everything: G is rebuilt from the field at the next sweep start.  `numpy_rng=True` also stores the state of NumPy's
+        global MT19937 stream, which is what feeds the sweeps in the drop-in `rng="numpy"` mode."""
         m = self.get_measurements()
         info = self.info()
-        np.savez_compressed(path, field=self.get_field(), sweep_counter=np.int64(info["sweep_counter"]),
+        extra = {}
+        if numpy_rng:
+            st = np.random.get_state()
+            extra = dict(np_rng_keys=st[1], np_rng_pos=np.int64(st[2]), np_rng_has_gauss=np.int64(st[3]), np_rng_gauss=np.float64(st[4]))
+        np.savez_compressed(self._checkpoint_path(path), field=self.get_field(), sweep_counter=np.int64(info["sweep_counter"]),
                             chain_offset=np.int64(self._chain_offset), seed=np.uint64(seed), n_sites=self.n_sites,
-                            n_slices=self.n_slices, n_chains=self.n_chains, mode=self.mode, stab_every=self.stab_every,
-                            g_sum=m["g_sum"], obs_sum=m["obs_sum"], n_meas=m["n_meas"], n_accepted=m["n_accepted"])
+                            n_slices=self.n_slices, n_chains=self.n_chains, mode=self.mode, arith=self.arith,
+                            stab_every=self.stab_every, lamb=np.float64(self.lamb), model_hash=self._model_hash,
+                            g_sum=m["g_sum"], obs_sum=m["obs_sum"], n_meas=m["n_meas"], n_accepted=m["n_accepted"], **extra)
 
     def load_checkpoint(self, path):
-        """Restore a `save_checkpoint` file into this engine (same lattice size, slices and chain count).  Returns the
-        RNG seed stored with it."""
-        with np.load(path) as z:
+        """Restore a `save_checkpoint` file into this engine.  The file must come from the same simulation: lattice size,
+        slices, chain count, lamb, exp_k, mode, arithmetic and stab_every are checked (ValueError otherwise).  Restores
+        NumPy's global stream if it was stored.  Returns the RNG seed stored with it."""
+        with np.load(self._checkpoint_path(path)) as z:
             if (int(z["n_sites"]), int(z["n_slices"]), int(z["n_chains"])) != (self.n_sites, self.n_slices, self.n_chains):
                 raise ValueError("checkpoint does not match this engine's (n_sites, n_slices, n_chains)")
+            if "model_hash" in z.files:           # files written before these fields existed carry no identity to check
+                same = (str(z["model_hash"]) == self._model_hash and float(z["lamb"]) == self.lamb and str(z["mode"]) == self.mode
+                        and str(z["arith"]) == self.arith and int(z["stab_every"]) == self.stab_every)
+                if not same:
+                    raise ValueError("checkpoint was written by a different simulation (exp_k / lamb / mode / arith / stab_every differ)")
             self.set_field(z["field"])
             self.set_sweep_counter(int(z["sweep_counter"]))
             self.set_chain_offset(int(z["chain_offset"]))
             self.set_measurements(dict(g_sum=z["g_sum"], obs_sum=z["obs_sum"], n_meas=z["n_meas"], n_accepted=z["n_accepted"]))
+            if "np_rng_keys" in z.files:
+                np.random.set_state(("MT19937", z["np_rng_keys"], int(z["np_rng_pos"]), int(z["np_rng_has_gauss"]), float(z["np_rng_gauss"])))
             return int(z["seed"])
 
     def device_ptr(self, which):

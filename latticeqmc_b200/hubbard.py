@@ -4,8 +4,8 @@ Host-side input producer for the hot path; API mirrors the reference ``lqmc/hubb
 (``HubbardModel(u, t, mu)``, ``set_params``, ``param_str``, ``n_sites``, ``build``, ``build_square``,
 ``ham_kinetic``).  Convention kept from the reference (``hubbard.py:30,99-100``): ``mu`` defaults to
 ``u/2`` and the diagonal of ``K`` is ``-mu``; together with the reference's HS decoupling this
-simulates ``mu_true = mu + u/2`` - the engine's physics mode takes an explicit
-``half_filling`` switch instead of silently changing this matrix.
+simulates ``mu_true = mu + u/2``.  Nothing here or in the engine corrects that silently: true
+half filling in physics mode is requested by building the model with ``mu=0`` (``tests/test_gpu_physics.py``).
 """
 import numpy as np
 

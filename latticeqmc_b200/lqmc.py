@@ -34,7 +34,7 @@ _UNIFORM_CHUNK_BYTES = 256 << 20
 class LatticeQMC:
 
     def __init__(self, model, beta, time_steps, warmup=300, sweeps=2000, det_mode=False, log_lvl=DEBUG,
-                 *, mode="parity", arith="exact", rng="numpy", seed=0, device=0, trace=True, stab_every=0):
+                 *, mode="parity", arith="exact", rng="numpy", seed=0, device=0, trace=None, stab_every=0, chain_offset=0):
         if log_lvl is not None:
             self.logger = get_logger()
             self.logger.setLevel(log_lvl)
@@ -63,7 +63,17 @@ class LatticeQMC:
         self.exp_k = None
 
         # engine options (additions; reference defaults unchanged)
-        self.mode, self.arith, self.rng, self.seed, self.device, self.trace = mode, arith, rng, seed, device, trace
+        # trace=True keeps the per-proposal (ratio, acc) of the last call in `last_trace` and refreshes `self.ratio` / `self.acc`
+        # (what the reference sets per proposal and `_debug` logs, lqmc.py:217-232,316-317).  It costs 9 bytes per proposal on the
+        # device, copied back after every call, so the default (None) turns it on only while a whole loop's record stays under
+        # 16 MB - small drop-in runs behave like the reference, production-size runs pay nothing.  chain_offset keys the device
+        # Philox stream (rng="philox"): distinct jobs of a scan must not share one (seed, chain, sweep) stream.
+        if trace is None:
+            trace = 9 * self.n_sites * time_steps * max(warmup, sweeps, 1) <= (16 << 20)
+        self.mode, self.arith, self.rng, self.seed, self.device, self.trace = mode, arith, rng, seed, device, bool(trace)
+        self.chain_offset = chain_offset
+        self.last_trace = None
+        self._sweeps_done = 0               # Philox sweep counter carried across engine re-creation (set_beta)
         self.stab_every = stab_every        # physics mode: QR/UDV-stabilised G every this many slices (0 = off)
         self._engine = None
 
@@ -122,7 +132,9 @@ class LatticeQMC:
         if self._engine is None:
             self._engine = SweepEngine(self.exp_k, self.lamb, self.time_steps, n_chains=1, exp_k_inv=self.exp_k_inv,
                                        device=self.device, mode=self.mode, arith=self.arith, trace=self.trace,
-                                       stab_every=self.stab_every)
+                                       stab_every=self.stab_every, chain_offset=self.chain_offset)
+            if self._sweeps_done:
+                self._engine.set_sweep_counter(self._sweeps_done)       # a new beta continues the stream, it does not replay it
         return self._engine
 
     # ------------------------------------------------------------------ inspection helpers (host, O(N^2))
@@ -166,7 +178,7 @@ class LatticeQMC:
             return None
         return np.random.rand(n_sweeps * self.time_steps * self.n_sites).reshape(1, n_sweeps, self.time_steps, self.n_sites)
 
-    def _run_sweeps(self, n_sweeps, measure, det=False):
+    def _run_sweeps(self, n_sweeps, measure, det=False, old_det=None):
         eng = self.engine
         eng.set_field(self.config.config[None])
         per_sweep = self.time_steps * self.n_sites * 8
@@ -174,8 +186,14 @@ class LatticeQMC:
         done = 0
         while done < n_sweeps:
             k = min(chunk, n_sweeps - done)
-            (eng.sweep_det if det else eng.sweep)(k, self._draw_uniforms(k), seed=self.seed, measure=measure)
+            if det:
+                # the first chunk starts from the caller's old_det (or the field's); later chunks carry the device value on
+                eng.sweep_det(k, self._draw_uniforms(k), seed=self.seed, measure=measure,
+                              old_det=(old_det if done == 0 else "carry"))
+            else:
+                eng.sweep(k, self._draw_uniforms(k), seed=self.seed, measure=measure)
             done += k
+        self._sweeps_done += n_sweeps
         self.config.config[...] = eng.get_field()[0]
         if self.trace and n_sweeps:
             acc, ratio = eng.get_trace()
@@ -219,10 +237,11 @@ class LatticeQMC:
 
     # ------------------------------------------------------------------ det mode (lqmc.py:236-299)
     def _update_step_det(self, old_det=None):
-        """One det-mode sweep on the device (lqmc.py:236-259); returns the new `old_det`.  The engine starts the call
-        from `det(get_m(0, +1)) * det(get_m(0, -1))` of the current field, which is what the reference's loops pass
-        in for their first sweep; `old_det` is accepted for signature compatibility."""
-        self._run_sweeps(1, measure=False, det=True)
+        """One det-mode sweep on the device (lqmc.py:236-259); returns the new `old_det`.  `old_det` is the value the ratios
+        of this sweep are taken against - the reference carries it from sweep to sweep (lqmc.py:264-270); `None` starts from
+        `det(get_m(0, +1)) * det(get_m(0, -1))` of the current field (what the reference's loops compute before their first
+        sweep)."""
+        self._run_sweeps(1, measure=False, det=True, old_det=old_det)
         return float(self.engine.get_det()[0])
 
     def warmup_loop_det(self):

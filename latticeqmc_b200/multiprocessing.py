@@ -64,6 +64,9 @@ class LqmcProcess(LatticeQMC):
 
     def __init__(self, i, iters, pipe, *args, seed=None, **kwargs):
         kwargs.pop("log_lvl", None)
+        # device Philox streams are keyed by (seed, chain offset, sweep): every job slot gets its own offset, or all points of
+        # a scan would consume the very same uniforms and their statistical errors would be fully correlated
+        kwargs.setdefault("chain_offset", i)
         super().__init__(*args, **kwargs, log_lvl=None)
         self.idx = i
         self.iters = iters

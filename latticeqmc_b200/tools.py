@@ -7,7 +7,7 @@ G(tau), ``exact.py:27-54``) and back the U=0 parity test.
 
 Note: ``local_moment`` factorises <n_up n_dn> from the *averaged* G, as the
 reference does (``tools.py:107-109``).  The correct per-configuration estimator is accumulated
-on the device; see ``SweepEngine.get_observables``.
+on the device: ``SweepEngine.get_measurements()['obs_sum']`` and ``multiprocessing.chain_statistics``.
 """
 import os
 

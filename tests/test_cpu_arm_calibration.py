@@ -1,0 +1,94 @@
+"""`bench.py`'s CPU arm times a PORT of the reference's interpreted loop (`kind: "port"`, the reference itself is Python under
+/root/reference and does not travel to the GPU box).  This test makes the port a measured stand-in: in the build container it runs
+the UNMODIFIED reference `LatticeQMC._update_step` (lqmc.py:301-347) on BASELINE configs[1] (8x8, U=4, beta=4, L=40), stops it
+after a few dozen proposals, and requires the port's seconds-per-proposal on the very same state to agree within 15 %."""
+import os
+import sys
+import time
+import types
+
+import numpy as np
+import pytest
+
+REFERENCE = "/root/reference"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _import_reference():
+    for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.collections", "mpl_toolkits", "mpl_toolkits.axes_grid1"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["matplotlib.collections"].LineCollection = object
+    sys.modules["mpl_toolkits.axes_grid1"].make_axes_locatable = lambda *a, **k: None
+    saved_path, saved_mod = list(sys.path), sys.modules.pop("lqmc", None)
+    saved_sub = {k: sys.modules.pop(k) for k in list(sys.modules) if k.startswith("lqmc.")}
+    sys.path[:] = [REFERENCE] + [p for p in sys.path if os.path.abspath(p or ".") != ROOT]
+    try:
+        import lqmc as ref
+        assert os.path.abspath(ref.__file__).startswith(REFERENCE)
+        return ref
+    finally:
+        # leave `lqmc` unresolved for whoever imports it next (this repo's shim or the reference), and restore the path
+        for k in [k for k in sys.modules if k == "lqmc" or k.startswith("lqmc.")]:
+            sys.modules.pop(k)
+        sys.path[:] = saved_path
+        if saved_mod is not None:
+            sys.modules["lqmc"] = saved_mod
+        sys.modules.update(saved_sub)
+
+
+class _Stop(Exception):
+    pass
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="the reference exists in the build container only")
+def test_port_seconds_per_proposal_match_the_unmodified_reference():
+    import bench
+    from oracle import sweep_oracle as so
+    ref = _import_reference()
+    n_props = 40
+    assert n_props + 1 <= 64
+    ratios, last = [], {}
+    for attempt in range(5):                       # median of up to five back-to-back pairs: the container's cores are shared
+        model = ref.HubbardModel(u=4, t=1)
+        model.build_square(8)
+        np.random.seed(7)
+        solver = ref.LatticeQMC(model, 4.0, 40, warmup=0, sweeps=0, log_lvl=None)
+        n, lt = solver.n_sites, solver.time_steps
+        field0 = solver.config.config.copy()
+        state = np.random.get_state()
+        uniforms = np.random.rand(n_props + 1)
+        np.random.set_state(state)
+        marks = []
+
+        def hook(i, l):
+            marks.append(time.perf_counter())
+            if len(marks) == n_props + 1:
+                raise _Stop
+
+        # instance-level replacement of the per-proposal log hook (lqmc.py:335): the reference's own computes a field mean and
+        # variance per proposal even with logging off; the port does not log, so neither side pays for it here
+        solver._debug = hook
+        try:
+            solver._update_step()
+        except _Stop:
+            pass
+        t_ref = (marks[-1] - marks[0]) / n_props              # proposals 1 .. n_props (the first mark follows proposal 0)
+        accepted_ref = int((solver.config.config != field0).sum())
+
+        # the port on the same field, the same sweep-start G and the same uniforms
+        h = field0.copy()
+        gu, gd = so.sweep_start_g(h, solver.exp_k, solver.lamb)
+        bench._one_proposal(so, gu, gd, h, 0, lt - 1, solver.lamb, uniforms[0])
+        t0 = time.perf_counter()
+        for i in range(1, n_props + 1):
+            bench._one_proposal(so, gu, gd, h, i, lt - 1, solver.lamb, uniforms[i])
+        t_port = (time.perf_counter() - t0) / n_props
+        assert np.array_equal(h, solver.config.config)           # same decisions on the same n_props + 1 proposals
+        ratios.append(t_port / t_ref)
+        last = dict(ref=t_ref, port=t_port)
+        if len(ratios) >= 3 and abs(float(np.median(ratios)) - 1) <= 0.10:
+            break
+    ratio = float(np.median(ratios))
+    print(f"reference {last['ref'] * 1e3:.3f} ms / proposal, port {last['port'] * 1e3:.3f} ms / proposal; port / reference per pair: "
+          f"{[round(r, 3) for r in ratios]}, median {ratio:.3f}")
+    assert abs(ratio - 1) <= 0.15, ratios

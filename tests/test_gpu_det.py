@@ -88,7 +88,7 @@ def test_det_mode_drop_in_replays_reference_run(golden):
     model = HubbardModel(u=4, t=1)
     model.build_square(2)
     np.random.seed(61)
-    solver = LatticeQMC(model, 2.0, 20, warmup=int(g["warm"]), sweeps=int(g["meas"]), det_mode=True, log_lvl=None)
+    solver = LatticeQMC(model, 2.0, 20, warmup=int(g["warm"]), sweeps=int(g["meas"]), det_mode=True, log_lvl=None, trace=True)
     assert np.array_equal(solver.config.config, g["field0"])
     gf = solver.run_lqmc()
     assert np.array_equal(solver.config.config, g["fields"][-1])
@@ -119,6 +119,37 @@ def test_det_mode_matches_exact_diagonalisation():
     tol = 5 * err + 0.01                                   # statistics + Trotter error O(U t dtau^2)
     assert abs(mean[0] - exact["n_up"]) < tol[0] and abs(mean[1] - exact["n_dn"]) < tol[1]
     assert abs(mean[2] - exact["docc"]) < tol[2]
+
+
+def test_old_det_is_carried_between_calls(golden):
+    """`_update_step_det(old_det)` takes the determinant the ratios are measured against as an argument and the reference's loops
+    carry it from sweep to sweep (lqmc.py:236-259, 264-270).  A loop split into several engine calls must therefore continue from
+    the carried value, not from a re-derived one: 3 sweeps in one call == 1 + 2 sweeps with `old_det="carry"` == the same with the
+    value read back and passed in explicitly - decisions, ratios, field and final old_det bit for bit."""
+    g = golden("det_2x2")
+    n, lt = g["field0"].shape
+    uni = g["uniforms"][None, :3]
+    runs = []
+    for how in ("one", "carry", "explicit"):
+        with _engine(g["exp_k"], float(g["lamb"]), lt, trace=True) as eng:
+            eng.set_field(g["field0"][None])
+            if how == "one":
+                eng.sweep_det(3, uni)
+                acc, ratio = eng.get_trace()
+            else:
+                eng.sweep_det(1, uni[:, :1])
+                a1, r1 = eng.get_trace()
+                eng.sweep_det(2, uni[:, 1:], old_det=("carry" if how == "carry" else eng.get_det()))
+                a2, r2 = eng.get_trace()
+                acc, ratio = np.concatenate([a1, a2], axis=1), np.concatenate([r1, r2], axis=1)
+            runs.append((acc.copy(), ratio.copy(), eng.get_field().copy(), eng.get_det().copy()))
+    for other in runs[1:]:
+        for x, y in zip(runs[0], other):
+            assert np.array_equal(x, y)
+    assert np.array_equal(runs[0][0][0], g["accs"][:3])
+    with _engine(g["exp_k"], float(g["lamb"]), lt) as eng:
+        with pytest.raises(Exception):
+            eng.sweep_det(1, uni[:, :1], old_det="carry")            # nothing to carry yet
 
 
 def test_det_mode_rejects_large_lattices():

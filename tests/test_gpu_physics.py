@@ -241,6 +241,34 @@ def test_checkpoint_resume_repeats_the_uninterrupted_run(tmp_path):
         assert np.array_equal(m[key], ref_m[key]), key
 
 
+def test_checkpoint_identity_is_checked_and_suffix_is_optional(tmp_path):
+    """A checkpoint of another simulation (different beta -> lamb / exp_k, different arithmetic) must not load silently, and
+    `save('ckpt')` / `load('ckpt')` agree on the file name (np.savez appends `.npz`).  With `numpy_rng=True` the host MT19937
+    stream - the one the drop-in `rng="numpy"` mode consumes - is stored and restored."""
+    from latticeqmc_b200 import SweepEngine
+    ham, lamb, exp_k, exp_k_inv = _setup(4.0, 2.0, 20)
+    n, lt = 4, 20
+    fields = np.stack([so.initial_field(n, lt, 70 + c) for c in range(2)])
+    stem = str(tmp_path / "ckpt")                                   # no suffix
+    with SweepEngine(exp_k, lamb, lt, n_chains=2, exp_k_inv=exp_k_inv, mode="physics") as eng:
+        eng.set_field(fields)
+        eng.sweep(2, None, seed=1, measure=True)
+        np.random.seed(99)
+        np.random.rand(7)
+        eng.save_checkpoint(stem, seed=1, numpy_rng=True)
+        expect_next = np.random.rand(3)
+        np.random.seed(5)                                           # disturb the stream
+        assert eng.load_checkpoint(stem) == 1
+        assert np.array_equal(np.random.rand(3), expect_next)
+    ham2, lamb2, exp_k2, exp_k_inv2 = _setup(4.0, 3.0, 20)            # other beta
+    with SweepEngine(exp_k2, lamb2, lt, n_chains=2, exp_k_inv=exp_k_inv2, mode="physics") as eng:
+        with pytest.raises(ValueError):
+            eng.load_checkpoint(stem)
+    with SweepEngine(exp_k, lamb, lt, n_chains=2, exp_k_inv=exp_k_inv, mode="physics", arith="fma") as eng:
+        with pytest.raises(ValueError):
+            eng.load_checkpoint(stem + ".npz")
+
+
 def test_chain_statistics_on_device_accumulators():
     """Error bars from `chain_statistics` on a real run: ED values inside mean +- 4 sigma + Trotter error."""
     from latticeqmc_b200 import SweepEngine

@@ -88,3 +88,18 @@ def test_chain_statistics_error_bars():
     # chains without measurements are ignored
     m["n_meas"][:10] = 0
     assert chain_statistics(m)["n_chains"] == chains - 10
+
+
+def test_scan_jobs_get_distinct_philox_streams():
+    """Every job slot of a process manager keys the device Philox stream with its own chain offset (all points of a
+    beta scan used to consume identical uniforms).  Host-side check: no engine is created."""
+    from latticeqmc_b200 import HubbardModel
+    from latticeqmc_b200.multiprocessing import LqmcProcess
+    model = HubbardModel(u=4, t=1)
+    model.build_square(2)
+    procs = [LqmcProcess(i, None, None, model, 2.0, 20, warmup=0, sweeps=0, rng="philox") for i in range(4)]
+    assert [p.chain_offset for p in procs] == [0, 1, 2, 3]
+    assert LqmcProcess(2, None, None, model, 2.0, 20, warmup=0, sweeps=0, chain_offset=17).chain_offset == 17
+    assert procs[0].last_trace is None
+    big = LqmcProcess(0, None, None, model, 2.0, 20, warmup=0, sweeps=10**6)
+    assert procs[0].trace is True and big.trace is False          # per-proposal record only while it stays small
