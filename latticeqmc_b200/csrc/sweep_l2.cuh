@@ -27,6 +27,7 @@
 // every phase here is the FP64 pipe peak; tensor-core fragments buy operand traffic (one double per 8 FMAs), not flops.
 #pragma once
 #include <type_traits>
+#include <cuda.h>                 // CUtensorMap (types and enums only: the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cuda_runtime.h>
 #include <cuda_pipeline_primitives.h>
 #include <stdint.h>
@@ -37,20 +38,19 @@
 
 namespace lqmc {
 
-struct L2Workspace {
-  double* T = nullptr;      // [chain][2][NP][NP] second matrix buffer (two-GEMM wrap, running product)
-  int kd = 0;               // delay depth the shared-memory budget allows
-  int tmem_mode = 0;        // tensor-memory slice path that fits the shared-memory region: 0 none, 1 NP <= 256, 2 384 < NP <= 512, 3 512 < NP <= 768
-  size_t smem = 0;          // dynamic shared memory per CTA
-};
 
 constexpr int L2_THREADS = 256;
 constexpr int L2_BM = 64, L2_BN = 128, L2_BK = 16;     // block tile and k-panel depth
 constexpr int L2_GY = 16, L2_GX = 16;                  // thread grid inside a block tile: 4 x 8 per thread
 #ifndef LQMC_L2_STAGING_TMA
-#define LQMC_L2_STAGING_TMA 0                          // 1: cp.async.bulk rows + mbarrier ring; 0: LDGSTS (cp.async) ring
+#define LQMC_L2_STAGING_TMA 1                          // 1: cp.async.bulk.tensor (tensor maps, 128-byte swizzle) + full / empty mbarrier ring; 0: LDGSTS (cp.async) ring
 #endif
-constexpr int L2_STAGES = 3;                           // operand-panel ring depth
+constexpr int L2_STAGES = 3;                           // operand-panel ring depth of the LDGSTS variant
+constexpr int L2_TMA_STAGES = 4;                       // ... of the TMA variant: 4 x (8 KB + 16 KB) dense, swizzled panels
+constexpr int L2_TMA_SUB = 16 * 16 * 8;                // one TMA box: 16 k-rows x 16 doubles (128-byte rows, the swizzle span) = 2 KB
+constexpr size_t L2_GEMM_DOUBLES_LDGSTS = (size_t)3 * 16 * (64 + 128 + 8);
+constexpr size_t L2_GEMM_DOUBLES_TMA = (size_t)4 * 16 * (64 + 128);
+constexpr size_t L2_GEMM_DOUBLES = L2_GEMM_DOUBLES_TMA > L2_GEMM_DOUBLES_LDGSTS ? L2_GEMM_DOUBLES_TMA : L2_GEMM_DOUBLES_LDGSTS;   // operand-stage region (aliases U / W)
 constexpr int L2_MAXQ = 4;                             // indices per thread in the vector phases (NP <= 1024)
 #ifndef LQMC_L2_KDT
 #define LQMC_L2_KDT 24
@@ -65,15 +65,29 @@ constexpr int L2_PUB = 4;                              // sites after a flip who
 // multiple of 128 would pad to 640 - (640/576)^3 = 1.37 x the GEMM work (ncu on the cfg5 wrap at NP = 640: DMMA pipe 80 % busy
 // at 21.5 algorithmic TFLOP/s).  The TMA staging variant copies whole 128-column rows and keeps the multiple of 128.
 inline int l2_padded_size(int n_sites) {
-#if LQMC_L2_STAGING_TMA
-  const int np = (n_sites + 127) / 128 * 128;
-#else
   const int np = (n_sites + 63) / 64 * 64 < 128 ? 128 : (n_sites + 63) / 64 * 64;
-#endif
   return np <= 1024 ? np : -1;
 }
 
+// Tensor maps of the GEMM operands (kernel parameter space, __grid_constant__): every buffer is one 2-D f64 tensor
+// [rows = matrices x NP][cols = NP], box 16 x 16, 128-byte swizzle.  G / T hold all chains' matrices stacked as rows.
+struct L2TmaMaps {
+  alignas(64) CUtensorMap G, T, E, Et, Ei, Eit;
+  const double* pG; const double* pT; const double* pE; const double* pEt; const double* pEi; const double* pEit;
+  long long n_elems;      // doubles in the G (and T) buffer
+  int valid;
+};
+
+struct L2Workspace {
+  double* T = nullptr;      // [chain][2][NP][NP] second matrix buffer (two-GEMM wrap, running product)
+  int kd = 0;               // delay depth the shared-memory budget allows
+  int tmem_mode = 0;        // tensor-memory slice path that fits the shared-memory region: 0 none, 1 NP <= 256, 2 384 < NP <= 512, 3 512 < NP <= 768
+  size_t smem = 0;          // dynamic shared memory per CTA
+  L2TmaMaps maps;           // tensor maps of the GEMM operands (built at the first launch)
+};
+
 struct L2Smem {
+  const L2TmaMaps* maps = nullptr;     // set by the sweep kernel when the launch carries tensor maps
   // vector phase
   double* U;      // [2 spin][KD][NP]   e vectors of the delayed flips
   double* W;      // [2 spin][KD][NP]   c vectors
@@ -97,15 +111,15 @@ struct L2Smem {
     pa = U;
     pb = pa + L2_STAGES * L2_BK * (L2_BM + 4);
     double* tail = W + (size_t)ns * KD * NP;
-    const size_t gemm_end = (size_t)L2_STAGES * L2_BK * (L2_BM + L2_BN + 8);
+    const size_t gemm_end = L2_GEMM_DOUBLES;
     if ((size_t)2 * ns * KD * NP < gemm_end) tail = U + gemm_end;
     d = tail;
     u = d + 4 * NP;
     red_v = u + NP;
     hist = red_v + 16;
     ring = hist + 64;
-    full = reinterpret_cast<uint64_t*>(ring + L2_RING * 2 * L2_KDT);
-    red_i = reinterpret_cast<int*>(full + 4);
+    full = reinterpret_cast<uint64_t*>(ring + L2_RING * 2 * L2_KDT);     // [0..3] "panel landed", [4..7] "panel consumed"
+    red_i = reinterpret_cast<int*>(full + 8);
     h = reinterpret_cast<int8_t*>(red_i + 16);
     hn = h + NP;
   }
@@ -113,9 +127,9 @@ struct L2Smem {
 
 inline size_t l2_smem_bytes(int NP, int KD, int ns = 2) {
   size_t vec = (size_t)2 * ns * KD * NP;
-  const size_t gemm = (size_t)L2_STAGES * L2_BK * (L2_BM + L2_BN + 8);
+  const size_t gemm = L2_GEMM_DOUBLES;
   if (vec < gemm) vec = gemm;
-  return (vec + 5 * (size_t)NP + 16 + 64 + L2_RING * 2 * L2_KDT + 4) * sizeof(double) + 16 * sizeof(int) + 2 * (size_t)NP + 16;
+  return (vec + 5 * (size_t)NP + 16 + 64 + L2_RING * 2 * L2_KDT + 8) * sizeof(double) + 16 * sizeof(int) + 2 * (size_t)NP + 16;
 }
 
 // ---- tiled GEMM:  C = A * B  with A given k-major (At[k*NP + i] = A[i][k]) and B row-major ------------------
@@ -238,7 +252,7 @@ __device__ __noinline__ void l2_gemm_sub(const double* __restrict__ At, const do
 #pragma unroll
         for (int n = 0; n < 4; ++n) hc[n] = *reinterpret_cast<const unsigned short*>(ep.hcol + j0 + 32 * wn + 8 * n + 2 * lk);
       }
-#if LQMC_L2_STAGING_TMA
+#if 0   // (round 1's row-wise cp.async.bulk staging; superseded by l2_gemm_tma_sub below)
       const uint32_t it0 = *sm.pipe_iter;
       L2PanelIssue pi;
       pi.srcA = At + (size_t)lane * NP + i0;
@@ -355,12 +369,205 @@ __device__ __noinline__ void l2_gemm_sub(const double* __restrict__ At, const do
   __syncthreads();
 }
 
+// ---- the same GEMM with TMA-staged operands (north_star item 2) ---------------------------------------------------------------
+// Operand panels arrive by cp.async.bulk.tensor (SASS UTMALDG): one elected thread issues 2 KB boxes of 16 k-rows x 16 doubles
+// through a 2-D tensor map of the whole buffer (all chains' matrices stacked as rows) with the 128-byte swizzle, four boxes for the
+// 64-wide left panel and eight for the 128-wide right panel; they complete on the stage's "full" mbarrier (expect_tx = 24 KB).
+// Nobody but that thread spends issue slots or LSU wavefronts on staging, and the panels are dense (no padding columns).
+//
+// Bank conflicts: a DMMA fragment load reads, per half warp, 4 k-rows x 4 consecutive doubles.  In a dense 128-byte-row box all
+// k-rows start in bank 0; the hardware swizzle XORs the 16-byte chunk index with (row & 7), which separates rows r and r' only if
+// (r ^ r') touches bit 1 or 2 of the chunk index - so a lane's k index within a k4 step is mapped to rows {0,2,4,6} (+1 for odd
+// steps, +8 for the second half of the panel) instead of {0,1,2,3}: the contraction index may be visited in any order as long as
+// both operands use the same one.  Every fragment load is then conflict-free (checked: l1tex__data_bank_conflicts in
+// profiles/r02g_*).
+//
+// Pipeline: L2_TMA_STAGES stages, "full" (TMA -> consumers, tx-count) and "empty" (consumers -> producer, one arrive per warp)
+// mbarriers, no __syncthreads in the main loop.  The panel sequence runs across the block tiles of the GEMM: while the warps are
+// in a tile's epilogue the first panels of the next tile are already in flight.  Out-of-range boxes of the half tile at the right
+// edge (NP = 64 mod 128) are zero-filled by the TMA unit.
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* map, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+               "l"(map), "r"(c0), "r"(c1), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_u32(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+struct L2TmaOperand { const void* map; int row0; };        // tensor map of the buffer and the matrix's first row in it
+struct L2GemmTmaCtx { uint32_t stage0; uint32_t bars; uint32_t* pipe_iter; const unsigned char* stage_ptr; double exp_pl, exp_ml; };
+__device__ __noinline__ void l2_gemm_tma_sub(const L2TmaOperand opA, const L2TmaOperand opB, double* __restrict__ Cout, int NP, int spin,
+                                             const L2Epilogue ep, const L2GemmTmaCtx sm) {
+  constexpr int S = L2_TMA_STAGES;
+  constexpr uint32_t STAGE_BYTES = (L2_BM + L2_BN) * L2_BK * sizeof(double);       // 24 KB
+  constexpr uint32_t A_BYTES = L2_BM * L2_BK * sizeof(double);                     // 8 KB: boxes 0..3 of a stage, then 8 B boxes
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp >> 2, wn = warp & 3;            // 2 x 4 warps, 32 x 32 warp tiles
+  const int lr = lane >> 2, lk = lane & 3;
+  const int nk = NP / L2_BK;
+  const int tiles_n = (NP + L2_BN - 1) / L2_BN, n_tiles = (NP / L2_BM) * tiles_n;
+  const int n_panels = n_tiles * nk;
+  const uint32_t full0 = sm.bars, empty0 = sm.bars + 8u * S;
+  const unsigned char* const stage_ptr = sm.stage_ptr;
+  __builtin_assume(__isShared(stage_ptr));
+  // generic-proxy writes of this CTA (previous epilogue, flush, the U / W region the stages alias) before async-proxy traffic
+  fence_proxy_async();
+  __syncthreads();
+  // the barriers are initialised once per kernel; panels are numbered across the GEMM calls of the launch (stage and phase parity)
+  const uint32_t q0 = *sm.pipe_iter;
+  // producer: one thread; panel q = (tile q / nk, k-panel q % nk) goes to stage (q0 + q) % S
+  auto issue = [&](int q) {
+    const int t = q / nk, kp = q - t * nk;
+    const int ti = t / tiles_n, tj = t - ti * tiles_n;
+    const int st = (q0 + q) % S;
+    const uint32_t dst = sm.stage0 + (uint32_t)st * STAGE_BYTES, bar = full0 + 8u * st;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(STAGE_BYTES) : "memory");
+#pragma unroll
+    for (int b = 0; b < L2_BM / 16; ++b) tma_load_2d(dst + b * L2_TMA_SUB, opA.map, ti * L2_BM + 16 * b, opA.row0 + kp * L2_BK, bar);
+#pragma unroll
+    for (int b = 0; b < L2_BN / 16; ++b)
+      tma_load_2d(dst + A_BYTES + b * L2_TMA_SUB, opB.map, tj * L2_BN + 16 * b, opB.row0 + kp * L2_BK, bar);
+  };
+  // the producer is ONE elected lane of warp 0 (elect.sync: the compiler then knows the TMA operands are uniform and emits the
+  // UTMALDG straight from uniform registers instead of a per-lane loop)
+  auto elected = [&]() -> bool {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}" : "=r"(pred));
+    return pred != 0;
+  };
+  if (warp == 0) {
+    if (elected())
+      for (int q = 0; q < S - 1 && q < n_panels; ++q) issue(q);
+    __syncwarp();
+  }
+  // per-lane fragment offsets inside a stage (bytes): box of the fragment's 16-column group, k-row 2 lk (+ step parity, + 8 for
+  // the second half), 16-byte chunk XOR (row & 7), 8-byte half
+  uint32_t offA[4], offB[4];                       // [m] / [n] for step parity 0, k-half 0; the other three steps are derived
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    const int e = 8 * (m & 1) + lr;                // element inside the 16-wide box
+    offA[m] = (uint32_t)((2 * wm + (m >> 1)) * L2_TMA_SUB + (2 * lk) * 128 + (((e >> 1) ^ (2 * lk)) << 4) + ((e & 1) << 3));
+    offB[m] = A_BYTES + (uint32_t)((2 * wn + (m >> 1)) * L2_TMA_SUB + (2 * lk) * 128 + (((e >> 1) ^ (2 * lk)) << 4) + ((e & 1) << 3));
+  }
+  int q = 0;
+  for (int t = 0; t < n_tiles; ++t) {
+    const int ti = t / tiles_n, tj = t - ti * tiles_n;
+    const int i0 = ti * L2_BM, j0 = tj * L2_BN;
+    const bool w_ok = j0 + 32 * wn < NP;                 // half tile at the right edge: this warp owns no columns (warp-uniform)
+    double acc[4][4][2];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+    // field bytes of this thread's rows / column pairs for the epilogue scales: in flight during the main loop
+    int hr[4] = {1, 1, 1, 1};
+    unsigned hc[4] = {0x0101u, 0x0101u, 0x0101u, 0x0101u};
+    if (ep.hrow) {
+#pragma unroll
+      for (int m = 0; m < 4; ++m) hr[m] = ep.hrow[i0 + 32 * wm + 8 * m + lr];
+    }
+    if (ep.hcol && w_ok) {
+#pragma unroll
+      for (int n = 0; n < 4; ++n) hc[n] = *reinterpret_cast<const unsigned short*>(ep.hcol + j0 + 32 * wn + 8 * n + 2 * lk);
+    }
+    for (int kp = 0; kp < nk; ++kp, ++q) {
+      const uint32_t qg = q0 + (uint32_t)q;
+      const int st = qg % S;
+      mbar_wait_u32(full0 + 8u * st, (qg / S) & 1u);
+      // ordinary (non-volatile) loads: the compiler may run the next step's fragment loads under the current step's DMMAs, but not
+      // above the barrier wait (a volatile asm with a memory clobber)
+      const unsigned char* base = stage_ptr + (size_t)st * STAGE_BYTES;
+      if (w_ok) {
+#pragma unroll
+        for (int s4 = 0; s4 < 4; ++s4) {
+          // step s4: k-rows 8 (s4 >> 1) + 2 lk + (s4 & 1); an odd row flips bit 0 of the chunk XOR, the second half adds 1 KB
+          const uint32_t delta = (uint32_t)((s4 >> 1) * 1024 + (s4 & 1) * 128), flip = (uint32_t)((s4 & 1) << 4);
+          double a[4], b[4];
+#pragma unroll
+          for (int m = 0; m < 4; ++m) a[m] = *reinterpret_cast<const double*>(base + ((offA[m] + delta) ^ flip));
+#pragma unroll
+          for (int n = 0; n < 4; ++n) b[n] = *reinterpret_cast<const double*>(base + ((offB[n] + delta) ^ flip));
+#pragma unroll
+          for (int m = 0; m < 4; ++m)
+#pragma unroll
+            for (int n = 0; n < 4; ++n) dmma884(acc[m][n], a[m], b[n]);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive_u32(empty0 + 8u * st);          // this warp is done with the stage
+      // The producer refills the stage panel q-1 sat in.  It does so AFTER its own warp's work on panel q: by then the other
+      // warps have long released panel q-1, so the wait does not hold warp 0 back (issued before the compute it made warp 0 the
+      // last warp of every panel: 0.93 ms per wrap against 0.78 with the cp.async ring, one CTA per SM).
+      if (warp == 0 && q + S - 1 < n_panels) {
+        if (elected()) {
+          if (q >= 1) mbar_wait_u32(empty0 + 8u * ((qg - 1) % S), ((qg - 1) / S) & 1u);
+          issue(q + S - 1);
+        }
+        __syncwarp();
+      }
+    }
+    if (!w_ok) continue;
+    // epilogue: element (row, col) = acc[m][n][s]
+    double cs[4][2];
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      cs[n][0] = ep.hcol ? hs_v2((int8_t)(hc[n] & 0xff), spin, ep.col_inv, sm.exp_pl, sm.exp_ml) : 1.0;
+      cs[n][1] = ep.hcol ? hs_v2((int8_t)(hc[n] >> 8), spin, ep.col_inv, sm.exp_pl, sm.exp_ml) : 1.0;
+    }
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const int row = i0 + 32 * wm + 8 * m + lr;
+      const double rs = hs_v2((int8_t)hr[m], spin, ep.row_inv, sm.exp_pl, sm.exp_ml);
+#pragma unroll
+      for (int n = 0; n < 4; ++n) {
+        const int col0 = j0 + 32 * wn + 8 * n + 2 * lk;
+#pragma unroll
+        for (int s2 = 0; s2 < 2; ++s2) {
+          double v = acc[m][n][s2];
+          if (ep.hrow) v *= rs;
+          if (ep.hcol) v *= cs[n][s2];
+          if (ep.add_identity && row == col0 + s2) v += 1.0;
+          acc[m][n][s2] = v;
+        }
+        if (!ep.transposed_out) {
+          *reinterpret_cast<double2*>(Cout + (size_t)row * NP + col0) = make_double2(acc[m][n][0], acc[m][n][1]);
+        } else {
+          Cout[(size_t)col0 * NP + row] = acc[m][n][0];
+          Cout[(size_t)(col0 + 1) * NP + row] = acc[m][n][1];
+        }
+      }
+    }
+  }
+  __syncthreads();          // all panels consumed, all results stored: the stages may be reused as U / W
+  if (tid == 0) *sm.pipe_iter = q0 + (uint32_t)n_panels;          // ordered before the next call's read by its entry barrier
+}
+
+__device__ __forceinline__ L2TmaOperand l2_tma_operand(const L2TmaMaps& m, const double* ptr, int NP) {
+  if (ptr == m.pE) return L2TmaOperand{&m.E, 0};
+  if (ptr == m.pEt) return L2TmaOperand{&m.Et, 0};
+  if (ptr == m.pEi) return L2TmaOperand{&m.Ei, 0};
+  if (ptr == m.pEit) return L2TmaOperand{&m.Eit, 0};
+  // a matrix of some chain inside the G or the T buffer: NP x NP blocks, so its first row is the element offset / NP
+  if (ptr >= m.pG && ptr < m.pG + m.n_elems) return L2TmaOperand{&m.G, (int)((ptr - m.pG) / NP)};
+  return L2TmaOperand{&m.T, (int)((ptr - m.pT) / NP)};
+}
+
+// One staging variant per binary: with both compiled in, every GEMM call site marshals two argument sets around two calls and the
+// one-launch sweep ran 2 % slower (274 vs 269 ms) whichever path was taken at run time.
 __device__ __forceinline__ void l2_gemm(const double* __restrict__ At, const double* __restrict__ B, double* __restrict__ Cout, int NP, int spin,
                                         const L2Epilogue& ep, const SweepParams& p, L2Smem& sm) {
+#if LQMC_L2_STAGING_TMA
+  L2GemmTmaCtx c;
+  c.stage0 = smem_u32(sm.U); c.bars = smem_u32(sm.full); c.pipe_iter = reinterpret_cast<uint32_t*>(sm.hist + 62);
+  c.stage_ptr = reinterpret_cast<const unsigned char*>(sm.U);
+  c.exp_pl = p.exp_pl; c.exp_ml = p.exp_ml;
+  l2_gemm_tma_sub(l2_tma_operand(*sm.maps, At, NP), l2_tma_operand(*sm.maps, B, NP), Cout, NP, spin, ep, c);
+#else
   L2GemmCtx c;
   c.pa = sm.pa; c.pb = sm.pb; c.full = sm.full; c.pipe_iter = reinterpret_cast<uint32_t*>(sm.hist + 62);
   c.exp_pl = p.exp_pl; c.exp_ml = p.exp_ml;
   l2_gemm_sub(At, B, Cout, NP, spin, ep, c);
+#endif
 }
 
 // ---- G0 <- G0 - sum_m U_m W_m^T for both spins (the delayed block update) -----------------------------------
@@ -1641,6 +1848,7 @@ __device__ void l2_wrap(double* __restrict__ Gc, double* __restrict__ Tc, int NP
 }
 
 struct L2Params {
+  L2TmaMaps maps;
   SweepParams p;
   double* T;
   int use_tmem;   // slice path: 0 shared memory, 1 tensor memory (NP <= 256), 2 / 3 tensor memory with 2 / 3 columns per thread
@@ -1651,11 +1859,12 @@ struct L2Params {
 // TMEM: 0 shared-memory slice path; 1 tensor-memory path, one column per thread (NP <= 256); 2 / 3 several columns per thread
 // (384 < NP <= 512: 2 x depth 24; 512 < NP <= 768: 3 x depth 16 where it fits; one CTA per SM at those sizes)
 template <bool EXACT, bool PHYS, int TMEM>
-__global__ void __launch_bounds__(L2_THREADS, TMEM >= 2 ? 1 : 2) sweep_l2_kernel(const L2Params lp) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+__global__ void __launch_bounds__(L2_THREADS, TMEM >= 2 ? 1 : 2) sweep_l2_kernel(const __grid_constant__ L2Params lp) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];       // 128-byte-swizzled TMA boxes need 1 KB-aligned stages
   const SweepParams& p = lp.p;
   const int NP = lp.NP, KD = lp.KD;
   L2Smem sm(smem_raw, NP, KD);
+  sm.maps = &lp.maps;        // the launcher refuses to launch without valid tensor maps; the 1 KB alignment is checked below
   const int chain = blockIdx.x, tid = threadIdx.x;
   const int N = p.n_sites, L = p.n_slices;
   int8_t* field = p.field + (size_t)chain * L * NP;
@@ -1666,8 +1875,11 @@ __global__ void __launch_bounds__(L2_THREADS, TMEM >= 2 ? 1 : 2) sweep_l2_kernel
   uint32_t tm_base = 0;
   if (TMEM == 1) tm_base = tmem_alloc_cta(reinterpret_cast<uint32_t*>(sm.hist + 63));
   if (TMEM >= 2) tm_base = tmem_alloc_cta_x(reinterpret_cast<uint32_t*>(sm.hist + 63));
+#if LQMC_L2_STAGING_TMA
+  if ((smem_u32(smem_raw) & 1023u) != 0) __trap();          // the swizzled TMA boxes assume 1 KB-aligned stages
+#endif
   if (tid == 0) {
-    for (int s0 = 0; s0 < L2_STAGES; ++s0) mbar_init(sm.full + s0, 1);
+    for (int s0 = 0; s0 < L2_TMA_STAGES; ++s0) { mbar_init(sm.full + s0, 1); mbar_init(sm.full + L2_TMA_STAGES + s0, L2_THREADS / 32); }
     *reinterpret_cast<uint32_t*>(sm.hist + 62) = 0;          // panels consumed so far (TMA staging: stage / phase parity)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -1760,7 +1972,7 @@ inline int l2_alloc(L2Workspace& w, int n_sites, int np, int n_slices, int n_cha
   if (np <= L2_THREADS) {
     // the tensor-memory path keeps U [2][L2_KDT][NP] in the region the generic path sizes for U and W
     size_t region = (size_t)4 * kd * np;
-    const size_t gemm = (size_t)L2_STAGES * L2_BK * (L2_BM + L2_BN + 8);
+    const size_t gemm = L2_GEMM_DOUBLES;
     if (region < gemm) region = gemm;
     w.tmem_mode = ((size_t)2 * L2_KDT * np <= region) ? 1 : 0;
   } else if (np > 384 && np <= 3 * L2_THREADS) {
@@ -1775,9 +1987,48 @@ inline int l2_alloc(L2Workspace& w, int n_sites, int np, int n_slices, int n_cha
 }
 inline void l2_free(L2Workspace& w) { if (w.T) cudaFree(w.T); w.T = nullptr; }
 
+// One 2-D f64 tensor map over a buffer of `rows` rows of NP doubles: box 16 x 16 (128-byte rows), 128-byte swizzle, zero fill
+// outside.  cuTensorMapEncodeTiled comes from the driver through the runtime (no link against libcuda).
+inline bool l2_encode_map(CUtensorMap* out, const double* base, int np, size_t rows) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                               const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) != cudaSuccess || !sym) return false;
+    fn = reinterpret_cast<EncodeFn>(sym);
+  }
+  const cuuint64_t dims[2] = {(cuuint64_t)np, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)np * sizeof(double)};
+  const cuuint32_t box[2] = {16, 16};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+inline void l2_build_maps(L2Workspace& w, const SweepParams& p, int np) {
+  L2TmaMaps& m = w.maps;
+  if (m.valid && m.pG == p.G && m.pT == w.T && m.pE == p.E && m.pEt == p.Et && m.pEi == p.Ei && m.pEit == p.Eit) return;
+  memset(&m, 0, sizeof(m));
+#if LQMC_L2_STAGING_TMA
+  const size_t rows = (size_t)p.n_chains * 2 * np;
+  bool ok = l2_encode_map(&m.G, p.G, np, rows) && l2_encode_map(&m.T, w.T, np, rows) && l2_encode_map(&m.E, p.E, np, np) &&
+            l2_encode_map(&m.Et, p.Et, np, np) && l2_encode_map(&m.Ei, p.Ei, np, np) && l2_encode_map(&m.Eit, p.Eit, np, np);
+  m.pG = p.G; m.pT = w.T; m.pE = p.E; m.pEt = p.Et; m.pEi = p.Ei; m.pEit = p.Eit;
+  m.n_elems = (long long)rows * np;
+  m.valid = ok ? 1 : 0;
+#endif
+}
+
 inline int launch_l2(L2Workspace& w, const SweepParams& p, int np, uint32_t flags, cudaStream_t s, long long* launches, char* err,
                      size_t errlen) {
   L2Params lp;
+  l2_build_maps(w, p, np);
+#if LQMC_L2_STAGING_TMA
+  if (!w.maps.valid) { snprintf(err, errlen, "cuTensorMapEncodeTiled failed for the GEMM operands (driver too old for TMA tensor maps?)"); return 2; }
+#endif
+  lp.maps = w.maps;
   lp.p = p; lp.T = w.T; lp.NP = np; lp.KD = w.kd;
   lp.use_tmem = p.do_propose ? w.tmem_mode : 0;
   if (const char* env = getenv("LQMC_L2_SLICE_PATH")) { if (strcmp(env, "smem") == 0) lp.use_tmem = 0; }     // experiments

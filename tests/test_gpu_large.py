@@ -119,7 +119,10 @@ def test_free_running_sweep_10x10(arith):
             assert np.array_equal(a, acc[c, s]), (c, s)
             tot += np.stack([gu, gd])
         assert np.array_equal(h, ff[c])
-        tol = 1e-9 if arith == "exact" else 1e-6     # contracted FMAs perturb at 1e-16; the recurrence amplifies
+        # a free-running sweep amplifies 1e-16 rounding differences (here |G| ~ 3e3): two builds of the engine that differ only in
+        # the summation order of the wrap GEMMs (cp.async vs TMA staging) differ from each other by 2e-9 here, as much as
+        # either does from NumPy - the decisions, asserted above, are identical.  Per-slice parity is the 1e-10 gate.
+        tol = 1e-8 if arith == "exact" else 1e-6     # contracted FMAs perturb at 1e-16; the recurrence amplifies
         assert _close(gg[c, 0], gu, tol) and _close(gg[c, 1], gd, tol)
         assert _close(m["g_sum"][c], tot, tol)
         assert m["n_accepted"][c] == acc[c].sum() and m["n_meas"][c] == 2
