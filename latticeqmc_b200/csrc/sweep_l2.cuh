@@ -942,6 +942,9 @@ __device__ __forceinline__ void tmem_ld_quad_wait(TmemQuad& q) {
                : "+r"(q.r[0]), "+r"(q.r[1]), "+r"(q.r[2]), "+r"(q.r[3]), "+r"(q.r[4]), "+r"(q.r[5]), "+r"(q.r[6]), "+r"(q.r[7]),
                  "+r"(q.r[8]), "+r"(q.r[9]), "+r"(q.r[10]), "+r"(q.r[11]), "+r"(q.r[12]), "+r"(q.r[13]), "+r"(q.r[14]), "+r"(q.r[15]));
 }
+#ifndef LQMC_FMA_FLUSH_DMMA
+#define LQMC_FMA_FLUSH_DMMA 1      // fma arithmetic: flush on DMMA fragments (0: the scalar walk with one FMA per element)
+#endif
 #ifndef LQMC_FLUSH_ROWS
 #define LQMC_FLUSH_ROWS 4          // rows per chunk of the two-column flush; the next chunk's G is prefetched into registers
 #endif
@@ -1045,6 +1048,121 @@ __device__ __noinline__ void l2_flush_tmem2(double* __restrict__ Gc, int nd, dou
   __syncthreads();
 }
 
+// columns [c_lo, c_lo + L2_COLWIN) of both spins, transposed into Tc (the window of a slice's first flips, and the window after a
+// tensor-core flush, whose register layout does not hold 4 consecutive rows of a column); NP == 256
+__device__ __forceinline__ void l2_colwin_init(const double* __restrict__ Gc, double* __restrict__ Tc, int c_lo = 0) {
+  constexpr int NP = 256;
+  const int tid = threadIdx.x;
+  // thread -> (spin, column c, 32-row block): 2 x 64 x 8 = 1024 pieces of 32 rows, four per thread; a warp reads 32 consecutive
+  // columns of one row at a time (256-byte segments) and every thread stores 32 contiguous rows (256 bytes)
+  for (int piece = tid; piece < 2 * L2_COLWIN * (NP / 32); piece += L2_THREADS) {
+    const int c = c_lo + piece % L2_COLWIN, rb = (piece / L2_COLWIN) % (NP / 32), spin = piece / (L2_COLWIN * (NP / 32));
+    if (c >= NP) continue;
+    const double* src = Gc + (size_t)spin * NP * NP + (size_t)(32 * rb) * NP + c;
+    double* dst = Tc + (size_t)spin * NP * NP + (size_t)c * NP + 32 * rb;
+#pragma unroll 4
+    for (int r = 0; r < 32; r += 4) {
+      const double a0 = src[(size_t)r * NP], a1 = src[(size_t)(r + 1) * NP], a2 = src[(size_t)(r + 2) * NP], a3 = src[(size_t)(r + 3) * NP];
+      *reinterpret_cast<double2*>(dst + r) = make_double2(a0, a1);
+      *reinterpret_cast<double2*>(dst + r + 2) = make_double2(a2, a3);
+    }
+  }
+}
+
+// ---- fma arithmetic: the flush as an FP64 tensor-core GEMM (north_star item 1) -------------------------------------------------
+// Where the reference's roundings are not claimed (LQMC_ARITH_FMA: one FMA per element update) the block update
+// G0 <- G0 - U W^T is a k = 24 GEMM and runs on DMMA fragments:
+//   * A = -e: fragments straight from the shared-memory history U3[k][row] (one LDS.64 per 4 DMMAs);
+//   * B = c: the c history lives in tensor memory, one lane per G column.  tcgen05.ld in the 16x256b shape hands thread
+//     (lr = t / 4, lk = t % 4) the two words 2 lk, 2 lk + 1 of lane lr (and of lane lr + 8) - the double c_{4s + lk} of column lr,
+//     i.e. exactly the mma.m8n8k4 B fragment (k = lk, column = lr).  Tensor memory feeds the tensor-core operand with no
+//     shuffle and no shared-memory round trip (layout checked on the device by tools/tmem_frag_test.cu);
+//   * C = G0: accumulator fragments loaded from and stored to global memory (row lr, two adjacent columns per lane).
+// Warp w owns the 32 columns whose histories sit in its lane quarter (window w / 4) and walks all 256 rows, two 8-row tiles at a
+// time: 8 independent accumulators per k step.  2 x 256 x 256 x 24 FMAs = 49 K pipe clocks per flush, half the exact flush, and
+// 1 / 8 of its shared-memory wavefronts - the scalar flush is LSU-bound in fma arithmetic (same time as the exact one).
+// Measured (profiles/r02_cfg4_summary.md): cfg4 in fma arithmetic 269 -> 250 ms per sweep.  Prefetching the next pair of tiles
+// makes the flush itself faster (11.3 K -> 9.6 K clocks per flip) but the sweep SLOWER (266 ms): back-to-back 16-clock DMMAs starve
+// the co-resident chain's latency-bound build (5.1 K -> 8.8 K clocks per flip), so the walk is left un-prefetched.
+__device__ __forceinline__ void tmem_ld_bfrag(uint32_t taddr, double& b0, double& b1) {
+  uint32_t r0, r1, r2, r3;
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x1.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  b0 = __hiloint2double((int)r1, (int)r0);
+  b1 = __hiloint2double((int)r3, (int)r2);
+}
+__device__ __noinline__ void l2_flush_tmem2_dmma(double* __restrict__ Gc, int nd, double* __restrict__ U3, uint32_t tm_base,
+                                                 double* __restrict__ Tc, int wlo) {
+  constexpr int NP = 256;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lr = lane >> 2, lk = lane & 3;
+  const int q = warp & 3, win = warp >> 2;
+  const uint32_t tm_quarter = tm_base + ((uint32_t)(32 * q) << 16);
+  const int nd4 = (nd + 3) & ~3;
+  if (nd4 != nd) {                                   // zero-pad the last k step (thread t: entry t of the e vectors, history of column t)
+    const uint32_t tm_my = tm_quarter + (uint32_t)(win * 4 * L2_KDT);
+    for (int m = nd; m < nd4; ++m)
+#pragma unroll
+      for (int spin = 0; spin < 2; ++spin) {
+        U3[((size_t)spin * L2_KDT + m) * NP + tid] = 0.0;
+        tmem_st_f64(tm_my + 2 * (spin * L2_KDT + m), 0.0);
+      }
+    tmem_wait_st();
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+  }
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const int c0 = 32 * q + 128 * win;                 // this warp's 32 columns
+  const int nsteps = nd4 / 4;
+  for (int spin = 0; spin < 2; ++spin) {
+    double b[L2_KDT / 4][4];
+#pragma unroll
+    for (int s4 = 0; s4 < L2_KDT / 4; ++s4) {
+      if (s4 < nsteps) {
+        const uint32_t col = (uint32_t)(win * 4 * L2_KDT + 2 * (spin * L2_KDT + 4 * s4));
+        tmem_ld_bfrag(tm_quarter + col, b[s4][0], b[s4][1]);                          // lanes 0-7 / 8-15 of the quarter: column tiles 0, 1
+        tmem_ld_bfrag(tm_quarter + (16u << 16) + col, b[s4][2], b[s4][3]);            // lanes 16-23 / 24-31: column tiles 2, 3
+      } else {
+        b[s4][0] = b[s4][1] = b[s4][2] = b[s4][3] = 0.0;
+      }
+    }
+    double* const Gs = Gc + (size_t)spin * NP * NP + c0 + 2 * lk;
+    const double* const Us = U3 + (size_t)spin * L2_KDT * NP + (size_t)lk * NP + lr;
+    for (int mi = 0; mi < NP / 8; mi += 2) {
+      double acc[2][4][2];
+#pragma unroll
+      for (int mm = 0; mm < 2; ++mm)
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+          const double2 v = *reinterpret_cast<const double2*>(Gs + (size_t)(8 * (mi + mm) + lr) * NP + 8 * n);
+          acc[mm][n][0] = v.x; acc[mm][n][1] = v.y;
+        }
+#pragma unroll
+      for (int s4 = 0; s4 < L2_KDT / 4; ++s4) {
+        if (s4 < nsteps) {
+          double a[2];
+#pragma unroll
+          for (int mm = 0; mm < 2; ++mm) a[mm] = -Us[(size_t)(4 * s4) * NP + 8 * (mi + mm)];
+#pragma unroll
+          for (int mm = 0; mm < 2; ++mm)
+#pragma unroll
+            for (int n = 0; n < 4; ++n) dmma884(acc[mm][n], a[mm], b[s4][n]);
+        }
+      }
+#pragma unroll
+      for (int mm = 0; mm < 2; ++mm)
+#pragma unroll
+        for (int n = 0; n < 4; ++n)
+          *reinterpret_cast<double2*>(Gs + (size_t)(8 * (mi + mm) + lr) * NP + 8 * n) = make_double2(acc[mm][n][0], acc[mm][n][1]);
+    }
+  }
+  __syncthreads();
+  if (wlo < NP) {                                    // the builder's transposed column window, from the freshly written G0
+    l2_colwin_init(Gc, Tc, wlo);
+    __syncthreads();
+  }
+}
+
 // The build of one accepted flip (row and column of the current G, Sherman-Morrison vectors) is a chain of dependent
 // latencies - the FP64 work in it is small - and with the flush at the pipe floor it is what the co-resident CTA's flush has to
 // hide.  Three things keep the chain short (r01: 3.5 K clocks per flip alone on an SM, 6.9 K next to a flushing CTA):
@@ -1063,24 +1181,6 @@ __device__ __noinline__ void l2_flush_tmem2(double* __restrict__ Gc, int nd, dou
 #ifndef LQMC_L2_PFD
 #define LQMC_L2_PFD 0
 #endif
-// columns [0, L2_COLWIN) of both spins, transposed into Tc (the window of a slice's first flips); NP == 256
-__device__ __forceinline__ void l2_colwin_init(const double* __restrict__ Gc, double* __restrict__ Tc) {
-  constexpr int NP = 256;
-  const int tid = threadIdx.x;
-  // thread -> (spin, column c, 32-row block): 2 x 64 x 8 = 1024 pieces of 32 rows, four per thread; a warp reads 32 consecutive
-  // columns of one row at a time (256-byte segments) and every thread stores 32 contiguous rows (256 bytes)
-  for (int piece = tid; piece < 2 * L2_COLWIN * (NP / 32); piece += L2_THREADS) {
-    const int c = piece % L2_COLWIN, rb = (piece / L2_COLWIN) % (NP / 32), spin = piece / (L2_COLWIN * (NP / 32));
-    const double* src = Gc + (size_t)spin * NP * NP + (size_t)(32 * rb) * NP + c;
-    double* dst = Tc + (size_t)spin * NP * NP + (size_t)c * NP + 32 * rb;
-#pragma unroll 4
-    for (int r = 0; r < 32; r += 4) {
-      const double a0 = src[(size_t)r * NP], a1 = src[(size_t)(r + 1) * NP], a2 = src[(size_t)(r + 2) * NP], a3 = src[(size_t)(r + 3) * NP];
-      *reinterpret_cast<double2*>(dst + r) = make_double2(a0, a1);
-      *reinterpret_cast<double2*>(dst + r + 2) = make_double2(a2, a3);
-    }
-  }
-}
 // Two chains share an SM (2 CTAs) and one FP64 pipe.  A flush wants the whole pipe for ~100 K clocks, a build hardly any of it:
 // the pair runs fastest in anti-phase (one chain flushes while the other builds its next 24 flips), but nothing makes two
 // independent CTAs fall into that rhythm - whatever offset they start with persists, and when both flush at once both then
@@ -1401,7 +1501,10 @@ __device__ __noinline__ int l2_propose_slice_tmem_sub(const L2SliceArgs a) {
 #endif
     if (nd == L2_KDT) {
       const bool tok = l2_flush_token_acquire();
-      if (NP == 256) { wlo = is + 1; l2_flush_tmem2<EXACT>(Gc, nd, U3, tm_base, Tc, wlo); } else l2_flush_tmem<EXACT>(Gc, NP, nd, U3, tm_my);
+      if (NP == 256) {
+        wlo = is + 1;
+        if (EXACT || !LQMC_FMA_FLUSH_DMMA) l2_flush_tmem2<EXACT>(Gc, nd, U3, tm_base, Tc, wlo); else l2_flush_tmem2_dmma(Gc, nd, U3, tm_base, Tc, wlo);
+      } else l2_flush_tmem<EXACT>(Gc, NP, nd, U3, tm_my);
       l2_flush_token_release(tok);
       nd = 0;
       if (PF > 0) {                               // G0 changed: reload the slots of the next candidates
@@ -1416,7 +1519,9 @@ __device__ __noinline__ int l2_propose_slice_tmem_sub(const L2SliceArgs a) {
   }
   if (nd > 0) {
     const bool tok = l2_flush_token_acquire();
-    if (NP == 256) l2_flush_tmem2<EXACT>(Gc, nd, U3, tm_base, Tc, NP); else l2_flush_tmem<EXACT>(Gc, NP, nd, U3, tm_my);
+    if (NP == 256) {
+      if (EXACT || !LQMC_FMA_FLUSH_DMMA) l2_flush_tmem2<EXACT>(Gc, nd, U3, tm_base, Tc, NP); else l2_flush_tmem2_dmma(Gc, nd, U3, tm_base, Tc, NP);
+    } else l2_flush_tmem<EXACT>(Gc, NP, nd, U3, tm_my);
     l2_flush_token_release(tok);
   }
 #ifdef LQMC_PHASE_CLOCKS
