@@ -299,9 +299,9 @@ int stab_init_impl(lqmc_engine* e) {
   int rc = 0;
   if (st.nfrag == 4) {
     int kd = 1;
-    while (kd < 32 && lqmc::l2_smem_bytes(st.NPs, kd + 1, 1) <= 110 * 1024) ++kd;
+    while (kd < 32 && lqmc::l2_smem_bytes(st.NPs, kd + 1, 1, false) <= 110 * 1024) ++kd;
     st.kd = kd;
-    st.smem_inv = lqmc::l2_smem_bytes(st.NPs, kd, 1);
+    st.smem_inv = lqmc::l2_smem_bytes(st.NPs, kd, 1, false);
     rc |= set_smem(lqmc::st_chain_kernel<4>, st.smem_gemm);
     rc |= set_smem(lqmc::st_v_kernel<4>, st.smem_gemm);
     rc |= set_smem(lqmc::st_gemm_kernel<4>, st.smem_gemm);

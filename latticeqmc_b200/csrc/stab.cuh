@@ -859,7 +859,7 @@ struct StInvArgs { double* M; int* piv; int NPs, KD; };
 
 __global__ void __launch_bounds__(L2_THREADS, 2) st_inverse_l2_kernel(const StInvArgs a) {
   extern __shared__ __align__(16) unsigned char st_smem[];
-  L2Smem sm(st_smem, a.NPs, a.KD, 1);
+  L2Smem sm(st_smem, a.NPs, a.KD, 1, false);
   l2_gj_inverse<1>(a.M + (size_t)blockIdx.x * a.NPs * a.NPs, a.NPs, a.KD, sm, a.piv + (size_t)blockIdx.x * a.NPs);
 }
 

@@ -105,14 +105,15 @@ struct L2Smem {
   uint64_t* full; // [L2_STAGES] mbarriers: "panel landed"
   uint32_t pipe_iter = 0;   // panels consumed so far by this CTA (uniform across threads): stage and phase parity
   // ns = matrices the CTA works on at once (2: both spins of a chain; 1: the single-matrix inverse of stab.cuh)
-  __device__ L2Smem(unsigned char* base, int NP, int KD, int ns = 2) {
+  // with_gemm: reserve the operand-stage region of the GEMMs (the single-matrix inverse of stab.cuh has no GEMM and must not pay for it)
+  __device__ L2Smem(unsigned char* base, int NP, int KD, int ns = 2, bool with_gemm = true) {
     U = reinterpret_cast<double*>(base);
     W = U + (size_t)ns * KD * NP;
     pa = U;
     pb = pa + L2_STAGES * L2_BK * (L2_BM + 4);
     double* tail = W + (size_t)ns * KD * NP;
     const size_t gemm_end = L2_GEMM_DOUBLES;
-    if ((size_t)2 * ns * KD * NP < gemm_end) tail = U + gemm_end;
+    if (with_gemm && (size_t)2 * ns * KD * NP < gemm_end) tail = U + gemm_end;
     d = tail;
     u = d + 4 * NP;
     red_v = u + NP;
@@ -125,10 +126,10 @@ struct L2Smem {
   }
 };
 
-inline size_t l2_smem_bytes(int NP, int KD, int ns = 2) {
+inline size_t l2_smem_bytes(int NP, int KD, int ns = 2, bool with_gemm = true) {
   size_t vec = (size_t)2 * ns * KD * NP;
   const size_t gemm = L2_GEMM_DOUBLES;
-  if (vec < gemm) vec = gemm;
+  if (with_gemm && vec < gemm) vec = gemm;
   return (vec + 5 * (size_t)NP + 16 + 64 + L2_RING * 2 * L2_KDT + 8) * sizeof(double) + 16 * sizeof(int) + 2 * (size_t)NP + 16;
 }
 
