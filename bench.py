@@ -323,7 +323,7 @@ def measure_workload(torch, dist, dev, rank, world, local, name, mode, stab, ari
     del flush
     res = dict(w=w, n=n, lt=lt, fields=fields, chains=chains, chains_total=chains_total, total_ms=total_ms, ms_per_step=total_ms / steps,
                accept=accept, launches=int(launches), wall_s=t_wall, clocks=sampler.stop() if sampler else None,
-               family=eng.info()["family"], physics=physics, stab=stab if physics else 0, barrier=barrier)
+               family=eng.info()["family"], ctas_per_chain=eng.ctas_per_chain(), physics=physics, stab=stab if physics else 0, barrier=barrier)
     res["value"] = chains_total * n * lt * steps / (total_ms * 1e-3)
     res["flops_per_step_all_ranks"] = (flops_per_sweep_physics(n, lt, accept, stab) if physics and stab
                                        else flops_per_sweep(n, lt, accept)) * chains_total
@@ -460,7 +460,8 @@ def run_ours(args):
             config=dict(workload=args.workload, description=w["text"], n_sites=n, n_slices=lt, chains_per_gpu=chains,
                         chains_total=chains_total, mode=args.mode, stab_every=args.stab if physics else 0,
                         arith=args.arith, rng="device philox4x32-10",
-                        kernel_family=res["family"], l2="flushed between timed steps (256 MiB memset, untimed)",
+                        kernel_family=res["family"], ctas_per_chain=res["ctas_per_chain"],
+                        l2="flushed between timed steps (256 MiB memset, untimed)",
                         parallelism=(f"{chains_total} chains sharded over {world} GPU(s) "
                                      f"({'fixed total, split' if args.scaling == 'strong' else 'fixed per GPU'}), no collective in the sweep")),
             accept_rate=accept, accepted_flips_per_s=value * accept,

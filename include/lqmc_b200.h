@@ -150,6 +150,11 @@ int lqmc_set_measurements(lqmc_engine* e, const double* g_sum, const double* obs
  * 4 n_meas (int64 [chain]), 5 n_accepted (int64 [chain]).  *n_bytes receives the allocation size. */
 int lqmc_device_ptr(lqmc_engine* e, int which, void** ptr, uint64_t* n_bytes);
 
+/* CTAs per Markov chain of the most recent sweep / slice / wrap launch: 1, or the size of the thread-block cluster one chain ran
+ * on (large-lattice kernel at 16x16 with fewer chains than half the SMs: the reference's analogue is a fixed job split over more
+ * worker processes, multiprocessing.py:260-267).  Results do not depend on it (bit-identical). */
+int lqmc_get_cluster(lqmc_engine* e, int* ctas_per_chain);
+
 /* Engine facts: padded size NP, global sweep counter, kernels launched so far, which kernel family
  * serves this size ("reg" = register-resident G, one CTA per chain; "l2" = G in HBM/L2 with delayed
  * rank-k updates). */

@@ -1016,6 +1016,12 @@ int lqmc_info(lqmc_engine* e, int* n_pad, int64_t* sweep_counter, int64_t* launc
   return LQMC_OK;
 }
 
+int lqmc_get_cluster(lqmc_engine* e, int* ctas_per_chain) {
+  if (!e || !ctas_per_chain) return fail(LQMC_ERR_INVALID, "engine or ctas_per_chain is NULL");
+  *ctas_per_chain = e->family_reg ? 1 : e->l2.last_cluster;
+  return LQMC_OK;
+}
+
 int lqmc_set_sweep_counter(lqmc_engine* e, int64_t counter) {
   if (!e) return fail(LQMC_ERR_INVALID, "engine is NULL");
   e->sweep_counter = counter;

@@ -84,10 +84,36 @@ struct L2Workspace {
   int tmem_mode = 0;        // tensor-memory slice path that fits the shared-memory region: 0 none, 1 NP <= 256, 2 384 < NP <= 512, 3 512 < NP <= 768
   size_t smem = 0;          // dynamic shared memory per CTA
   L2TmaMaps maps;           // tensor maps of the GEMM operands (built at the first launch)
+  int last_cluster = 1;     // CTAs per chain of the most recent launch
 };
+
+// ---- one chain on a thread-block cluster (strong scaling: fewer chains than SMs) --------------------------------------------
+// With fewer chains than SMs one CTA per chain leaves most of the GPU idle (37 chains: a quarter of a B200).  The sweep kernel can
+// instead run one chain on a cluster of CS = 2 / 4 / 8 CTAs (one per SM, co-scheduled by the hardware):
+//   * the two phases that carry the work - GEMM tiles (wrap, sweep-start product) and the rows of the delayed-update flush - are
+//     SPLIT over the CTAs of the cluster;
+//   * the latency-bound build of a flip (acceptance scan, row / column rebuild, Sherman-Morrison vectors) is REPLICATED: every CTA
+//     reads the same G0 rows / columns, performs the same arithmetic in the same order and therefore takes the same decisions
+//     and holds the same (e, c) histories - which it needs anyway for its share of the flush.  No vector is exchanged; the only
+//     communication is the hardware cluster barrier (barrier.cluster arrive.release / wait.acquire) that orders the global-memory
+//     writes of one phase before the reads of the next;
+//   * the serial sweep-start inverse runs on rank 0 alone (6 % of the recompute).
+// Every element of G still sees the reference's operations in the reference's order: bit-identical to the one-CTA kernel.
+__device__ __forceinline__ void l2_cluster_sync(int cs) {
+  if (cs > 1) {
+    __threadfence();                                          // this CTA's global writes (flush, epilogue) before the release
+    asm volatile("fence.proxy.async;" ::: "memory");          // ... also for the TMA (async-proxy) reads of the peers
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    __threadfence();
+  } else {
+    __syncthreads();
+  }
+}
 
 struct L2Smem {
   const L2TmaMaps* maps = nullptr;     // set by the sweep kernel when the launch carries tensor maps
+  int cs = 1, crank = 0;               // cluster size and this CTA's rank in it (1 / 0: one CTA per chain)
   // vector phase
   double* U;      // [2 spin][KD][NP]   e vectors of the delayed flips
   double* W;      // [2 spin][KD][NP]   c vectors
@@ -396,7 +422,7 @@ __device__ __forceinline__ void mbar_arrive_u32(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 struct L2TmaOperand { const void* map; int row0; };        // tensor map of the buffer and the matrix's first row in it
-struct L2GemmTmaCtx { uint32_t stage0; uint32_t bars; uint32_t* pipe_iter; const unsigned char* stage_ptr; double exp_pl, exp_ml; };
+struct L2GemmTmaCtx { uint32_t stage0; uint32_t bars; uint32_t* pipe_iter; const unsigned char* stage_ptr; double exp_pl, exp_ml; int cs, crank; };
 __device__ __noinline__ void l2_gemm_tma_sub(const L2TmaOperand opA, const L2TmaOperand opB, double* __restrict__ Cout, int NP, int spin,
                                              const L2Epilogue ep, const L2GemmTmaCtx sm) {
   constexpr int S = L2_TMA_STAGES;
@@ -406,7 +432,9 @@ __device__ __noinline__ void l2_gemm_tma_sub(const L2TmaOperand opA, const L2Tma
   const int wm = warp >> 2, wn = warp & 3;            // 2 x 4 warps, 32 x 32 warp tiles
   const int lr = lane >> 2, lk = lane & 3;
   const int nk = NP / L2_BK;
-  const int tiles_n = (NP + L2_BN - 1) / L2_BN, n_tiles = (NP / L2_BM) * tiles_n;
+  const int tiles_n = (NP + L2_BN - 1) / L2_BN, n_tiles_all = (NP / L2_BM) * tiles_n;
+  // block tiles crank, crank + cs, ... of the GEMM are this CTA's (cs = 1: all of them)
+  const int n_tiles = (n_tiles_all - sm.crank + sm.cs - 1) / sm.cs;
   const int n_panels = n_tiles * nk;
   const uint32_t full0 = sm.bars, empty0 = sm.bars + 8u * S;
   const unsigned char* const stage_ptr = sm.stage_ptr;
@@ -418,7 +446,8 @@ __device__ __noinline__ void l2_gemm_tma_sub(const L2TmaOperand opA, const L2Tma
   const uint32_t q0 = *sm.pipe_iter;
   // producer: one thread; panel q = (tile q / nk, k-panel q % nk) goes to stage (q0 + q) % S
   auto issue = [&](int q) {
-    const int t = q / nk, kp = q - t * nk;
+    const int tl = q / nk, kp = q - tl * nk;
+    const int t = sm.crank + tl * sm.cs;
     const int ti = t / tiles_n, tj = t - ti * tiles_n;
     const int st = (q0 + q) % S;
     const uint32_t dst = sm.stage0 + (uint32_t)st * STAGE_BYTES, bar = full0 + 8u * st;
@@ -451,7 +480,8 @@ __device__ __noinline__ void l2_gemm_tma_sub(const L2TmaOperand opA, const L2Tma
     offB[m] = A_BYTES + (uint32_t)((2 * wn + (m >> 1)) * L2_TMA_SUB + (2 * lk) * 128 + (((e >> 1) ^ (2 * lk)) << 4) + ((e & 1) << 3));
   }
   int q = 0;
-  for (int t = 0; t < n_tiles; ++t) {
+  for (int tl = 0; tl < n_tiles; ++tl) {
+    const int t = sm.crank + tl * sm.cs;
     const int ti = t / tiles_n, tj = t - ti * tiles_n;
     const int i0 = ti * L2_BM, j0 = tj * L2_BN;
     const bool w_ok = j0 + 32 * wn < NP;                 // half tile at the right edge: this warp owns no columns (warp-uniform)
@@ -561,8 +591,9 @@ __device__ __forceinline__ void l2_gemm(const double* __restrict__ At, const dou
   L2GemmTmaCtx c;
   c.stage0 = smem_u32(sm.U); c.bars = smem_u32(sm.full); c.pipe_iter = reinterpret_cast<uint32_t*>(sm.hist + 62);
   c.stage_ptr = reinterpret_cast<const unsigned char*>(sm.U);
-  c.exp_pl = p.exp_pl; c.exp_ml = p.exp_ml;
+  c.exp_pl = p.exp_pl; c.exp_ml = p.exp_ml; c.cs = sm.cs; c.crank = sm.crank;
   l2_gemm_tma_sub(l2_tma_operand(*sm.maps, At, NP), l2_tma_operand(*sm.maps, B, NP), Cout, NP, spin, ep, c);
+  if (sm.cs > 1) l2_cluster_sync(sm.cs);          // every tile of the product is in memory before any CTA reads it as an operand
 #else
   L2GemmCtx c;
   c.pa = sm.pa; c.pb = sm.pb; c.full = sm.full; c.pipe_iter = reinterpret_cast<uint32_t*>(sm.hist + 62);
@@ -975,7 +1006,7 @@ __device__ __forceinline__ void l2_flush_apply4(double (&g)[R][2], const TmemQua
 constexpr int L2_COLWIN = 64;
 template <bool EXACT>
 __device__ __noinline__ void l2_flush_tmem2(double* __restrict__ Gc, int nd, double* __restrict__ U3, uint32_t tm_base,
-                                            double* __restrict__ Tc, int wlo) {
+                                            double* __restrict__ Tc, int wlo, int cs, int crank) {
   constexpr int NP = 256, R = LQMC_FLUSH_ROWS;
   const int tid = threadIdx.x, warp = tid >> 5;
   const int jj = tid & 127, rbase = (tid >> 7) * (NP / 2);
@@ -995,10 +1026,12 @@ __device__ __noinline__ void l2_flush_tmem2(double* __restrict__ Gc, int nd, dou
   }
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   // the two spins are one walk of 2 x 128 / R chunks: the prefetch of the next chunk runs across the spin boundary
-  constexpr int CH = NP / 2 / R;                     // chunks per spin
+  constexpr int CHA = NP / 2 / R;                    // chunks per spin and thread half
+  const int ch_lo = crank * CHA / cs, CH = (crank + 1) * CHA / cs - ch_lo;   // this CTA of a cluster walks chunks [ch_lo, ch_lo + CH) (any cluster size)
+  auto chunk_row = [&](int ch) -> int { return (ch_lo + ch % CH) * R; };
   auto chunk_ptr = [&](int ch) -> double* {
-    const int spin = ch / CH, r0 = (ch % CH) * R;    // CH is a power of two
-    return Gc + (size_t)spin * NP * NP + (size_t)(rbase + r0) * NP + jj;
+    const int spin = ch / CH;
+    return Gc + (size_t)spin * NP * NP + (size_t)(rbase + chunk_row(ch)) * NP + jj;
   };
   double nxt[R][2];
   {
@@ -1009,7 +1042,7 @@ __device__ __noinline__ void l2_flush_tmem2(double* __restrict__ Gc, int nd, dou
   TmemQuad ca, cb;
   tmem_ld_quad_issue(tm_lane, tm_lane + 4 * L2_KDT, ca);
   for (int ch = 0; ch < 2 * CH; ++ch) {
-    const int spin = ch / CH, r0 = (ch % CH) * R;
+    const int spin = ch / CH, r0 = chunk_row(ch);
     double* const col = chunk_ptr(ch);
     const double* const Us = U3 + (size_t)spin * L2_KDT * NP + rbase + r0;
     const uint32_t tm0 = tm_lane + 2 * (spin * L2_KDT), tm1 = tm0 + 4 * L2_KDT;
@@ -1051,19 +1084,20 @@ __device__ __noinline__ void l2_flush_tmem2(double* __restrict__ Gc, int nd, dou
 
 // columns [c_lo, c_lo + L2_COLWIN) of both spins, transposed into Tc (the window of a slice's first flips, and the window after a
 // tensor-core flush, whose register layout does not hold 4 consecutive rows of a column); NP == 256
-__device__ __forceinline__ void l2_colwin_init(const double* __restrict__ Gc, double* __restrict__ Tc, int c_lo = 0) {
+__device__ __forceinline__ void l2_colwin_init(const double* __restrict__ Gc, double* __restrict__ Tc, int c_lo = 0, int cs = 1, int crank = 0) {
   constexpr int NP = 256;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x + L2_THREADS * crank;         // pieces dealt out over all threads of the cluster
   // thread -> (spin, column c, 32-row block): 2 x 64 x 8 = 1024 pieces of 32 rows, four per thread; a warp reads 32 consecutive
   // columns of one row at a time (256-byte segments) and every thread stores 32 contiguous rows (256 bytes)
-  for (int piece = tid; piece < 2 * L2_COLWIN * (NP / 32); piece += L2_THREADS) {
+  for (int piece = tid; piece < 2 * L2_COLWIN * (NP / 32); piece += L2_THREADS * cs) {
     const int c = c_lo + piece % L2_COLWIN, rb = (piece / L2_COLWIN) % (NP / 32), spin = piece / (L2_COLWIN * (NP / 32));
     if (c >= NP) continue;
     const double* src = Gc + (size_t)spin * NP * NP + (size_t)(32 * rb) * NP + c;
     double* dst = Tc + (size_t)spin * NP * NP + (size_t)c * NP + 32 * rb;
 #pragma unroll 4
     for (int r = 0; r < 32; r += 4) {
-      const double a0 = src[(size_t)r * NP], a1 = src[(size_t)(r + 1) * NP], a2 = src[(size_t)(r + 2) * NP], a3 = src[(size_t)(r + 3) * NP];
+      const double a0 = __ldcg(src + (size_t)r * NP), a1 = __ldcg(src + (size_t)(r + 1) * NP), a2 = __ldcg(src + (size_t)(r + 2) * NP),
+                   a3 = __ldcg(src + (size_t)(r + 3) * NP);            // L2: the matrix may have been written by a peer CTA of the cluster
       *reinterpret_cast<double2*>(dst + r) = make_double2(a0, a1);
       *reinterpret_cast<double2*>(dst + r + 2) = make_double2(a2, a3);
     }
@@ -1093,7 +1127,7 @@ __device__ __forceinline__ void tmem_ld_bfrag(uint32_t taddr, double& b0, double
   b1 = __hiloint2double((int)r3, (int)r2);
 }
 __device__ __noinline__ void l2_flush_tmem2_dmma(double* __restrict__ Gc, int nd, double* __restrict__ U3, uint32_t tm_base,
-                                                 double* __restrict__ Tc, int wlo) {
+                                                 double* __restrict__ Tc, int wlo, int cs, int crank) {
   constexpr int NP = 256;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int lr = lane >> 2, lk = lane & 3;
@@ -1129,7 +1163,8 @@ __device__ __noinline__ void l2_flush_tmem2_dmma(double* __restrict__ Gc, int nd
     }
     double* const Gs = Gc + (size_t)spin * NP * NP + c0 + 2 * lk;
     const double* const Us = U3 + (size_t)spin * L2_KDT * NP + (size_t)lk * NP + lr;
-    for (int mi = 0; mi < NP / 8; mi += 2) {
+    const int mi_lo = 2 * (crank * (NP / 16) / cs), mi_hi = 2 * ((crank + 1) * (NP / 16) / cs);     // pairs of 8-row tiles of this CTA of a cluster
+    for (int mi = mi_lo; mi < mi_hi; mi += 2) {
       double acc[2][4][2];
 #pragma unroll
       for (int mm = 0; mm < 2; ++mm)
@@ -1157,10 +1192,10 @@ __device__ __noinline__ void l2_flush_tmem2_dmma(double* __restrict__ Gc, int nd
           *reinterpret_cast<double2*>(Gs + (size_t)(8 * (mi + mm) + lr) * NP + 8 * n) = make_double2(acc[mm][n][0], acc[mm][n][1]);
     }
   }
-  __syncthreads();
+  l2_cluster_sync(cs);
   if (wlo < NP) {                                    // the builder's transposed column window, from the freshly written G0
-    l2_colwin_init(Gc, Tc, wlo);
-    __syncthreads();
+    l2_colwin_init(Gc, Tc, wlo, cs, crank);
+    if (cs == 1) __syncthreads();                    // (in a cluster the caller's barrier after the flush orders these stores)
   }
 }
 
@@ -1229,6 +1264,7 @@ struct L2SliceArgs {
   long long trace_base;
   uint32_t tm_base;
   int NP, N;
+  int cs, crank;
 };
 struct L2SliceView {                       // the members of L2Smem / SweepParams the slice path touches, under their old names
   double* U; double* d; double* u; double* hist; double* ring; int8_t* h;
@@ -1243,6 +1279,7 @@ __device__ __noinline__ int l2_propose_slice_tmem_sub(const L2SliceArgs a) {
   const uint32_t tm_base = a.tm_base;
   L2SliceView sm{a.U, a.d, a.u, a.hist, a.ring, a.h, nullptr, nullptr, nullptr, 0.0, 0.0, 0};
   L2SliceView p{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, a.tr_ratio, a.tr_acc, a.obs, a.f_p2, a.f_m2, a.N};
+  const int cs = a.cs, crank = a.crank;
   int n_accepted = 0;
   static_assert(PF >= 0 && PF <= 3, "prefetch depth");
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1256,10 +1293,10 @@ __device__ __noinline__ int l2_propose_slice_tmem_sub(const L2SliceArgs a) {
   const uint32_t tm_my = tm_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)((warp >> 2) * 4 * L2_KDT);
   double* const myring = sm.ring + (size_t)(j & (L2_RING - 1)) * 2 * L2_KDT;
   for (int spin = 0; spin < 2; ++spin)
-    for (int q = tid; q < NP; q += L2_THREADS) sm.d[spin * NP + q] = Gc[(size_t)spin * NN + (size_t)q * NP + q];
+    for (int q = tid; q < NP; q += L2_THREADS) sm.d[spin * NP + q] = __ldcg(Gc + (size_t)spin * NN + (size_t)q * NP + q);
   int wlo = NP;                                  // first column of the transposed window in Tc (NP: none)
-  if (NP == 256) { l2_colwin_init(Gc, Tc); wlo = 0; }
-  __syncthreads();
+  if (NP == 256) { l2_colwin_init(Gc, Tc, 0, cs, crank); wlo = 0; }
+  l2_cluster_sync(cs);
   int nd = 0, i0 = 0, cur = 0;
   int pf_base = -(1 << 20);                      // prow / pcol [k] = G0 row / column of site pf_base + k (valid until the next flush)
   int pub_base = -(1 << 20);                     // ring slots of sites pub_base + 1 .. pub_base + L2_PUB hold those sites' c history
@@ -1269,10 +1306,10 @@ __device__ __noinline__ int l2_propose_slice_tmem_sub(const L2SliceArgs a) {
     if (act) {
       const bool win = (unsigned)(s - wlo) < (unsigned)L2_COLWIN;      // CTA-uniform
       const double* cp = win ? Tc + (size_t)s * NP + j : Gc + (size_t)j * NP + s;
-      c[0] = cp[0];
-      c[1] = cp[NN];
-      r[0] = Gc[(size_t)s * NP + j];
-      r[1] = Gc[NN + (size_t)s * NP + j];
+      c[0] = __ldcg(cp);                             // L2 loads: in a cluster these lines are written by peer CTAs (flush, wrap)
+      c[1] = __ldcg(cp + NN);
+      r[0] = __ldcg(Gc + (size_t)s * NP + j);
+      r[1] = __ldcg(Gc + NN + (size_t)s * NP + j);
     }
   };
   // register-free look-ahead: rows / window columns of the sites up to LQMC_L2_PFD ahead are pulled into L2 (prefetch.global.L2
@@ -1502,10 +1539,13 @@ __device__ __noinline__ int l2_propose_slice_tmem_sub(const L2SliceArgs a) {
 #endif
     if (nd == L2_KDT) {
       const bool tok = l2_flush_token_acquire();
+      if (cs > 1) l2_cluster_sync(cs);             // every CTA of the cluster has read what it needs of the un-flushed G0
       if (NP == 256) {
         wlo = is + 1;
-        if (EXACT || !LQMC_FMA_FLUSH_DMMA) l2_flush_tmem2<EXACT>(Gc, nd, U3, tm_base, Tc, wlo); else l2_flush_tmem2_dmma(Gc, nd, U3, tm_base, Tc, wlo);
+        if (EXACT || !LQMC_FMA_FLUSH_DMMA) l2_flush_tmem2<EXACT>(Gc, nd, U3, tm_base, Tc, wlo, cs, crank);
+        else l2_flush_tmem2_dmma(Gc, nd, U3, tm_base, Tc, wlo, cs, crank);
       } else l2_flush_tmem<EXACT>(Gc, NP, nd, U3, tm_my);
+      if (cs > 1) l2_cluster_sync(cs);             // ... and now sees every CTA's share of the flushed one
       l2_flush_token_release(tok);
       nd = 0;
       if (PF > 0) {                               // G0 changed: reload the slots of the next candidates
@@ -1520,11 +1560,14 @@ __device__ __noinline__ int l2_propose_slice_tmem_sub(const L2SliceArgs a) {
   }
   if (nd > 0) {
     const bool tok = l2_flush_token_acquire();
+    if (cs > 1) l2_cluster_sync(cs);
     if (NP == 256) {
-      if (EXACT || !LQMC_FMA_FLUSH_DMMA) l2_flush_tmem2<EXACT>(Gc, nd, U3, tm_base, Tc, NP); else l2_flush_tmem2_dmma(Gc, nd, U3, tm_base, Tc, NP);
+      if (EXACT || !LQMC_FMA_FLUSH_DMMA) l2_flush_tmem2<EXACT>(Gc, nd, U3, tm_base, Tc, NP, cs, crank);
+      else l2_flush_tmem2_dmma(Gc, nd, U3, tm_base, Tc, NP, cs, crank);
     } else l2_flush_tmem<EXACT>(Gc, NP, nd, U3, tm_my);
     l2_flush_token_release(tok);
   }
+  if (cs > 1) l2_cluster_sync(cs);                 // the slice's last writes of G0 before the wrap GEMMs of the peers read it
 #ifdef LQMC_PHASE_CLOCKS
   { const long long tk1 = clock64(); tk_flush += tk1 - tk0;
     if (tid == 0) { double* ob = p.obs_sum + (size_t)blockIdx.x * 3 * N; ob[0] = (double)tk_scan; ob[1] = (double)tk_build; ob[2] = (double)tk_flush; ob[3] = (double)n_accepted;
@@ -1544,6 +1587,7 @@ __device__ __forceinline__ void l2_propose_slice_tmem(double* __restrict__ Gc, d
   a.Gc = Gc; a.Tc = Tc; a.U = sm.U; a.d = sm.d; a.u = sm.u; a.hist = sm.hist; a.ring = sm.ring; a.h = sm.h;
   a.tr_ratio = p.tr_ratio; a.tr_acc = p.tr_acc; a.obs = p.obs_sum;
   a.f_p2 = p.f_p2; a.f_m2 = p.f_m2; a.trace_base = trace_base; a.tm_base = tm_base; a.NP = NP; a.N = p.n_sites;
+  a.cs = sm.cs; a.crank = sm.crank;
   n_accepted += l2_propose_slice_tmem_sub<EXACT, PHYS>(a);
 }
 
@@ -1917,13 +1961,13 @@ __device__ void l2_recompute(double* __restrict__ Gc, double* __restrict__ Tc, i
         for (int c = tid; c < NP; c += L2_THREADS)
           G[(size_t)r * NP + c] = p.E[(size_t)r * NP + c] * hs_v(hl[c], spin, p) + (r == c ? 1.0 : 0.0);
     } else {
-      // first factor, stored k-major (transposed): cur[c][r] = E[r][c] * v_c
-      for (int c = 0; c < NP; ++c) {
+      // first factor, stored k-major (transposed): cur[c][r] = E[r][c] * v_c   (columns split over the cluster)
+      for (int c = sm.crank; c < NP; c += sm.cs) {
         const double v = hs_v(hl[c], spin, p);
         for (int r = tid; r < NP; r += L2_THREADS) cur[(size_t)c * NP + r] = p.Et[(size_t)c * NP + r] * v;
       }
     }
-    __syncthreads();
+    l2_cluster_sync(sm.cs);
     for (int m = 1; m < L; ++m) {
       l = (l0 - 1 - m + 2 * L) % L;
       L2Epilogue ep;
@@ -1934,7 +1978,9 @@ __device__ void l2_recompute(double* __restrict__ Gc, double* __restrict__ Tc, i
       double* t = cur; cur = oth; oth = t;
     }
   }
-  l2_gj_inverse<2>(Gc, NP, KD, sm, piv_global);
+  // the Gauss-Jordan inverse is a serial chain of pivots: rank 0 of a cluster runs it alone
+  if (sm.crank == 0) l2_gj_inverse<2>(Gc, NP, KD, sm, piv_global);
+  if (sm.cs > 1) l2_cluster_sync(sm.cs);
 }
 
 // ---- wrap from slice l to l-1 ------------------------------------------------------------------------------
@@ -1960,6 +2006,7 @@ struct L2Params {
   int use_tmem;   // slice path: 0 shared memory, 1 tensor memory (NP <= 256), 2 / 3 tensor memory with 2 / 3 columns per thread
   int* piv;       // [chain][2][NP] scratch
   int NP, KD;
+  int cluster;    // CTAs per chain (thread-block cluster size; 1 = one CTA per chain)
 };
 
 // TMEM: 0 shared-memory slice path; 1 tensor-memory path, one column per thread (NP <= 256); 2 / 3 several columns per thread
@@ -1971,7 +2018,8 @@ __global__ void __launch_bounds__(L2_THREADS, TMEM >= 2 ? 1 : 2) sweep_l2_kernel
   const int NP = lp.NP, KD = lp.KD;
   L2Smem sm(smem_raw, NP, KD);
   sm.maps = &lp.maps;        // the launcher refuses to launch without valid tensor maps; the 1 KB alignment is checked below
-  const int chain = blockIdx.x, tid = threadIdx.x;
+  sm.cs = lp.cluster; sm.crank = (int)(blockIdx.x % (unsigned)lp.cluster);       // cluster dimension = (cluster, 1, 1): rank = blockIdx.x % size
+  const int chain = blockIdx.x / lp.cluster, tid = threadIdx.x;
   const int N = p.n_sites, L = p.n_slices;
   int8_t* field = p.field + (size_t)chain * L * NP;
   double* Gc = p.G + (size_t)chain * 2 * NP * NP;
@@ -2036,7 +2084,7 @@ __global__ void __launch_bounds__(L2_THREADS, TMEM >= 2 ? 1 : 2) sweep_l2_kernel
 #ifdef LQMC_PHASE_CLOCKS
     if (tid == 0 && p.do_recompute) { double* ob = p.obs_sum + (size_t)chain * 3 * N; ob[16] = (double)kt_rec; ob[17] = (double)kt_slice; ob[18] = (double)kt_wrap; }
 #endif
-    if (p.measure) {
+    if (p.measure && sm.crank == 0) {
       __syncthreads();
       for (int spin = 0; spin < 2; ++spin) {
         const double* G = Gc + (size_t)spin * NP * NP;
@@ -2052,8 +2100,9 @@ __global__ void __launch_bounds__(L2_THREADS, TMEM >= 2 ? 1 : 2) sweep_l2_kernel
       if (tid == 0) p.n_meas[chain] += 1;
       __syncthreads();
     }
+    if (sm.cs > 1) l2_cluster_sync(sm.cs);        // rank 0 has read G for the measurement before the next sweep's product overwrites it
   }
-  if (tid == 0 && n_accepted) p.n_acc[chain] += n_accepted;
+  if (tid == 0 && n_accepted && sm.crank == 0) p.n_acc[chain] += n_accepted;
   if (TMEM == 1) tmem_free_cta(tm_base);
   if (TMEM >= 2) tmem_free_cta_x(tm_base);
 }
@@ -2136,15 +2185,58 @@ inline int launch_l2(L2Workspace& w, const SweepParams& p, int np, uint32_t flag
 #endif
   lp.maps = w.maps;
   lp.p = p; lp.T = w.T; lp.NP = np; lp.KD = w.kd;
+  lp.cluster = 1;
   lp.use_tmem = p.do_propose ? w.tmem_mode : 0;
   if (const char* env = getenv("LQMC_L2_SLICE_PATH")) { if (strcmp(env, "smem") == 0) lp.use_tmem = 0; }     // experiments
   lp.piv = reinterpret_cast<int*>(w.T + (size_t)p.n_chains * 2 * np * np);
   const bool exact = !(flags & 0x2u), phys = (flags & 0x1u) != 0;
+  // Strong scaling: with few chains, one chain per cluster of CTAs (one CTA per SM: the cluster variant asks for more than half an
+  // SM's shared memory).  Largest cluster size whose clusters are all co-resident for this chain count; NP = 256 tensor-memory
+  // path only (the split flush / tile schedule is written for it).  LQMC_L2_CLUSTER = 1 / 2 / 4 / 8 overrides (experiments).
+  const size_t smem_cluster = (w.smem > (size_t)116 * 1024) ? w.smem : (size_t)118 * 1024;
+  auto pick_cluster = [&](auto kernel) -> int {
+#if LQMC_L2_STAGING_TMA
+    if (np != 256 || lp.use_tmem != 1 || w.tmem_mode != 1) return 1;
+    int forced = 0;
+    if (const char* env = getenv("LQMC_L2_CLUSTER")) forced = atoi(env);
+    if (forced == 1) return 1;
+    int n_sm = 0, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (!forced && 2 * p.n_chains > n_sm) return 1;              // enough chains to fill the GPU with one CTA each
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cluster) != cudaSuccess) return 1;
+    for (int cs = 8; cs >= 2; --cs) {
+      if (forced && cs != forced) continue;
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)(p.n_chains * cs)); cfg.blockDim = dim3(L2_THREADS); cfg.dynamicSmemBytes = smem_cluster;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      int max_clusters = 0;
+      if (cudaOccupancyMaxActiveClusters(&max_clusters, kernel, &cfg) != cudaSuccess) { cudaGetLastError(); continue; }
+      if (max_clusters >= p.n_chains) return cs;
+    }
+#endif
+    return 1;
+  };
   auto go = [&](auto kernel) -> int {
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.smem);
-    if (e == cudaSuccess) {
-      kernel<<<p.n_chains, L2_THREADS, w.smem, s>>>(lp);
-      e = cudaGetLastError();
+    const int cs = pick_cluster(kernel);
+    lp.cluster = cs;
+    w.last_cluster = cs;
+    cudaError_t e;
+    if (cs > 1) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)(p.n_chains * cs)); cfg.blockDim = dim3(L2_THREADS); cfg.dynamicSmemBytes = smem_cluster; cfg.stream = s;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      e = cudaLaunchKernelEx(&cfg, kernel, lp);
+    } else {
+      e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.smem);
+      if (e == cudaSuccess) {
+        kernel<<<p.n_chains, L2_THREADS, w.smem, s>>>(lp);
+        e = cudaGetLastError();
+      }
     }
     if (e != cudaSuccess) { snprintf(err, errlen, "sweep_l2_kernel launch failed: %s", cudaGetErrorString(e)); return 2; }
     *launches += 1;

@@ -24,7 +24,7 @@ EXPORTS = (
     "lqmc_get_trace", "lqmc_get_measurements", "lqmc_reset_measurements", "lqmc_device_ptr", "lqmc_info",
     "lqmc_set_sweep_counter", "lqmc_set_chain_offset", "lqmc_philox_uniforms", "lqmc_last_error",
     "lqmc_version", "lqmc_selftest_division", "lqmc_recompute_stable", "lqmc_set_stabilization",
-    "lqmc_set_measurements", "lqmc_sweep_det", "lqmc_get_det", "lqmc_set_det", "lqmc_sweep_submit",
+    "lqmc_set_measurements", "lqmc_sweep_det", "lqmc_get_det", "lqmc_set_det", "lqmc_sweep_submit", "lqmc_get_cluster",
 )
 
 
@@ -65,6 +65,7 @@ def load_library(path=None):
     lib.lqmc_sweep_det.argtypes = [vp, ctypes.c_int, vp, ctypes.c_uint64, ctypes.c_int]
     lib.lqmc_get_det.argtypes = [vp, vp]
     lib.lqmc_set_det.argtypes = [vp, vp]
+    lib.lqmc_get_cluster.argtypes = [vp, ctypes.POINTER(ctypes.c_int)]
     lib.lqmc_sweep_submit.argtypes = [vp, ctypes.c_int, vp, ctypes.c_uint64, ctypes.c_int]
     lib.lqmc_sweep_async.argtypes = [vp, ctypes.c_int, vp, ctypes.c_uint64, ctypes.c_int, vp]
     lib.lqmc_sync.argtypes = [vp]
@@ -394,6 +395,12 @@ class SweepEngine:
         fam = ctypes.create_string_buffer(8)
         self._check(self._lib.lqmc_info(self._h, ctypes.byref(n_pad), ctypes.byref(counter), ctypes.byref(launches), fam))
         return dict(n_pad=n_pad.value, sweep_counter=counter.value, launches=launches.value, family=fam.value.decode())
+
+    def ctas_per_chain(self):
+        """CTAs one chain ran on in the most recent launch (1, or the thread-block cluster size chosen for few chains)."""
+        v = ctypes.c_int()
+        self._check(self._lib.lqmc_get_cluster(self._h, ctypes.byref(v)))
+        return v.value
 
     def set_sweep_counter(self, counter):
         self._check(self._lib.lqmc_set_sweep_counter(self._h, int(counter)))

@@ -285,3 +285,36 @@ def test_cfg5_reference_slices(golden):
         out = eng.get_g()[0]
         assert _sub_close(out[0], g, "post98_up", 1e-9) and _sub_close(out[1], g, "post98_dn", 1e-9)
         assert np.array_equal(eng.get_field()[0], g["field1"])
+
+
+@pytest.mark.parametrize("arith", ["exact", "fma"])
+def test_one_chain_per_cluster_is_bit_identical(monkeypatch, arith):
+    """Strong scaling (round 2): with few chains the 16x16 kernel runs ONE chain on a thread-block cluster - GEMM tiles and flush
+    rows split over the CTAs, the build of every flip replicated.  Every element still sees the same operations in the same
+    order, so field, G, decisions, ratios and accumulators must be bit-identical to one CTA per chain, for every cluster size
+    (3 chains: the automatic choice is a cluster of 8; sizes that do not divide the tile / chunk counts are covered too)."""
+    ham = so.ideal_square_kinetic(16, 1.0, 2.0)
+    n, lt = 256, 6
+    dtau, lamb, exp_k = so.set_beta_constants(ham, 4.0, 0.6, lt)
+    fields = np.stack([so.initial_field(n, lt, seed=900 + c) for c in range(3)])
+    out = {}
+    for cs in ("1", "2", "3", "5", "8", None):
+        if cs is None:
+            monkeypatch.delenv("LQMC_L2_CLUSTER", raising=False)
+        else:
+            monkeypatch.setenv("LQMC_L2_CLUSTER", cs)
+        with _engine(exp_k, lamb, lt, n_chains=3, trace=True, arith=arith) as eng:
+            eng.set_field(fields)
+            eng.sweep(2, None, seed=77, measure=True)
+            acc, ratio = eng.get_trace()
+            m = eng.get_measurements()
+            out[cs] = (eng.get_field(), eng.get_g(), acc, ratio, m["g_sum"], m["obs_sum"], m["n_meas"], m["n_accepted"])
+    for cs, r in out.items():
+        for x, y in zip(r, out["1"]):
+            assert np.array_equal(x, y), cs
+    # and the one-CTA result is the oracle's (first sweep of chain 0; well-conditioned product)
+    from latticeqmc_b200 import philox_uniforms
+    h = fields[0].copy()
+    u0 = philox_uniforms(77, 0, 0, n * lt).reshape(lt, n)
+    gu, gd, r, a = so.update_step(h, exp_k, lamb, u0)
+    assert np.array_equal(a, out["1"][2][0, 0])
