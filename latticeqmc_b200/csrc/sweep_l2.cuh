@@ -99,7 +99,27 @@ struct L2Workspace {
 //     writes of one phase before the reads of the next;
 //   * the serial sweep-start inverse runs on rank 0 alone (6 % of the recompute).
 // Every element of G still sees the reference's operations in the reference's order: bit-identical to the one-CTA kernel.
+// A pointer that reaches a __noinline__ subroutine inside a by-value argument is a plain generic value to the compiler: every
+// access through it becomes a generic LD.E / ST.E.  Round-tripping it through its real state space tells the address-space inference
+// which one it is (LDS / STS, LDG / STG again).
+template <class T> __device__ __forceinline__ T* as_shared(T* p) {
+  return reinterpret_cast<T*>(__cvta_shared_to_generic(__cvta_generic_to_shared(const_cast<void*>(static_cast<const void*>(p)))));
+}
+template <class T> __device__ __forceinline__ T* as_global(T* p) {
+  return reinterpret_cast<T*>(__cvta_global_to_generic(__cvta_generic_to_global(const_cast<void*>(static_cast<const void*>(p)))));
+}
+#ifndef LQMC_CLUSTER_LDCG
+#define LQMC_CLUSTER_LDCG 1
+#endif
+template <bool CL>
+__device__ __forceinline__ double l2_ld_peer(const double* p) {
+  if (CL && LQMC_CLUSTER_LDCG) return __ldcg(p);        // a cluster peer may have written the line: read it from L2
+  return *p;
+}
 __device__ __forceinline__ void l2_cluster_sync(int cs) {
+#ifdef LQMC_NO_CLUSTER
+  __syncthreads(); return;
+#endif
   if (cs > 1) {
     __threadfence();                                          // this CTA's global writes (flush, epilogue) before the release
     asm volatile("fence.proxy.async;" ::: "memory");          // ... also for the TMA (async-proxy) reads of the peers
@@ -423,8 +443,13 @@ __device__ __forceinline__ void mbar_arrive_u32(uint32_t bar) {
 }
 struct L2TmaOperand { const void* map; int row0; };        // tensor map of the buffer and the matrix's first row in it
 struct L2GemmTmaCtx { uint32_t stage0; uint32_t bars; uint32_t* pipe_iter; const unsigned char* stage_ptr; double exp_pl, exp_ml; int cs, crank; };
+// CL: the launch runs one chain per thread-block cluster.  A template flag, not a run-time test: with the cluster code compiled into
+// the one-CTA kernel its slice phase ran 20 % slower (1.77 -> 2.12 ms; cause not isolated - not the barrier instructions, not the
+// L2-only loads, not the run-time chunk ranges), so the one-CTA instantiation contains none of it.
+template <bool CL>
 __device__ __noinline__ void l2_gemm_tma_sub(const L2TmaOperand opA, const L2TmaOperand opB, double* __restrict__ Cout, int NP, int spin,
                                              const L2Epilogue ep, const L2GemmTmaCtx sm) {
+  const int ccs = CL ? sm.cs : 1, ccrank = CL ? sm.crank : 0;
   constexpr int S = L2_TMA_STAGES;
   constexpr uint32_t STAGE_BYTES = (L2_BM + L2_BN) * L2_BK * sizeof(double);       // 24 KB
   constexpr uint32_t A_BYTES = L2_BM * L2_BK * sizeof(double);                     // 8 KB: boxes 0..3 of a stage, then 8 B boxes
@@ -434,7 +459,7 @@ __device__ __noinline__ void l2_gemm_tma_sub(const L2TmaOperand opA, const L2Tma
   const int nk = NP / L2_BK;
   const int tiles_n = (NP + L2_BN - 1) / L2_BN, n_tiles_all = (NP / L2_BM) * tiles_n;
   // block tiles crank, crank + cs, ... of the GEMM are this CTA's (cs = 1: all of them)
-  const int n_tiles = (n_tiles_all - sm.crank + sm.cs - 1) / sm.cs;
+  const int n_tiles = (n_tiles_all - ccrank + ccs - 1) / ccs;
   const int n_panels = n_tiles * nk;
   const uint32_t full0 = sm.bars, empty0 = sm.bars + 8u * S;
   const unsigned char* const stage_ptr = sm.stage_ptr;
@@ -447,7 +472,7 @@ __device__ __noinline__ void l2_gemm_tma_sub(const L2TmaOperand opA, const L2Tma
   // producer: one thread; panel q = (tile q / nk, k-panel q % nk) goes to stage (q0 + q) % S
   auto issue = [&](int q) {
     const int tl = q / nk, kp = q - tl * nk;
-    const int t = sm.crank + tl * sm.cs;
+    const int t = ccrank + tl * ccs;
     const int ti = t / tiles_n, tj = t - ti * tiles_n;
     const int st = (q0 + q) % S;
     const uint32_t dst = sm.stage0 + (uint32_t)st * STAGE_BYTES, bar = full0 + 8u * st;
@@ -481,7 +506,7 @@ __device__ __noinline__ void l2_gemm_tma_sub(const L2TmaOperand opA, const L2Tma
   }
   int q = 0;
   for (int tl = 0; tl < n_tiles; ++tl) {
-    const int t = sm.crank + tl * sm.cs;
+    const int t = ccrank + tl * ccs;
     const int ti = t / tiles_n, tj = t - ti * tiles_n;
     const int i0 = ti * L2_BM, j0 = tj * L2_BN;
     const bool w_ok = j0 + 32 * wn < NP;                 // half tile at the right edge: this warp owns no columns (warp-uniform)
@@ -585,6 +610,7 @@ __device__ __forceinline__ L2TmaOperand l2_tma_operand(const L2TmaMaps& m, const
 
 // One staging variant per binary: with both compiled in, every GEMM call site marshals two argument sets around two calls and the
 // one-launch sweep ran 2 % slower (274 vs 269 ms) whichever path was taken at run time.
+template <bool CL>
 __device__ __forceinline__ void l2_gemm(const double* __restrict__ At, const double* __restrict__ B, double* __restrict__ Cout, int NP, int spin,
                                         const L2Epilogue& ep, const SweepParams& p, L2Smem& sm) {
 #if LQMC_L2_STAGING_TMA
@@ -592,8 +618,8 @@ __device__ __forceinline__ void l2_gemm(const double* __restrict__ At, const dou
   c.stage0 = smem_u32(sm.U); c.bars = smem_u32(sm.full); c.pipe_iter = reinterpret_cast<uint32_t*>(sm.hist + 62);
   c.stage_ptr = reinterpret_cast<const unsigned char*>(sm.U);
   c.exp_pl = p.exp_pl; c.exp_ml = p.exp_ml; c.cs = sm.cs; c.crank = sm.crank;
-  l2_gemm_tma_sub(l2_tma_operand(*sm.maps, At, NP), l2_tma_operand(*sm.maps, B, NP), Cout, NP, spin, ep, c);
-  if (sm.cs > 1) l2_cluster_sync(sm.cs);          // every tile of the product is in memory before any CTA reads it as an operand
+  l2_gemm_tma_sub<CL>(l2_tma_operand(*sm.maps, At, NP), l2_tma_operand(*sm.maps, B, NP), Cout, NP, spin, ep, c);
+  if (CL && sm.cs > 1) l2_cluster_sync(sm.cs);    // every tile of the product is in memory before any CTA reads it as an operand
 #else
   L2GemmCtx c;
   c.pa = sm.pa; c.pb = sm.pb; c.full = sm.full; c.pipe_iter = reinterpret_cast<uint32_t*>(sm.hist + 62);
@@ -1004,10 +1030,12 @@ __device__ __forceinline__ void l2_flush_apply4(double (&g)[R][2], const TmemQua
 // transposed into the idle second matrix buffer, Tc[spin][c][r] = G0[r][c]: 32 contiguous bytes per thread and chunk, + 12 % flush
 // traffic, and the builder's column becomes one coalesced 2 KB read.
 constexpr int L2_COLWIN = 64;
+// One CTA per chain: the round-2 flush with compile-time chunk arithmetic (kept verbatim next to the cluster-capable version below)
 template <bool EXACT>
-__device__ __noinline__ void l2_flush_tmem2(double* __restrict__ Gc, int nd, double* __restrict__ U3, uint32_t tm_base,
-                                            double* __restrict__ Tc, int wlo, int cs, int crank) {
+__device__ __noinline__ void l2_flush_tmem2_single(double* __restrict__ Gc, int nd, double* __restrict__ U3, uint32_t tm_base,
+                                            double* __restrict__ Tc, int wlo) {
   constexpr int NP = 256, R = LQMC_FLUSH_ROWS;
+  U3 = as_shared(U3); Gc = as_global(Gc); Tc = as_global(Tc);
   const int tid = threadIdx.x, warp = tid >> 5;
   const int jj = tid & 127, rbase = (tid >> 7) * (NP / 2);
   const uint32_t tm_lane = tm_base + ((uint32_t)(32 * (warp & 3)) << 16);
@@ -1026,12 +1054,10 @@ __device__ __noinline__ void l2_flush_tmem2(double* __restrict__ Gc, int nd, dou
   }
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   // the two spins are one walk of 2 x 128 / R chunks: the prefetch of the next chunk runs across the spin boundary
-  constexpr int CHA = NP / 2 / R;                    // chunks per spin and thread half
-  const int ch_lo = crank * CHA / cs, CH = (crank + 1) * CHA / cs - ch_lo;   // this CTA of a cluster walks chunks [ch_lo, ch_lo + CH) (any cluster size)
-  auto chunk_row = [&](int ch) -> int { return (ch_lo + ch % CH) * R; };
+  constexpr int CH = NP / 2 / R;                     // chunks per spin
   auto chunk_ptr = [&](int ch) -> double* {
-    const int spin = ch / CH;
-    return Gc + (size_t)spin * NP * NP + (size_t)(rbase + chunk_row(ch)) * NP + jj;
+    const int spin = ch / CH, r0 = (ch % CH) * R;    // CH is a power of two
+    return Gc + (size_t)spin * NP * NP + (size_t)(rbase + r0) * NP + jj;
   };
   double nxt[R][2];
   {
@@ -1042,7 +1068,7 @@ __device__ __noinline__ void l2_flush_tmem2(double* __restrict__ Gc, int nd, dou
   TmemQuad ca, cb;
   tmem_ld_quad_issue(tm_lane, tm_lane + 4 * L2_KDT, ca);
   for (int ch = 0; ch < 2 * CH; ++ch) {
-    const int spin = ch / CH, r0 = chunk_row(ch);
+    const int spin = ch / CH, r0 = (ch % CH) * R;
     double* const col = chunk_ptr(ch);
     const double* const Us = U3 + (size_t)spin * L2_KDT * NP + rbase + r0;
     const uint32_t tm0 = tm_lane + 2 * (spin * L2_KDT), tm1 = tm0 + 4 * L2_KDT;
@@ -1082,8 +1108,94 @@ __device__ __noinline__ void l2_flush_tmem2(double* __restrict__ Gc, int nd, dou
   __syncthreads();
 }
 
+// SINGLE: one CTA per chain - the chunk range is a compile-time constant (the cluster variant's run-time range cost the
+// one-CTA kernel 8 % of its slice phase when it was the only version)
+template <bool EXACT, bool SINGLE>
+__device__ __noinline__ void l2_flush_tmem2(double* __restrict__ Gc, int nd, double* __restrict__ U3, uint32_t tm_base,
+                                            double* __restrict__ Tc, int wlo, int cs, int crank) {
+  constexpr int NP = 256, R = LQMC_FLUSH_ROWS;
+  U3 = as_shared(U3); Gc = as_global(Gc); Tc = as_global(Tc);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int jj = tid & 127, rbase = (tid >> 7) * (NP / 2);
+  const uint32_t tm_lane = tm_base + ((uint32_t)(32 * (warp & 3)) << 16);
+  const int nd8 = (nd + 7) & ~7;
+  if (nd8 != nd) {                                   // zero-pad: thread t owns entry t of every e vector and the c history of column t
+    const uint32_t tm_my = tm_lane + (uint32_t)((warp >> 2) * 4 * L2_KDT);
+    for (int m = nd; m < nd8; ++m)
+#pragma unroll
+      for (int spin = 0; spin < 2; ++spin) {
+        U3[((size_t)spin * L2_KDT + m) * NP + tid] = 0.0;
+        tmem_st_f64(tm_my + 2 * (spin * L2_KDT + m), 0.0);
+      }
+    tmem_wait_st();
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+  }
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  // the two spins are one walk of 2 x 128 / R chunks: the prefetch of the next chunk runs across the spin boundary
+  constexpr int CHA = NP / 2 / R;                    // chunks per spin and thread half
+  // this CTA of a cluster walks chunks [ch_lo, ch_lo + CH) (any cluster size)
+  const int ch_lo = SINGLE ? 0 : crank * CHA / cs, CH = SINGLE ? CHA : (crank + 1) * CHA / cs - ch_lo;
+  // the walk (spin, local chunk) is kept as running counters: no integer division in the loop
+  auto chunk_ptr = [&](int spin, int lc) -> double* {
+    return Gc + (size_t)spin * NP * NP + (size_t)(rbase + (ch_lo + lc) * R) * NP + jj;
+  };
+  double nxt[R][2];
+  {
+    const double* c0 = chunk_ptr(0, 0);
+#pragma unroll
+    for (int r = 0; r < R; ++r) { nxt[r][0] = c0[(size_t)r * NP]; nxt[r][1] = c0[(size_t)r * NP + 128]; }
+  }
+  TmemQuad ca, cb;
+  tmem_ld_quad_issue(tm_lane, tm_lane + 4 * L2_KDT, ca);
+  int spin = 0, lc = 0;
+  for (int ch = 0; ch < 2 * CH; ++ch) {
+    const int r0 = (ch_lo + lc) * R;
+    double* const col = chunk_ptr(spin, lc);
+    const double* const Us = U3 + (size_t)spin * L2_KDT * NP + rbase + r0;
+    const uint32_t tm0 = tm_lane + 2 * (spin * L2_KDT), tm1 = tm0 + 4 * L2_KDT;
+    // the chunk after this one (possibly the first of the other spin): its G0 is prefetched, its history starts at update 0
+    int spin_n = spin, lc_n = lc + 1;
+    if (lc_n == CH) { lc_n = 0; spin_n = spin + 1; }
+    const int spin_h = spin_n < 2 ? spin_n : 1;
+    const uint32_t tn0 = tm_lane + 2 * (spin_h * L2_KDT), tn1 = tn0 + 4 * L2_KDT;
+    double g[R][2];
+#pragma unroll
+    for (int r = 0; r < R; ++r) { g[r][0] = nxt[r][0]; g[r][1] = nxt[r][1]; }
+    if (ch + 1 < 2 * CH) {
+      const double* cn = chunk_ptr(spin_n, lc_n);
+#pragma unroll
+      for (int r = 0; r < R; ++r) { nxt[r][0] = cn[(size_t)r * NP]; nxt[r][1] = cn[(size_t)r * NP + 128]; }
+    }
+    for (int m0 = 0; m0 < nd8; m0 += 8) {
+      const bool last = m0 + 8 >= nd8;
+      tmem_ld_quad_wait(ca);
+      tmem_ld_quad_issue(tm0 + 2 * (m0 + 4), tm1 + 2 * (m0 + 4), cb);
+      l2_flush_apply4<EXACT, R>(g, ca, Us + (size_t)m0 * NP, NP);
+      tmem_ld_quad_wait(cb);
+      tmem_ld_quad_issue(last ? tn0 : tm0 + 2 * (m0 + 8), last ? tn1 : tm1 + 2 * (m0 + 8), ca);
+      l2_flush_apply4<EXACT, R>(g, cb, Us + (size_t)(m0 + 4) * NP, NP);
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) { col[(size_t)r * NP] = g[r][0]; col[(size_t)r * NP + 128] = g[r][1]; }
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {
+      const int c = jj + 128 * cc;
+      if ((unsigned)(c - wlo) < (unsigned)L2_COLWIN) {
+        double* dst = Tc + (size_t)spin * NP * NP + (size_t)c * NP + rbase + r0;
+#pragma unroll
+        for (int r = 0; r < R; r += 2) *reinterpret_cast<double2*>(dst + r) = make_double2(g[r][cc], g[r + 1][cc]);
+      }
+    }
+    spin = spin_n; lc = lc_n;
+  }
+  tmem_ld_quad_wait(ca);                               // drain the last (unused) history prefetch
+  __syncthreads();
+}
+
 // columns [c_lo, c_lo + L2_COLWIN) of both spins, transposed into Tc (the window of a slice's first flips, and the window after a
 // tensor-core flush, whose register layout does not hold 4 consecutive rows of a column); NP == 256
+template <bool CL>
 __device__ __forceinline__ void l2_colwin_init(const double* __restrict__ Gc, double* __restrict__ Tc, int c_lo = 0, int cs = 1, int crank = 0) {
   constexpr int NP = 256;
   const int tid = threadIdx.x + L2_THREADS * crank;         // pieces dealt out over all threads of the cluster
@@ -1096,8 +1208,8 @@ __device__ __forceinline__ void l2_colwin_init(const double* __restrict__ Gc, do
     double* dst = Tc + (size_t)spin * NP * NP + (size_t)c * NP + 32 * rb;
 #pragma unroll 4
     for (int r = 0; r < 32; r += 4) {
-      const double a0 = __ldcg(src + (size_t)r * NP), a1 = __ldcg(src + (size_t)(r + 1) * NP), a2 = __ldcg(src + (size_t)(r + 2) * NP),
-                   a3 = __ldcg(src + (size_t)(r + 3) * NP);            // L2: the matrix may have been written by a peer CTA of the cluster
+      const double a0 = l2_ld_peer<CL>(src + (size_t)r * NP), a1 = l2_ld_peer<CL>(src + (size_t)(r + 1) * NP),
+                   a2 = l2_ld_peer<CL>(src + (size_t)(r + 2) * NP), a3 = l2_ld_peer<CL>(src + (size_t)(r + 3) * NP);
       *reinterpret_cast<double2*>(dst + r) = make_double2(a0, a1);
       *reinterpret_cast<double2*>(dst + r + 2) = make_double2(a2, a3);
     }
@@ -1126,8 +1238,11 @@ __device__ __forceinline__ void tmem_ld_bfrag(uint32_t taddr, double& b0, double
   b0 = __hiloint2double((int)r1, (int)r0);
   b1 = __hiloint2double((int)r3, (int)r2);
 }
+template <bool CL>
 __device__ __noinline__ void l2_flush_tmem2_dmma(double* __restrict__ Gc, int nd, double* __restrict__ U3, uint32_t tm_base,
-                                                 double* __restrict__ Tc, int wlo, int cs, int crank) {
+                                                 double* __restrict__ Tc, int wlo, int cs_, int crank_) {
+  const int cs = CL ? cs_ : 1, crank = CL ? crank_ : 0;
+  U3 = as_shared(U3); Gc = as_global(Gc); Tc = as_global(Tc);
   constexpr int NP = 256;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int lr = lane >> 2, lk = lane & 3;
@@ -1192,9 +1307,9 @@ __device__ __noinline__ void l2_flush_tmem2_dmma(double* __restrict__ Gc, int nd
           *reinterpret_cast<double2*>(Gs + (size_t)(8 * (mi + mm) + lr) * NP + 8 * n) = make_double2(acc[mm][n][0], acc[mm][n][1]);
     }
   }
-  l2_cluster_sync(cs);
+  if (CL) l2_cluster_sync(cs); else __syncthreads();
   if (wlo < NP) {                                    // the builder's transposed column window, from the freshly written G0
-    l2_colwin_init(Gc, Tc, wlo, cs, crank);
+    l2_colwin_init<CL>(Gc, Tc, wlo, cs, crank);
     if (cs == 1) __syncthreads();                    // (in a cluster the caller's barrier after the flush orders these stores)
   }
 }
@@ -1263,23 +1378,25 @@ struct L2SliceArgs {
   double f_p2, f_m2;
   long long trace_base;
   uint32_t tm_base;
-  int NP, N;
-  int cs, crank;
+  // 16-bit fields keep the struct at 128 bytes: one int more and nvcc stops scalarising the by-value argument - the pointers lose
+  // their (deduced) shared / global state space and every history access becomes a generic LD.E / ST.E (build 5 K -> 10 K clocks)
+  unsigned short NP, N, cs, crank;
 };
+static_assert(sizeof(L2SliceArgs) <= 128, "keep L2SliceArgs scalarisable");
 struct L2SliceView {                       // the members of L2Smem / SweepParams the slice path touches, under their old names
   double* U; double* d; double* u; double* hist; double* ring; int8_t* h;
   double* tr_ratio; uint8_t* tr_acc; double* obs_sum; double f_p2, f_m2; int n_sites;
 };
-template <bool EXACT, bool PHYS>
+template <bool EXACT, bool PHYS, bool CL>
 __device__ __noinline__ int l2_propose_slice_tmem_sub(const L2SliceArgs a) {
   constexpr int PF = LQMC_L2_PF;
-  double* const Gc = a.Gc; double* const Tc = a.Tc;
+  double* const Gc = as_global(a.Gc); double* const Tc = as_global(a.Tc);
   const int NP = a.NP;
   const long long trace_base = a.trace_base;
   const uint32_t tm_base = a.tm_base;
-  L2SliceView sm{a.U, a.d, a.u, a.hist, a.ring, a.h, nullptr, nullptr, nullptr, 0.0, 0.0, 0};
+  L2SliceView sm{as_shared(a.U), as_shared(a.d), as_shared(a.u), as_shared(a.hist), as_shared(a.ring), as_shared(a.h), nullptr, nullptr, nullptr, 0.0, 0.0, 0};
   L2SliceView p{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, a.tr_ratio, a.tr_acc, a.obs, a.f_p2, a.f_m2, a.N};
-  const int cs = a.cs, crank = a.crank;
+  const int cs = CL ? a.cs : 1, crank = CL ? a.crank : 0;
   int n_accepted = 0;
   static_assert(PF >= 0 && PF <= 3, "prefetch depth");
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1293,10 +1410,10 @@ __device__ __noinline__ int l2_propose_slice_tmem_sub(const L2SliceArgs a) {
   const uint32_t tm_my = tm_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)((warp >> 2) * 4 * L2_KDT);
   double* const myring = sm.ring + (size_t)(j & (L2_RING - 1)) * 2 * L2_KDT;
   for (int spin = 0; spin < 2; ++spin)
-    for (int q = tid; q < NP; q += L2_THREADS) sm.d[spin * NP + q] = __ldcg(Gc + (size_t)spin * NN + (size_t)q * NP + q);
+    for (int q = tid; q < NP; q += L2_THREADS) sm.d[spin * NP + q] = l2_ld_peer<CL>(Gc + (size_t)spin * NN + (size_t)q * NP + q);
   int wlo = NP;                                  // first column of the transposed window in Tc (NP: none)
-  if (NP == 256) { l2_colwin_init(Gc, Tc, 0, cs, crank); wlo = 0; }
-  l2_cluster_sync(cs);
+  if (NP == 256) { l2_colwin_init<CL>(Gc, Tc, 0, cs, crank); wlo = 0; }
+  if (CL) l2_cluster_sync(cs); else __syncthreads();
   int nd = 0, i0 = 0, cur = 0;
   int pf_base = -(1 << 20);                      // prow / pcol [k] = G0 row / column of site pf_base + k (valid until the next flush)
   int pub_base = -(1 << 20);                     // ring slots of sites pub_base + 1 .. pub_base + L2_PUB hold those sites' c history
@@ -1306,10 +1423,10 @@ __device__ __noinline__ int l2_propose_slice_tmem_sub(const L2SliceArgs a) {
     if (act) {
       const bool win = (unsigned)(s - wlo) < (unsigned)L2_COLWIN;      // CTA-uniform
       const double* cp = win ? Tc + (size_t)s * NP + j : Gc + (size_t)j * NP + s;
-      c[0] = __ldcg(cp);                             // L2 loads: in a cluster these lines are written by peer CTAs (flush, wrap)
-      c[1] = __ldcg(cp + NN);
-      r[0] = __ldcg(Gc + (size_t)s * NP + j);
-      r[1] = __ldcg(Gc + NN + (size_t)s * NP + j);
+      c[0] = l2_ld_peer<CL>(cp);                     // L2 loads: in a cluster these lines are written by peer CTAs (flush, wrap)
+      c[1] = l2_ld_peer<CL>(cp + NN);
+      r[0] = l2_ld_peer<CL>(Gc + (size_t)s * NP + j);
+      r[1] = l2_ld_peer<CL>(Gc + NN + (size_t)s * NP + j);
     }
   };
   // register-free look-ahead: rows / window columns of the sites up to LQMC_L2_PFD ahead are pulled into L2 (prefetch.global.L2
@@ -1539,13 +1656,14 @@ __device__ __noinline__ int l2_propose_slice_tmem_sub(const L2SliceArgs a) {
 #endif
     if (nd == L2_KDT) {
       const bool tok = l2_flush_token_acquire();
-      if (cs > 1) l2_cluster_sync(cs);             // every CTA of the cluster has read what it needs of the un-flushed G0
+      if (CL && cs > 1) l2_cluster_sync(cs);       // every CTA of the cluster has read what it needs of the un-flushed G0
       if (NP == 256) {
         wlo = is + 1;
-        if (EXACT || !LQMC_FMA_FLUSH_DMMA) l2_flush_tmem2<EXACT>(Gc, nd, U3, tm_base, Tc, wlo, cs, crank);
-        else l2_flush_tmem2_dmma(Gc, nd, U3, tm_base, Tc, wlo, cs, crank);
+        if (EXACT || !LQMC_FMA_FLUSH_DMMA) {
+          if (!CL || cs == 1) l2_flush_tmem2_single<EXACT>(Gc, nd, U3, tm_base, Tc, wlo); else l2_flush_tmem2<EXACT, false>(Gc, nd, U3, tm_base, Tc, wlo, cs, crank);
+        } else l2_flush_tmem2_dmma<CL>(Gc, nd, U3, tm_base, Tc, wlo, cs, crank);
       } else l2_flush_tmem<EXACT>(Gc, NP, nd, U3, tm_my);
-      if (cs > 1) l2_cluster_sync(cs);             // ... and now sees every CTA's share of the flushed one
+      if (CL && cs > 1) l2_cluster_sync(cs);       // ... and now sees every CTA's share of the flushed one
       l2_flush_token_release(tok);
       nd = 0;
       if (PF > 0) {                               // G0 changed: reload the slots of the next candidates
@@ -1560,14 +1678,15 @@ __device__ __noinline__ int l2_propose_slice_tmem_sub(const L2SliceArgs a) {
   }
   if (nd > 0) {
     const bool tok = l2_flush_token_acquire();
-    if (cs > 1) l2_cluster_sync(cs);
+    if (CL && cs > 1) l2_cluster_sync(cs);
     if (NP == 256) {
-      if (EXACT || !LQMC_FMA_FLUSH_DMMA) l2_flush_tmem2<EXACT>(Gc, nd, U3, tm_base, Tc, NP, cs, crank);
-      else l2_flush_tmem2_dmma(Gc, nd, U3, tm_base, Tc, NP, cs, crank);
+      if (EXACT || !LQMC_FMA_FLUSH_DMMA) {
+        if (!CL || cs == 1) l2_flush_tmem2_single<EXACT>(Gc, nd, U3, tm_base, Tc, NP); else l2_flush_tmem2<EXACT, false>(Gc, nd, U3, tm_base, Tc, NP, cs, crank);
+      } else l2_flush_tmem2_dmma<CL>(Gc, nd, U3, tm_base, Tc, NP, cs, crank);
     } else l2_flush_tmem<EXACT>(Gc, NP, nd, U3, tm_my);
     l2_flush_token_release(tok);
   }
-  if (cs > 1) l2_cluster_sync(cs);                 // the slice's last writes of G0 before the wrap GEMMs of the peers read it
+  if (CL && cs > 1) l2_cluster_sync(cs);           // the slice's last writes of G0 before the wrap GEMMs of the peers read it
 #ifdef LQMC_PHASE_CLOCKS
   { const long long tk1 = clock64(); tk_flush += tk1 - tk0;
     if (tid == 0) { double* ob = p.obs_sum + (size_t)blockIdx.x * 3 * N; ob[0] = (double)tk_scan; ob[1] = (double)tk_build; ob[2] = (double)tk_flush; ob[3] = (double)n_accepted;
@@ -1580,15 +1699,15 @@ __device__ __noinline__ int l2_propose_slice_tmem_sub(const L2SliceArgs a) {
   return n_accepted;
 }
 
-template <bool EXACT, bool PHYS>
+template <bool EXACT, bool PHYS, bool CL>
 __device__ __forceinline__ void l2_propose_slice_tmem(double* __restrict__ Gc, double* __restrict__ Tc, int NP, L2Smem& sm, const SweepParams& p,
                                                       long long trace_base, int& n_accepted, uint32_t tm_base) {
   L2SliceArgs a;
   a.Gc = Gc; a.Tc = Tc; a.U = sm.U; a.d = sm.d; a.u = sm.u; a.hist = sm.hist; a.ring = sm.ring; a.h = sm.h;
   a.tr_ratio = p.tr_ratio; a.tr_acc = p.tr_acc; a.obs = p.obs_sum;
-  a.f_p2 = p.f_p2; a.f_m2 = p.f_m2; a.trace_base = trace_base; a.tm_base = tm_base; a.NP = NP; a.N = p.n_sites;
-  a.cs = sm.cs; a.crank = sm.crank;
-  n_accepted += l2_propose_slice_tmem_sub<EXACT, PHYS>(a);
+  a.f_p2 = p.f_p2; a.f_m2 = p.f_m2; a.trace_base = trace_base; a.tm_base = tm_base; a.NP = (unsigned short)NP; a.N = (unsigned short)p.n_sites;
+  a.cs = (unsigned short)sm.cs; a.crank = (unsigned short)sm.crank;
+  n_accepted += l2_propose_slice_tmem_sub<EXACT, PHYS, CL>(a);
 }
 
 // ---- 256 < NP <= 640: the tensor-memory slice path with several columns per thread ------------------------------------------
@@ -1944,6 +2063,7 @@ __device__ void l2_gj_inverse(double* __restrict__ Gc, int NP, int KD, L2Smem& s
 }
 
 // ---- sweep-start G = inv(I + prod B) in memory ----------------------------------------------------------------
+template <bool CL>
 __device__ void l2_recompute(double* __restrict__ Gc, double* __restrict__ Tc, int NP, int KD, const int8_t* field, int l0,
                              const SweepParams& p, L2Smem& sm, int* piv_global) {
   const int L = p.n_slices;
@@ -1962,40 +2082,40 @@ __device__ void l2_recompute(double* __restrict__ Gc, double* __restrict__ Tc, i
           G[(size_t)r * NP + c] = p.E[(size_t)r * NP + c] * hs_v(hl[c], spin, p) + (r == c ? 1.0 : 0.0);
     } else {
       // first factor, stored k-major (transposed): cur[c][r] = E[r][c] * v_c   (columns split over the cluster)
-      for (int c = sm.crank; c < NP; c += sm.cs) {
+      for (int c = (CL ? sm.crank : 0); c < NP; c += (CL ? sm.cs : 1)) {
         const double v = hs_v(hl[c], spin, p);
         for (int r = tid; r < NP; r += L2_THREADS) cur[(size_t)c * NP + r] = p.Et[(size_t)c * NP + r] * v;
       }
     }
-    l2_cluster_sync(sm.cs);
+    if (CL) l2_cluster_sync(sm.cs); else __syncthreads();
     for (int m = 1; m < L; ++m) {
       l = (l0 - 1 - m + 2 * L) % L;
       L2Epilogue ep;
       ep.hcol = field + (size_t)l * NP;
       ep.transposed_out = (m != L - 1);
       ep.add_identity = (m == L - 1);
-      l2_gemm(cur, p.E, oth, NP, spin, ep, p, sm);
+      l2_gemm<CL>(cur, p.E, oth, NP, spin, ep, p, sm);
       double* t = cur; cur = oth; oth = t;
     }
   }
   // the Gauss-Jordan inverse is a serial chain of pivots: rank 0 of a cluster runs it alone
-  if (sm.crank == 0) l2_gj_inverse<2>(Gc, NP, KD, sm, piv_global);
-  if (sm.cs > 1) l2_cluster_sync(sm.cs);
+  if (!CL || sm.crank == 0) l2_gj_inverse<2>(Gc, NP, KD, sm, piv_global);
+  if (CL && sm.cs > 1) l2_cluster_sync(sm.cs);
 }
 
 // ---- wrap from slice l to l-1 ------------------------------------------------------------------------------
-template <bool PHYS>
+template <bool PHYS, bool CL>
 __device__ void l2_wrap(double* __restrict__ Gc, double* __restrict__ Tc, int NP, const int8_t* hprev, const SweepParams& p, L2Smem& sm) {
   for (int spin = 0; spin < 2; ++spin) {
     double* G = Gc + (size_t)spin * NP * NP;
     double* T = Tc + (size_t)spin * NP * NP;
     L2Epilogue e1;
     e1.transposed_out = true;
-    l2_gemm(PHYS ? p.Eit : p.Et, G, T, NP, spin, e1, p, sm);           // T^T = (E G)^T   (or E^-1 G)
+    l2_gemm<CL>(PHYS ? p.Eit : p.Et, G, T, NP, spin, e1, p, sm);           // T^T = (E G)^T   (or E^-1 G)
     L2Epilogue e2;
     e2.hrow = hprev; e2.hcol = hprev;
     e2.row_inv = PHYS; e2.col_inv = !PHYS;
-    l2_gemm(T, PHYS ? p.E : p.Ei, G, NP, spin, e2, p, sm);              // G = D (E G E^-1) D^-1
+    l2_gemm<CL>(T, PHYS ? p.E : p.Ei, G, NP, spin, e2, p, sm);              // G = D (E G E^-1) D^-1
   }
 }
 
@@ -2011,15 +2131,15 @@ struct L2Params {
 
 // TMEM: 0 shared-memory slice path; 1 tensor-memory path, one column per thread (NP <= 256); 2 / 3 several columns per thread
 // (384 < NP <= 512: 2 x depth 24; 512 < NP <= 768: 3 x depth 16 where it fits; one CTA per SM at those sizes)
-template <bool EXACT, bool PHYS, int TMEM>
+template <bool EXACT, bool PHYS, int TMEM, bool CL = false>
 __global__ void __launch_bounds__(L2_THREADS, TMEM >= 2 ? 1 : 2) sweep_l2_kernel(const __grid_constant__ L2Params lp) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];       // 128-byte-swizzled TMA boxes need 1 KB-aligned stages
   const SweepParams& p = lp.p;
   const int NP = lp.NP, KD = lp.KD;
   L2Smem sm(smem_raw, NP, KD);
   sm.maps = &lp.maps;        // the launcher refuses to launch without valid tensor maps; the 1 KB alignment is checked below
-  sm.cs = lp.cluster; sm.crank = (int)(blockIdx.x % (unsigned)lp.cluster);       // cluster dimension = (cluster, 1, 1): rank = blockIdx.x % size
-  const int chain = blockIdx.x / lp.cluster, tid = threadIdx.x;
+  if (CL) { sm.cs = lp.cluster; sm.crank = (int)(blockIdx.x % (unsigned)lp.cluster); }      // cluster dimension = (size, 1, 1): rank = blockIdx.x % size
+  const int chain = CL ? (int)(blockIdx.x / (unsigned)lp.cluster) : (int)blockIdx.x, tid = threadIdx.x;
   const int N = p.n_sites, L = p.n_slices;
   int8_t* field = p.field + (size_t)chain * L * NP;
   double* Gc = p.G + (size_t)chain * 2 * NP * NP;
@@ -2046,14 +2166,14 @@ __global__ void __launch_bounds__(L2_THREADS, TMEM >= 2 ? 1 : 2) sweep_l2_kernel
 #else
 #define LQMC_KT(acc)
 #endif
-    if (p.do_recompute) l2_recompute(Gc, Tc, NP, KD, field, p.recompute_l0, p, sm, piv);
+    if (p.do_recompute) l2_recompute<CL>(Gc, Tc, NP, KD, field, p.recompute_l0, p, sm, piv);
     LQMC_KT(kt_rec)
     for (int step = p.step_lo; step < p.step_hi; ++step) {
       const int l = L - 1 - step;
       const long long base = (((long long)chain * p.buf_sweeps + p.buf_sweep0 + sweep) * p.buf_steps + (step - p.buf_step0)) * N;
       if (p.wrap_first && step == p.step_lo) {
         __syncthreads();
-        l2_wrap<PHYS>(Gc, Tc, NP, field + (size_t)l * NP, p, sm);
+        l2_wrap<PHYS, CL>(Gc, Tc, NP, field + (size_t)l * NP, p, sm);
       }
       if (p.do_propose) {
         __syncthreads();
@@ -2067,7 +2187,7 @@ __global__ void __launch_bounds__(L2_THREADS, TMEM >= 2 ? 1 : 2) sweep_l2_kernel
           sm.u[j] = u;
         }
         LQMC_KT(kt_wrap)
-        if (TMEM == 1) l2_propose_slice_tmem<EXACT, PHYS>(Gc, Tc, NP, sm, p, base, n_accepted, tm_base);
+        if (TMEM == 1) l2_propose_slice_tmem<EXACT, PHYS, CL>(Gc, Tc, NP, sm, p, base, n_accepted, tm_base);
         else if (TMEM == 2) l2_propose_slice_tmemx<EXACT, PHYS, 2, 24>(Gc, NP, sm, p, base, n_accepted, tm_base);
         else if (TMEM == 3) l2_propose_slice_tmemx<EXACT, PHYS, 3, 16>(Gc, NP, sm, p, base, n_accepted, tm_base);
         else l2_propose_slice<EXACT, PHYS, L2_MAXQ>(Gc, NP, KD, sm, p, base, n_accepted);
@@ -2077,14 +2197,14 @@ __global__ void __launch_bounds__(L2_THREADS, TMEM >= 2 ? 1 : 2) sweep_l2_kernel
       }
       if (p.do_wrap && l > 0 && !(p.skip_last_wrap && step == p.step_hi - 1)) {
         __syncthreads();
-        l2_wrap<PHYS>(Gc, Tc, NP, field + (size_t)(l - 1) * NP, p, sm);
+        l2_wrap<PHYS, CL>(Gc, Tc, NP, field + (size_t)(l - 1) * NP, p, sm);
         LQMC_KT(kt_wrap)
       }
     }
 #ifdef LQMC_PHASE_CLOCKS
     if (tid == 0 && p.do_recompute) { double* ob = p.obs_sum + (size_t)chain * 3 * N; ob[16] = (double)kt_rec; ob[17] = (double)kt_slice; ob[18] = (double)kt_wrap; }
 #endif
-    if (p.measure && sm.crank == 0) {
+    if (p.measure && (!CL || sm.crank == 0)) {
       __syncthreads();
       for (int spin = 0; spin < 2; ++spin) {
         const double* G = Gc + (size_t)spin * NP * NP;
@@ -2100,9 +2220,9 @@ __global__ void __launch_bounds__(L2_THREADS, TMEM >= 2 ? 1 : 2) sweep_l2_kernel
       if (tid == 0) p.n_meas[chain] += 1;
       __syncthreads();
     }
-    if (sm.cs > 1) l2_cluster_sync(sm.cs);        // rank 0 has read G for the measurement before the next sweep's product overwrites it
+    if (CL && sm.cs > 1) l2_cluster_sync(sm.cs);  // rank 0 has read G for the measurement before the next sweep's product overwrites it
   }
-  if (tid == 0 && n_accepted && sm.crank == 0) p.n_acc[chain] += n_accepted;
+  if (tid == 0 && n_accepted && (!CL || sm.crank == 0)) p.n_acc[chain] += n_accepted;
   if (TMEM == 1) tmem_free_cta(tm_base);
   if (TMEM >= 2) tmem_free_cta_x(tm_base);
 }
@@ -2219,18 +2339,20 @@ inline int launch_l2(L2Workspace& w, const SweepParams& p, int np, uint32_t flag
 #endif
     return 1;
   };
-  auto go = [&](auto kernel) -> int {
-    const int cs = pick_cluster(kernel);
+  // kernel: one CTA per chain; kernel_cl: the same kernel with the cluster code compiled in (nullptr where it does not exist)
+  auto go = [&](auto kernel, auto kernel_cl) -> int {
+    int cs = 1;
+    if constexpr (!std::is_same_v<decltype(kernel_cl), std::nullptr_t>) cs = pick_cluster(kernel_cl);
     lp.cluster = cs;
     w.last_cluster = cs;
-    cudaError_t e;
+    cudaError_t e = cudaSuccess;
     if (cs > 1) {
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3((unsigned)(p.n_chains * cs)); cfg.blockDim = dim3(L2_THREADS); cfg.dynamicSmemBytes = smem_cluster; cfg.stream = s;
       cudaLaunchAttribute at[1];
       at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
       cfg.attrs = at; cfg.numAttrs = 1;
-      e = cudaLaunchKernelEx(&cfg, kernel, lp);
+      if constexpr (!std::is_same_v<decltype(kernel_cl), std::nullptr_t>) e = cudaLaunchKernelEx(&cfg, kernel_cl, lp);
     } else {
       e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.smem);
       if (e == cudaSuccess) {
@@ -2244,10 +2366,17 @@ inline int launch_l2(L2Workspace& w, const SweepParams& p, int np, uint32_t flag
   };
   auto pick = [&](auto tm) -> int {
     constexpr int TM = decltype(tm)::value;
-    if (exact && !phys) return go(sweep_l2_kernel<true, false, TM>);
-    if (!exact && !phys) return go(sweep_l2_kernel<false, false, TM>);
-    if (exact && phys) return go(sweep_l2_kernel<true, true, TM>);
-    return go(sweep_l2_kernel<false, true, TM>);
+    if constexpr (TM == 1) {          // the cluster variant exists for the NP <= 256 tensor-memory path only
+      if (exact && !phys) return go(sweep_l2_kernel<true, false, 1, false>, sweep_l2_kernel<true, false, 1, true>);
+      if (!exact && !phys) return go(sweep_l2_kernel<false, false, 1, false>, sweep_l2_kernel<false, false, 1, true>);
+      if (exact && phys) return go(sweep_l2_kernel<true, true, 1, false>, sweep_l2_kernel<true, true, 1, true>);
+      return go(sweep_l2_kernel<false, true, 1, false>, sweep_l2_kernel<false, true, 1, true>);
+    } else {
+      if (exact && !phys) return go(sweep_l2_kernel<true, false, TM, false>, nullptr);
+      if (!exact && !phys) return go(sweep_l2_kernel<false, false, TM, false>, nullptr);
+      if (exact && phys) return go(sweep_l2_kernel<true, true, TM, false>, nullptr);
+      return go(sweep_l2_kernel<false, true, TM, false>, nullptr);
+    }
   };
   switch (lp.use_tmem) {
     case 1: return pick(std::integral_constant<int, 1>());
