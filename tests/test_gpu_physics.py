@@ -141,7 +141,12 @@ def test_stabilised_recompute_matches_oracle(case):
 @pytest.mark.parametrize("case", [("square", 2, 4.0, 2.0, 20, 5, 3), ("square", 4, 4.0, 4.0, 40, 8, 2), ("ring", 64, 8.0, 8.0, 80, 10, 1),
                                    ("square", 4, 4.0, 2.0, 20, 8, 2),       # ragged: segments of 8, 8, 4 slices
                                    ("square", 10, 4.0, 1.0, 10, 4, 2),      # N = 100: large-lattice kernel, segments 4, 4, 2
-                                   ("square", 3, 4.0, 2.0, 20, 20, 2)])     # one segment = stabilised sweep start only
+                                   ("square", 3, 4.0, 2.0, 20, 20, 2),      # one segment = stabilised sweep start only
+                                   # the benchmarked sizes (round 2): two-sided combine + wrap_first / skip_last_wrap segmentation at
+                                   # N = 256 (BASELINE configs[3] lattice; 1 chain runs on a cluster of 8 CTAs, 2 chains on 8 as well)
+                                   # and N = 576 (configs[4] lattice, multi-column tensor-memory slice path)
+                                   ("square", 16, 4.0, 2.4, 24, 8, 2),
+                                   ("square", 24, 6.0, 1.6, 16, 8, 1)])
 def test_stabilised_physics_sweep_matches_oracle(case):
     """Physics-mode sweeps with `stab_every`: G rebuilt by QR/UDV at the top of every segment, wraps inside.
     Same decisions as the oracle's `physics_sweep(stab_every=k)` on the same uniforms, G(0) within 1e-8."""
