@@ -1738,12 +1738,26 @@ __device__ __forceinline__ void tmem_free_cta_x(uint32_t base) {
 // loaded give CPT x 8 independent multiply-subtract chains per thread and 1 / CPT of the shared-memory loads per update.
 // The c histories of all columns (CPT x KDX doubles) live in registers for the pass - these kernels run one CTA per SM and
 // may use 255 registers.
+// (r2) Branch-free like the two-column flush: updates past nd are applied with e = 0 (rows nd .. KDX-1 of U3 are zeroed before a partial
+// flush) and c = 0 (selected at load time), so the fully unrolled update loop has no per-update branch and the compiler schedules
+// the shared-memory loads of e ahead of the multiply-subtract chains.  The threads that own the L2_COLWIN columns after the flush
+// point also store them transposed into Tc (8 consecutive rows = 64 contiguous bytes per thread and chunk): the builder's column of
+// G0 becomes a coalesced read instead of an NP-line gather.
 template <bool EXACT, int CPT, int KDX>
-__device__ void l2_flush_tmemx(double* __restrict__ Gc, int NP, int nd, const double* __restrict__ U3, uint32_t tm_my) {
+__device__ void l2_flush_tmemx(double* __restrict__ Gc, int NP, int nd, double* __restrict__ U3, uint32_t tm_my, double* __restrict__ Tc, int wlo) {
   const int tid = threadIdx.x;
-  bool jv[CPT];
+  bool jv[CPT], jw[CPT];
 #pragma unroll
-  for (int q = 0; q < CPT; ++q) jv[q] = tid + L2_THREADS * q < NP;       // warp-uniform: NP is a multiple of 64
+  for (int q = 0; q < CPT; ++q) {
+    jv[q] = tid + L2_THREADS * q < NP;       // warp-uniform: NP is a multiple of 64
+    jw[q] = jv[q] && (unsigned)(tid + L2_THREADS * q - wlo) < (unsigned)L2_COLWIN;
+  }
+  if (nd < KDX) {
+    for (int spin = 0; spin < 2; ++spin)
+      for (int m = nd; m < KDX; ++m)
+        for (int r = tid; r < NP; r += L2_THREADS) U3[((size_t)spin * KDX + m) * NP + r] = 0.0;
+    __syncthreads();
+  }
   for (int spin = 0; spin < 2; ++spin) {
     double cj[CPT][KDX];
 #pragma unroll
@@ -1753,9 +1767,10 @@ __device__ void l2_flush_tmemx(double* __restrict__ Gc, int NP, int nd, const do
         double v[8];
         tmem_ld_f64x8(tm_my + 2 * ((2 * q + spin) * KDX + m0), v);
 #pragma unroll
-        for (int t = 0; t < 8; ++t) cj[q][m0 + t] = v[t];
+        for (int t = 0; t < 8; ++t) cj[q][m0 + t] = (m0 + t < nd) ? v[t] : 0.0;
       }
     double* const col = Gc + (size_t)spin * NP * NP + tid;
+    double* const colT = Tc + (size_t)spin * NP * NP + (size_t)tid * NP;
     const double* const Us = U3 + (size_t)spin * KDX * NP;
     double nxt[CPT][8];
 #pragma unroll
@@ -1776,31 +1791,52 @@ __device__ void l2_flush_tmemx(double* __restrict__ Gc, int NP, int nd, const do
       }
 #pragma unroll
       for (int m = 0; m < KDX; ++m) {
-        if (m < nd) {
-          const double* ur = Us + (size_t)m * NP + r0;
+        const double* ur = Us + (size_t)m * NP + r0;
 #pragma unroll
-          for (int r = 0; r < 8; r += 2) {
-            const double2 e = *reinterpret_cast<const double2*>(ur + r);
+        for (int r = 0; r < 8; r += 2) {
+          const double2 e = *reinterpret_cast<const double2*>(ur + r);
 #pragma unroll
-            for (int q = 0; q < CPT; ++q) {
-              g[q][r] = rank1<EXACT>(g[q][r], e.x, cj[q][m]);
-              g[q][r + 1] = rank1<EXACT>(g[q][r + 1], e.y, cj[q][m]);
-            }
+          for (int q = 0; q < CPT; ++q) {
+            g[q][r] = rank1<EXACT>(g[q][r], e.x, cj[q][m]);
+            g[q][r + 1] = rank1<EXACT>(g[q][r + 1], e.y, cj[q][m]);
           }
         }
       }
 #pragma unroll
-      for (int q = 0; q < CPT; ++q)
+      for (int q = 0; q < CPT; ++q) {
 #pragma unroll
         for (int r = 0; r < 8; ++r)
           if (jv[q]) col[(size_t)(r0 + r) * NP + L2_THREADS * q] = g[q][r];
+        if (jw[q]) {
+          double* dst = colT + (size_t)(L2_THREADS * q) * NP + r0;
+#pragma unroll
+          for (int r = 0; r < 8; r += 2) *reinterpret_cast<double2*>(dst + r) = make_double2(g[q][r], g[q][r + 1]);
+        }
+      }
     }
   }
   __syncthreads();
 }
 
+// columns [c_lo, c_lo + L2_COLWIN) of both spins, transposed into Tc - any NP (the window of a slice's first flips)
+__device__ __forceinline__ void l2_colwin_init_np(const double* __restrict__ Gc, double* __restrict__ Tc, int NP, int c_lo) {
+  const int tid = threadIdx.x, nb = NP / 32;
+  for (int piece = tid; piece < 2 * L2_COLWIN * nb; piece += L2_THREADS) {
+    const int c = c_lo + piece % L2_COLWIN, rb = (piece / L2_COLWIN) % nb, spin = piece / (L2_COLWIN * nb);
+    if (c >= NP) continue;
+    const double* src = Gc + (size_t)spin * NP * NP + (size_t)(32 * rb) * NP + c;
+    double* dst = Tc + (size_t)spin * NP * NP + (size_t)c * NP + 32 * rb;
+#pragma unroll 4
+    for (int r = 0; r < 32; r += 4) {
+      const double a0 = src[(size_t)r * NP], a1 = src[(size_t)(r + 1) * NP], a2 = src[(size_t)(r + 2) * NP], a3 = src[(size_t)(r + 3) * NP];
+      *reinterpret_cast<double2*>(dst + r) = make_double2(a0, a1);
+      *reinterpret_cast<double2*>(dst + r + 2) = make_double2(a2, a3);
+    }
+  }
+}
+
 template <bool EXACT, bool PHYS, int CPT, int KDX>
-__device__ void l2_propose_slice_tmemx(double* __restrict__ Gc, int NP, L2Smem& sm, const SweepParams& p, long long trace_base,
+__device__ void l2_propose_slice_tmemx(double* __restrict__ Gc, double* __restrict__ Tc, int NP, L2Smem& sm, const SweepParams& p, long long trace_base,
                                        int& n_accepted, uint32_t tm_base) {
   static_assert(KDX % 8 == 0 && 8 * CPT * KDX <= L2_TMEMX_COLS && 2 * KDX <= 62, "TMEM windows / history slots");
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1810,6 +1846,8 @@ __device__ void l2_propose_slice_tmemx(double* __restrict__ Gc, int NP, L2Smem& 
   const uint32_t tm_my = tm_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)((warp >> 2) * 4 * CPT * KDX);
   for (int spin = 0; spin < 2; ++spin)
     for (int q = tid; q < NP; q += L2_THREADS) sm.d[spin * NP + q] = Gc[(size_t)spin * NP * NP + (size_t)q * NP + q];
+  l2_colwin_init_np(Gc, Tc, NP, 0);              // transposed copy of the first L2_COLWIN columns (see l2_flush_tmemx)
+  int wlo = 0;
   __syncthreads();
   int nd = 0, i0 = 0, cur = 0;
   while (i0 < N) {
@@ -1852,7 +1890,9 @@ __device__ void l2_propose_slice_tmemx(double* __restrict__ Gc, int NP, L2Smem& 
       for (int spin = 0; spin < 2; ++spin) {
         const double* G = Gc + (size_t)spin * NP * NP;
         row[q][spin] = (j < NP) ? G[(size_t)is * NP + j] : 0.0;
-        col[q][spin] = (j < NP) ? G[(size_t)j * NP + is] : 0.0;
+        col[q][spin] = (j < NP) ? (((unsigned)(is - wlo) < (unsigned)L2_COLWIN) ? Tc[(size_t)spin * NP * NP + (size_t)is * NP + j]
+                                                                                 : G[(size_t)j * NP + is])
+                                : 0.0;
       }
     }
     // the warp that owns site `is` publishes that site's c history
@@ -1921,10 +1961,10 @@ __device__ void l2_propose_slice_tmemx(double* __restrict__ Gc, int NP, L2Smem& 
     cur ^= 1;
     __syncthreads();
     if (tid == 0) sm.h[is] = (int8_t)(-hs);     // after the barrier: no warp is still scanning site `is`
-    if (nd == KDX) { l2_flush_tmemx<EXACT, CPT, KDX>(Gc, NP, nd, U3, tm_my); nd = 0; }
+    if (nd == KDX) { wlo = is + 1; l2_flush_tmemx<EXACT, CPT, KDX>(Gc, NP, nd, U3, tm_my, Tc, wlo); nd = 0; }
     i0 = is + 1;
   }
-  if (nd > 0) l2_flush_tmemx<EXACT, CPT, KDX>(Gc, NP, nd, U3, tm_my);
+  if (nd > 0) l2_flush_tmemx<EXACT, CPT, KDX>(Gc, NP, nd, U3, tm_my, Tc, NP);
 }
 
 // ---- Gauss-Jordan inverse in memory (both spins in lockstep, in place), partial pivoting, delayed updates ----------
@@ -2188,8 +2228,8 @@ __global__ void __launch_bounds__(L2_THREADS, TMEM >= 2 ? 1 : 2) sweep_l2_kernel
         }
         LQMC_KT(kt_wrap)
         if (TMEM == 1) l2_propose_slice_tmem<EXACT, PHYS, CL>(Gc, Tc, NP, sm, p, base, n_accepted, tm_base);
-        else if (TMEM == 2) l2_propose_slice_tmemx<EXACT, PHYS, 2, 24>(Gc, NP, sm, p, base, n_accepted, tm_base);
-        else if (TMEM == 3) l2_propose_slice_tmemx<EXACT, PHYS, 3, 16>(Gc, NP, sm, p, base, n_accepted, tm_base);
+        else if (TMEM == 2) l2_propose_slice_tmemx<EXACT, PHYS, 2, 24>(Gc, Tc, NP, sm, p, base, n_accepted, tm_base);
+        else if (TMEM == 3) l2_propose_slice_tmemx<EXACT, PHYS, 3, 16>(Gc, Tc, NP, sm, p, base, n_accepted, tm_base);
         else l2_propose_slice<EXACT, PHYS, L2_MAXQ>(Gc, NP, KD, sm, p, base, n_accepted);
         __syncthreads();
         for (int j = tid; j < NP; j += L2_THREADS) field[(size_t)l * NP + j] = sm.h[j];
