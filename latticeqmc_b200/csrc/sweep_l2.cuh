@@ -1332,6 +1332,9 @@ __device__ __noinline__ void l2_flush_tmem2_dmma(double* __restrict__ Gc, int nd
 #ifndef LQMC_L2_PFD
 #define LQMC_L2_PFD 0
 #endif
+#ifndef LQMC_L2_SPEC
+#define LQMC_L2_SPEC 0
+#endif
 // Two chains share an SM (2 CTAs) and one FP64 pipe.  A flush wants the whole pipe for ~100 K clocks, a build hardly any of it:
 // the pair runs fastest in anti-phase (one chain flushes while the other builds its next 24 flips), but nothing makes two
 // independent CTAs fall into that rhythm - whatever offset they start with persists, and when both flush at once both then
@@ -1462,6 +1465,14 @@ __device__ __noinline__ int l2_propose_slice_tmem_sub(const L2SliceArgs a) {
   while (i0 < N) {
     const double* dcur = sm.d + cur * 2 * NP;
     double* dnxt = sm.d + (cur ^ 1) * 2 * NP;
+#if LQMC_L2_SPEC
+    // Speculative loads: the very next site is the next accepted one with probability ~0.6.  Its G0 row / column are requested
+    // BEFORE the scan decides - the registers live only inside this iteration (the loop-carried prefetch slots of PF > 0 are what
+    // ptxas turned into blocking local-memory traffic) - so the scan hides part of their latency; a miss reloads.
+    double srow[2], scol[2];
+    const int spec = i0;
+    load_site(spec, srow, scol);
+#endif
     const int i = i0 + lane;
     bool acc = false;
     double gu = 0.0, gd = 0.0, ratio = 0.0;
@@ -1502,10 +1513,16 @@ __device__ __noinline__ int l2_propose_slice_tmem_sub(const L2SliceArgs a) {
       for (int k = 0; k < PF; ++k)
         if (k == dpf) { row[0] = prow[k][0]; row[1] = prow[k][1]; col[0] = pcol[k][0]; col[1] = pcol[k][1]; }
     } else {
-      load_site(is, row, col);
-#ifdef LQMC_PHASE_CLOCKS
-      ++n_miss;
+#if LQMC_L2_SPEC
+      if (is == spec) { row[0] = srow[0]; row[1] = srow[1]; col[0] = scol[0]; col[1] = scol[1]; }
+      else
 #endif
+      {
+        load_site(is, row, col);
+#ifdef LQMC_PHASE_CLOCKS
+        ++n_miss;
+#endif
+      }
     }
     if (PF >= 1) {
       // slots for sites is + 1 .. is + PF: keep what is already there (shifted), load the rest
