@@ -115,7 +115,8 @@ int lqmc_sweep_submit(lqmc_engine* e, int n_sweeps, const double* uniforms, uint
  * old_det is initialised from get_m(0, +-1) at the start of the call (warmup_loop_det lqmc.py:261-270;
  * measure_loop_det :272-299) and carried through the n_sweeps sweeps; with measure != 0, inv(get_m(0, +-1)) is
  * added to the accumulators after every sweep (lqmc.py:293-297).  uniforms / seed / trace as in lqmc_sweep.
- * Independent of the engine's mode flag.  N <= 64 (LQMC_ERR_UNSUPPORTED above): it is a validation tool. */
+ * Independent of the engine's mode flag.  N <= 64: matrices in shared memory; larger lattices: the same code on a global-memory workspace (a validation tool, O(N^3) per
+ * proposal); LQMC_ERR_UNSUPPORTED only if the field of one chain (N L bytes) does not fit shared memory. */
 int lqmc_sweep_det(lqmc_engine* e, int n_sweeps, const double* uniforms, uint64_t seed, int measure);
 /* old_det of every chain after the last lqmc_sweep_det (what _update_step_det returns, lqmc.py:259): f64 [chain]. */
 int lqmc_get_det(lqmc_engine* e, double* det_old);

@@ -61,6 +61,7 @@ struct lqmc_engine {
   long long* dNmeas = nullptr;
   long long* dNacc = nullptr;
   double* dDetOld = nullptr;       // det mode: old_det per chain (lqmc.py:236-259)
+  double* dDetWork = nullptr;      // det mode, N > 64: [chain][4][N][N] matrices
   double* dUni = nullptr;   size_t uniCap = 0;     // staged host uniforms
   double* dTrRatio = nullptr; uint8_t* dTrAcc = nullptr; size_t trCap = 0; size_t trCount = 0;
   lqmc::L2Workspace l2;
@@ -652,7 +653,7 @@ int lqmc_create(lqmc_engine** out, int device, int n_sites, int n_slices, int n_
 void lqmc_destroy(lqmc_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
-  void* ptrs[] = {e->dE, e->dEt, e->dEi, e->dEit, e->dField, e->dFieldRaw, e->dBad, e->dG, e->dGsum, e->dObs, e->dNmeas, e->dNacc, e->dUni, e->dTrRatio, e->dTrAcc, e->dDetOld};
+  void* ptrs[] = {e->dE, e->dEt, e->dEi, e->dEit, e->dField, e->dFieldRaw, e->dBad, e->dG, e->dGsum, e->dObs, e->dNmeas, e->dNacc, e->dUni, e->dTrRatio, e->dTrAcc, e->dDetOld, e->dDetWork};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   lqmc::l2_free(e->l2);
@@ -857,13 +858,13 @@ int lqmc_sweep_det(lqmc_engine* e, int n_sweeps, const double* uniforms, uint64_
   if (!e) return fail(LQMC_ERR_INVALID, "engine is NULL");
   if (n_sweeps < 0) return fail(LQMC_ERR_INVALID, "n_sweeps = %d is negative", n_sweeps);
   if (n_sweeps == 0) return LQMC_OK;
-  if (e->N > lqmc::DET_MAX_N)
-    return fail(LQMC_ERR_UNSUPPORTED, "det mode keeps its matrices in shared memory: N = %d > %d", e->N, lqmc::DET_MAX_N);
   const size_t smem = lqmc::det_smem_bytes(e->N, e->L);
   if (smem > 227 * 1024) return fail(LQMC_ERR_UNSUPPORTED, "det mode needs %zu bytes of shared memory (N = %d, L = %d)", smem, e->N, e->L);
   CU(cudaSetDevice(e->device));
   cudaStream_t s = e->stream;
   if (!e->dDetOld) CU(cudaMalloc(&e->dDetOld, (size_t)e->C * sizeof(double)));
+  if (e->N > lqmc::DET_MAX_N && !e->dDetWork)   // large lattices: the four N x N matrices of a chain live in global memory
+    CU(cudaMalloc(&e->dDetWork, (size_t)e->C * 4 * e->N * e->N * sizeof(double)));
   const double* d_u = nullptr;
   if (uniforms) {
     int rc = stage_uniforms(e, uniforms, (size_t)e->C * n_sweeps * e->L * e->N, s);
@@ -880,6 +881,7 @@ int lqmc_sweep_det(lqmc_engine* e, int n_sweeps, const double* uniforms, uint64_
   p.buf_sweeps = n_sweeps; p.det_old = e->dDetOld; p.n_acc = e->dNacc;
   if (e->flags & LQMC_TRACE) { p.tr_ratio = e->dTrRatio; p.tr_acc = e->dTrAcc; }
   p.exp_pl = e->hs[0]; p.exp_ml = e->hs[1];
+  p.work = e->dDetWork;
   // measured: one launch per sweep, each followed by G = inv(get_m(0)) + accumulation (the sweep kernels' recompute);
   // unmeasured: all sweeps in one launch
   const int per_launch = measure ? 1 : n_sweeps;

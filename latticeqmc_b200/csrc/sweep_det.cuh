@@ -7,7 +7,9 @@
 // for all N proposals of a slice: it is built once per slice (L-1 GEMMs) and every proposal costs one GEMM and one LU per
 // spin - the same floating-point operations in the same association order as rebuilding everything, L times cheaper.
 //
-// One CTA per chain, 512 threads = 2 spins x 256; all matrices (N <= 64) live in shared memory.  det = product of the
+// One CTA per chain, 512 threads = 2 spins x 256.  N <= 64: all matrices live in shared memory.  Larger lattices (the
+// reference has no size limit, it is just O(L N^3) per proposal): the same code on a per-chain global-memory workspace
+// (4 N^2 doubles, L2-resident) and exp(-dtau K) read in place - a validation tool, not a roofline kernel.  det = product of the
 // LU pivots with partial pivoting (first entry of largest magnitude, the getrf rule); NumPy forms sign * exp(sum log|u_ii|)
 // instead (umath_linalg det), so ratios agree to ~1e-13 relative, not bitwise.
 #pragma once
@@ -19,7 +21,7 @@ namespace lqmc {
 
 constexpr int DET_THREADS = 512;
 constexpr int DET_TPS = 256;       // threads per spin
-constexpr int DET_MAX_N = 64;
+constexpr int DET_MAX_N = 64;     // largest N with the matrices in shared memory
 
 struct DetParams {
   int n_sites, n_slices, NPf, ldE;
@@ -35,26 +37,28 @@ struct DetParams {
   double* tr_ratio;        // [chain][buf_sweeps][L][N] or nullptr
   uint8_t* tr_acc;
   double exp_pl, exp_ml;
+  double* work;            // nullptr: matrices in shared memory (N <= DET_MAX_N); else [chain][4][N][N] global workspace
 };
 
 inline size_t det_smem_bytes(int N, int L) {
-  return ((size_t)5 * N * N + 8) * sizeof(double) + 8 * sizeof(int) + (size_t)N * L + 16;
+  const size_t mats = N <= DET_MAX_N ? (size_t)5 * N * N : 0;
+  return (mats + 8) * sizeof(double) + 8 * sizeof(int) + (size_t)N * L + 16;
 }
 
 __device__ __forceinline__ void det_bar(int spin) { asm volatile("bar.sync %0, %1;" ::"r"(1 + spin), "n"(DET_TPS) : "memory"); }
 
 // out = in . (E diag(v_l)) for this spin (in == nullptr: the scalar 1 of get_m's first step, lqmc.py:179-183)
-__device__ __forceinline__ void det_gemm(double* __restrict__ out, const double* __restrict__ in, const double* __restrict__ Es,
+__device__ __forceinline__ void det_gemm(double* __restrict__ out, const double* __restrict__ in, const double* __restrict__ Es, int ldE,
                                          const int8_t* __restrict__ hl, int N, int spin, int t, double exp_pl, double exp_ml) {
   for (int e = t; e < N * N; e += DET_TPS) {
     const int r = e / N, c = e - r * N;
     const double v = ((hl[c] > 0) != (spin != 0)) ? exp_ml : exp_pl;
     if (in == nullptr) {
-      out[e] = __dmul_rn(Es[e], v);
+      out[e] = __dmul_rn(Es[r * ldE + c], v);
     } else {
       double acc = 0.0;
       const double* row = in + r * N;
-      for (int k = 0; k < N; ++k) acc = fma(row[k], __dmul_rn(Es[k * N + c], v), acc);
+      for (int k = 0; k < N; ++k) acc = fma(row[k], __dmul_rn(Es[k * ldE + c], v), acc);
       out[e] = acc;
     }
   }
@@ -83,14 +87,14 @@ __device__ double det_lu(double* __restrict__ A, int N, int spin, int t, int* pi
     const int pr = pivrow[spin];
     if (pr != k) {
       det = -det;
-      if (t < N) { const double x = A[k * N + t]; A[k * N + t] = A[pr * N + t]; A[pr * N + t] = x; }
+      for (int c = t; c < N; c += DET_TPS) { const double x = A[k * N + c]; A[k * N + c] = A[pr * N + c]; A[pr * N + c] = x; }
     }
     det_bar(spin);
     const double akk = A[k * N + k];
     det = __dmul_rn(det, akk);
     const int n = N - k - 1;
     if (akk != 0.0 && n > 0) {
-      if (t < n) A[(k + 1 + t) * N + k] = A[(k + 1 + t) * N + k] / akk;
+      for (int r = t; r < n; r += DET_TPS) A[(k + 1 + r) * N + k] = A[(k + 1 + r) * N + k] / akk;
       det_bar(spin);
       for (int e = t; e < n * n; e += DET_TPS) {
         const int rr = e / n, cc = e - rr * n;
@@ -106,16 +110,20 @@ __device__ double det_lu(double* __restrict__ A, int N, int spin, int t, int* pi
 __global__ void __launch_bounds__(DET_THREADS, 1) sweep_det_kernel(const DetParams p) {
   extern __shared__ __align__(16) unsigned char det_smem_raw[];
   const int N = p.n_sites, L = p.n_slices, NN = N * N;
-  double* Es = reinterpret_cast<double*>(det_smem_raw);     // [N][N]
-  double* bufA = Es + NN;                                   // [2 spin][N][N] prefix product of the first L-1 factors
-  double* bufM = bufA + 2 * NN;                             // [2 spin][N][N] ping-pong partner / LU workspace
-  double* dets = bufM + 2 * NN;                             // [2]
-  int* pivrow = reinterpret_cast<int*>(dets + 8);           // [2]
-  int8_t* hf = reinterpret_cast<int8_t*>(pivrow + 8);       // [L][N]
   const int chain = blockIdx.x, tid = threadIdx.x;
   const int spin = tid / DET_TPS, t = tid % DET_TPS;
+  const bool glob = p.work != nullptr;
+  double* sm_d = reinterpret_cast<double*>(det_smem_raw);
+  const double* Es = glob ? p.E : sm_d;                                          // [N][N], row stride ldE
+  const int ldE = glob ? p.ldE : N;
+  double* bufA = glob ? p.work + (size_t)chain * 4 * NN : sm_d + NN;             // [2 spin][N][N] prefix product of the first L-1 factors
+  double* bufM = bufA + 2 * NN;                                                  // [2 spin][N][N] ping-pong partner / LU workspace
+  double* dets = glob ? sm_d : bufM + 2 * NN;                                    // [2]
+  int* pivrow = reinterpret_cast<int*>(dets + 8);           // [2]
+  int8_t* hf = reinterpret_cast<int8_t*>(pivrow + 8);       // [L][N]
   int8_t* field = p.field + (size_t)chain * L * p.NPf;
-  for (int e = tid; e < NN; e += DET_THREADS) Es[e] = p.E[(size_t)(e / N) * p.ldE + (e % N)];
+  if (!glob)
+    for (int e = tid; e < NN; e += DET_THREADS) sm_d[e] = p.E[(size_t)(e / N) * p.ldE + (e % N)];
   for (int e = tid; e < N * L; e += DET_THREADS) hf[e] = field[(size_t)(e / N) * p.NPf + (e % N)];
   __syncthreads();
   double* A = bufA + spin * NN;
@@ -128,7 +136,7 @@ __global__ void __launch_bounds__(DET_THREADS, 1) sweep_det_kernel(const DetPara
     const double* prev = nullptr;
     for (int m = 0; m < nf; ++m) {
       const int l = ((l0 - 1 - m) % L + L) % L;
-      det_gemm(cur, prev, Es, hf + l * N, N, spin, t, p.exp_pl, p.exp_ml);
+      det_gemm(cur, prev, Es, ldE, hf + l * N, N, spin, t, p.exp_pl, p.exp_ml);
       det_bar(spin);
       prev = cur;
       cur = (cur == A) ? M : A;
@@ -136,9 +144,9 @@ __global__ void __launch_bounds__(DET_THREADS, 1) sweep_det_kernel(const DetPara
   };
   // finish(l0): M = I + prefix . B_{l0}; returns det M_up * det M_dn to every thread
   auto finish = [&](int l0) -> double {
-    det_gemm(M, (L > 1) ? A : nullptr, Es, hf + l0 * N, N, spin, t, p.exp_pl, p.exp_ml);
+    det_gemm(M, (L > 1) ? A : nullptr, Es, ldE, hf + l0 * N, N, spin, t, p.exp_pl, p.exp_ml);
     det_bar(spin);
-    if (t < N) M[t * N + t] = __dadd_rn(M[t * N + t], 1.0);
+    for (int r = t; r < N; r += DET_TPS) M[r * N + r] = __dadd_rn(M[r * N + r], 1.0);
     det_bar(spin);
     const double d = det_lu(M, N, spin, t, pivrow);
     if (t == 0) dets[spin] = d;
@@ -176,7 +184,7 @@ __global__ void __launch_bounds__(DET_THREADS, 1) sweep_det_kernel(const DetPara
         if (tid == 0 && p.tr_ratio != nullptr) { p.tr_ratio[base + i] = ratio; p.tr_acc[base + i] = acc ? 1 : 0; }
       }
       __syncthreads();
-      if (tid < N) field[(size_t)l * p.NPf + tid] = hf[l * N + tid];
+      for (int c = tid; c < N; c += DET_THREADS) field[(size_t)l * p.NPf + c] = hf[l * N + c];
     }
   }
   if (tid == 0) {

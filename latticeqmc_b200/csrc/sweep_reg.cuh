@@ -34,6 +34,16 @@
 #include <stdint.h>
 #include "philox.h"
 
+// 1: propose_slice_delayed (rank-1 updates of a slice delayed, lane-parallel accept scan).  Bit-identical to the immediate path
+// and measured SLOWER (cfg2 3.37 vs 3.18 ms per sweep, cfg3 23.7 vs 22.2): both are bound by the per-flip chain of dependent
+// instructions at ~5 clocks each with 4 warps per scheduler, not by the tile update (profiles/r02j_*).
+#ifndef LQMC_REG_DELAYED
+#define LQMC_REG_DELAYED 0
+#endif
+#ifndef LQMC_REG_KD
+#define LQMC_REG_KD 16
+#endif
+
 namespace lqmc {
 
 struct SweepParams {
@@ -75,10 +85,13 @@ struct RegCfg {
   static constexpr int GMIN = GY < GX ? GY : GX;
   static constexpr int S = NP + 2;        // shared row stride in doubles: even (16-B vectors), odd/2 (banks)
   static constexpr int HS = TPS / NP;     // threads per matrix row in the inverse
+  static constexpr int KD = LQMC_REG_KD;  // delay depth of the rank-1 updates inside a slice (propose_slice_delayed)
   static constexpr size_t smem_bytes = (size_t(2) * NP * S + 2 * NP + 8 * NP + NP + 2 * WPS) * sizeof(double)
-                                       + (2 * WPS + 2 * NP) * sizeof(int) + 2 * NP;
+                                       + (2 * WPS + 2 * NP) * sizeof(int) + 2 * NP
+                                       + (LQMC_REG_DELAYED ? (size_t(4) * NP + size_t(4) * (KD + 2) * NP) * sizeof(double) : 0);
   static_assert(TR % 2 == 0 && TC % 2 == 0, "tiles are made of element pairs");
   static_assert(TPS % 32 == 0 && TPS >= NP && TPS % NP == 0, "thread grid");
+  static_assert(TPS >= 2 * NP, "a spin group rebuilds row and column of the flipped site with one thread per element");
 };
 
 template <class C>
@@ -93,6 +106,9 @@ struct RegSmem {
   int* piv;        // [2][NP]
   int8_t* h;       // [NP] field column of the slice being updated
   int8_t* hn;      // [NP] field column the wrap scales with
+  double* dh;      // [2 buf][2 spin][NP]     delayed path: diagonal as of the flip before the last one
+  double* eh;      // [2 spin][NP][KD+2]      delayed path: e vectors of the pending flips, site-major
+  double* ch;      // [2 spin][NP][KD+2]      c vectors
   __device__ explicit RegSmem(unsigned char* base) {
     constexpr int NP = C::NP, S = C::S, WPS = C::WPS;
     stage = reinterpret_cast<double*>(base);
@@ -105,6 +121,9 @@ struct RegSmem {
     piv = red_i + 2 * WPS;
     h = reinterpret_cast<int8_t*>(piv + 2 * NP);
     hn = h + NP;
+    dh = reinterpret_cast<double*>(hn + NP);
+    eh = dh + 4 * NP;
+    ch = eh + 2 * (C::KD + 2) * NP;
   }
 };
 
@@ -637,6 +656,203 @@ __device__ void propose_slice(double (&g)[C::TR][C::TC], RegSmem<C>& sm, const S
   }
 }
 
+// ---- the N proposals of one time slice, rank-1 updates delayed ------------------------------------------
+// Same arithmetic as propose_slice, different schedule.  Applying every accepted flip to the register tiles right
+// away puts a publish -> bar.sync -> 2*TR*TC FP64 instructions chain between two flips (2.3 K clocks per flip with
+// two CTAs per SM).  Here the (e, c) vectors of up to KD flips stay in shared memory, the register tiles keep the
+// Green's function G0 of the last flush (also mirrored row-major in `stage`), and a flip only needs row i and
+// column i of the CURRENT G:
+//     G[i][j] = (((G0[i][j] - e_0[i] c_0[j]) - e_1[i] c_1[j]) - ...)        one thread per element, 2*NP per spin
+// which is exactly the sequence of roundings the element would have seen in the tile (separate multiply and
+// subtract in exact arithmetic), so decisions, vectors and the flushed G are bit-identical to the undelayed path.
+// The flush applies the pending updates to the tiles back to back (no barrier in between: FP64-pipe-bound).
+//   * History layout: site-major, eh[site][m] / ch[site][m] with row stride HSTR = KD + 2 doubles: a thread's chain
+//     operands are contiguous (one 128-bit load per two updates, conflict-free at that stride), unused slots of a
+//     group of 8 are +0 (e = c = +0 changes no bit), so the chain is straight-line code of 8 or 16 updates that the
+//     compiler interleaves with the rest of the flip's arithmetic.
+//   * The accept scan is lane-parallel: a warp evaluates the ratios of 32 sites at once from the lazily updated
+//     diagonal (d as of the flip before the last one, folded with the last flip's vectors, both kept compact in
+//     sm.e / sm.c), the ballot finds the first accepted site, everything before it is rejected for free; every warp
+//     does this redundantly, so the decision is CTA-uniform without communication.  Each lane also forms the flip's
+//     denominator and its reciprocal for ITS site (SIMD: no more instructions than for one site), which takes the
+//     reciprocal off the post-accept critical path.
+template <class C>
+struct RegHist {
+  static constexpr int KD = C::KD, HSTR = KD + 2;
+  static_assert(KD == 8 || KD == 16, "chains of 8 or 16 updates");
+};
+
+template <int STEPS, bool EXACT>
+__device__ __forceinline__ double pending_chain(double x, const double* __restrict__ ea, const double* __restrict__ ca) {
+#pragma unroll
+  for (int m = 0; m < STEPS; m += 2) {
+    const double2 e2 = *reinterpret_cast<const double2*>(ea + m);
+    const double2 c2 = *reinterpret_cast<const double2*>(ca + m);
+    x = rank1<EXACT>(x, e2.x, c2.x);
+    x = rank1<EXACT>(x, e2.y, c2.y);
+  }
+  return x;
+}
+
+template <class C, bool EXACT>
+__device__ __forceinline__ void apply_pending(double (&g)[C::TR][C::TC], const double* __restrict__ eh, const double* __restrict__ ch,
+                                              int k, int ty, int tx) {
+  constexpr int TR = C::TR, TC = C::TC, HSTR = RegHist<C>::HSTR;
+  const double* er[TR];
+  const double* cr[TC];
+#pragma unroll
+  for (int a = 0; a < TR; ++a) er[a] = eh + row_of<C>(ty, a) * HSTR;
+#pragma unroll
+  for (int b = 0; b < TC; ++b) cr[b] = ch + col_of<C>(tx, b) * HSTR;
+  for (int m = 0; m < k; m += 2) {          // k odd: slot k holds +0
+    double2 e2[TR], c2[TC];
+#pragma unroll
+    for (int a = 0; a < TR; ++a) e2[a] = *reinterpret_cast<const double2*>(er[a] + m);
+#pragma unroll
+    for (int b = 0; b < TC; ++b) c2[b] = *reinterpret_cast<const double2*>(cr[b] + m);
+#pragma unroll
+    for (int a = 0; a < TR; ++a)
+#pragma unroll
+      for (int b = 0; b < TC; ++b) g[a][b] = rank1<EXACT>(g[a][b], e2[a].x, c2[b].x);
+#pragma unroll
+    for (int a = 0; a < TR; ++a)
+#pragma unroll
+      for (int b = 0; b < TC; ++b) g[a][b] = rank1<EXACT>(g[a][b], e2[a].y, c2[b].y);
+  }
+}
+
+#ifdef LQMC_PHASE_CLOCKS
+struct RegClocks { long long rec, slice, wrap, scan, build, flush, flips, scans, b_load, b_chain, b_vec, b_bar; };
+#define RCLK(...) __VA_ARGS__
+#else
+#define RCLK(...)
+#endif
+template <class C, bool EXACT, bool PHYS>
+__device__ void propose_slice_delayed(double (&g)[C::TR][C::TC], RegSmem<C>& sm, const SweepParams& p, long long trace_base,
+                                      int spin, int t, int ty, int tx, int& n_accepted
+#ifdef LQMC_PHASE_CLOCKS
+                                      , RegClocks& ck
+#endif
+                                      ) {
+  constexpr int NP = C::NP, S = C::S, KD = C::KD, HSTR = RegHist<C>::HSTR;
+  const int N = p.n_sites;
+  const int lane = threadIdx.x & 31;
+  double* stage = sm.stage + spin * NP * S;
+  double* eh = sm.eh + spin * NP * HSTR;
+  double* ch = sm.ch + spin * NP * HSTR;
+  store_tile<C>(stage, g, ty, tx);
+  store_diag<C>(sm.dh + spin * NP, g, ty, tx);
+  if (t < NP) { sm.e[spin * NP + t] = 0.0; sm.c[spin * NP + t] = 0.0; }
+  __syncthreads();
+  // cur: buffer of the diagonal (as of the flip before the last one) and of the last flip's compact (e, c)
+  int cur = 0, k = 0, i0 = 0;
+  while (i0 < N) {
+    // ---- scan: ratios of sites i0 .. i0+31 (lqmc.py:313-317), and this spin's denominator / reciprocal ----
+    RCLK(const long long c0 = clock64(); ck.scans += 1;)
+    const int i = i0 + lane;
+    bool acc = false;
+    double ratio = 0.0, den = 1.0, rcp = 1.0;       // den / rcp: parity 1 + c_i and its reciprocal; physics: Delta / R in rcp
+    int8_t h = 1;
+    if (i < N) {
+      const double* dc = sm.dh + cur * 2 * NP;
+      const double* el = sm.e + cur * 2 * NP;
+      const double* cl = sm.c + cur * 2 * NP;
+      h = sm.h[i];
+      const double gu = rank1<EXACT>(dc[i], el[i], cl[i]);
+      const double gd = rank1<EXACT>(dc[NP + i], el[NP + i], cl[NP + i]);
+      const double fu = (h > 0) ? p.f_p2 : p.f_m2;
+      const double fd = (h > 0) ? p.f_m2 : p.f_p2;
+      const double du = __dadd_rn(1.0, __dmul_rn(__dsub_rn(1.0, gu), fu));
+      const double dd = __dadd_rn(1.0, __dmul_rn(__dsub_rn(1.0, gd), fd));
+      ratio = __dmul_rn(du, dd);
+      acc = sm.u[i] <= ratio;
+      if (!PHYS) {
+        // parity: gamma_up = exp(-arg)-1, gamma_dn = exp(+arg)-1 (lqmc.py:320-323); denominator 1 + c_i
+        const double gamma = spin ? fu : fd;
+        den = __dadd_rn(1.0, __dadd_rn(__dmul_rn(-gamma, spin ? gd : gu), gamma));
+        rcp = __drcp_rn(den);
+      } else {
+        rcp = (spin ? fd : fu) / (spin ? dd : du);
+      }
+    }
+    const unsigned ball = __ballot_sync(0xffffffffu, acc);
+    const int nf = ball ? (__ffs(ball) - 1) : 31;
+    if (p.tr_ratio != nullptr && threadIdx.x < 32 && i < N && lane <= nf) {
+      p.tr_ratio[trace_base + i] = ratio;
+      p.tr_acc[trace_base + i] = acc ? 1 : 0;
+    }
+    if (!ball) { i0 += 32; RCLK(ck.scan += clock64() - c0;) continue; }
+    RCLK(const long long c1 = clock64(); ck.scan += c1 - c0;)
+    const int is = i0 + nf;
+    const int8_t hs = (int8_t)__shfl_sync(0xffffffffu, (int)h, nf);
+    den = __shfl_sync(0xffffffffu, den, nf);
+    rcp = __shfl_sync(0xffffffffu, rcp, nf);
+    // ---- build: row / column `is` of the current G, the flip's vectors into history slot k ----
+    const int nxt = cur ^ 1;
+    if (t < 2 * NP) {
+      const bool isrow = t < NP;
+      const int j = isrow ? t : t - NP;
+      double x = isrow ? stage[is * S + j] : stage[j * S + is];
+      const double* ea = eh + (isrow ? is : j) * HSTR;
+      const double* ca = ch + (isrow ? j : is) * HSTR;
+      RCLK(long long cb0 = clock64() + (__double_as_longlong(x) & 0); ck.b_load += cb0 - c1;)
+      if (k > 0) {
+        if (KD == 8 || k <= 8) x = pending_chain<8, EXACT>(x, ea, ca);
+        else x = pending_chain<KD, EXACT>(x, ea, ca);
+      }
+      RCLK(long long cb1 = clock64() + (__double_as_longlong(x) & 0); ck.b_chain += cb1 - cb0;)
+      double v;
+      if (!PHYS) {
+        if (isrow) {
+          const double gamma = ((hs > 0) != (spin != 0)) ? p.f_m2 : p.f_p2;     // spin ? fu : fd
+          v = __dmul_rn(-gamma, x);
+          if (j == is) v = __dadd_rn(v, gamma);
+        } else {
+          v = EXACT ? div_shared_rcp(x, den, rcp, div_safe(den)) : x * rcp;
+        }
+      } else {
+        // physics: G <- G - (e_i - G[:,i]) (Delta/R) G[i,:],  Delta = exp(2 sigma lamb h) - 1
+        v = isrow ? x : ((j == is) ? (1.0 - x) * rcp : -x * rcp);
+      }
+      double* hv = (isrow ? ch : eh) + j * HSTR + k;
+      *hv = v;
+      (isrow ? sm.c : sm.e)[(nxt * 2 + spin) * NP + j] = v;
+      if ((k & 7) == 0) {    // a new group of 8 slots: the unused ones read as +0
+        hv[1] = 0.0;
+#pragma unroll
+        for (int q = 2; q < 8; q += 2) *reinterpret_cast<double2*>(hv + q) = make_double2(0.0, 0.0);
+      }
+      if (isrow)   // the diagonal as of the previous flip (the new flip's vectors become the lazy part)
+        sm.dh[(nxt * 2 + spin) * NP + j] = rank1<EXACT>(sm.dh[(cur * 2 + spin) * NP + j], sm.e[(cur * 2 + spin) * NP + j],
+                                                        sm.c[(cur * 2 + spin) * NP + j]);
+    }
+    RCLK(const long long cb2 = clock64(); ck.b_vec += cb2 - c1;)
+    __syncthreads();
+    RCLK(ck.b_bar += clock64() - cb2;)
+    if (threadIdx.x == 0) sm.h[is] = -hs;   // after the barrier: slower warps were still scanning h[is]
+    ++n_accepted;
+    ++k; cur = nxt; i0 = is + 1;
+    RCLK(const long long c2 = clock64(); ck.build += c2 - c1; ck.flips += 1;)
+    if (k == KD && i0 < N) {
+      // ---- flush: pending updates into the tiles, G0 mirror and diagonal brought up to date ----
+      apply_pending<C, EXACT>(g, eh, ch, k, ty, tx);
+      if (t < NP) {
+        const int o = (cur * 2 + spin) * NP + t, on = ((cur ^ 1) * 2 + spin) * NP + t;
+        sm.dh[on] = rank1<EXACT>(sm.dh[o], sm.e[o], sm.c[o]);
+        sm.e[on] = 0.0; sm.c[on] = 0.0;
+      }
+      store_tile<C>(stage, g, ty, tx);
+      __syncthreads();
+      cur ^= 1; k = 0;
+      RCLK(ck.flush += clock64() - c2;)
+    }
+  }
+  RCLK(const long long c3 = clock64();)
+  apply_pending<C, EXACT>(g, eh, ch, k, ty, tx);
+  RCLK(ck.flush += clock64() - c3;)
+}
+
+
 template <class C, bool EXACT, bool PHYS>
 __global__ void __launch_bounds__(C::THREADS, (C::THREADS == 256) ? 2 : 4) sweep_reg_kernel(const SweepParams p) {
   constexpr int TR = C::TR, TC = C::TC, NP = C::NP, GY = C::GY, TPS = C::TPS;
@@ -650,11 +866,14 @@ __global__ void __launch_bounds__(C::THREADS, (C::THREADS == 256) ? 2 : 4) sweep
   double* Gc = p.G + ((size_t)chain * 2 + spin) * NP * NP;
   double g[TR][TC];
   int n_accepted = 0;
+  RCLK(RegClocks ck = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; long long cka;)
 
   if (!p.do_recompute) load_tile<C>(Gc, NP, g, ty, tx);
 
   for (int sweep = 0; sweep < p.n_sweeps; ++sweep) {
+    RCLK(cka = clock64();)
     if (p.do_recompute) recompute_g<C>(g, sm, p, field, p.recompute_l0, spin, t, ty, tx);
+    RCLK(ck.rec += clock64() - cka;)
     for (int step = p.step_lo; step < p.step_hi; ++step) {
       const int l = L - 1 - step;
       const long long base = (((long long)chain * p.buf_sweeps + p.buf_sweep0 + sweep) * p.buf_steps + (step - p.buf_step0)) * N;
@@ -664,6 +883,7 @@ __global__ void __launch_bounds__(C::THREADS, (C::THREADS == 256) ? 2 : 4) sweep
         wrap_g<C, PHYS>(g, sm, p, spin, ty, tx);
       }
       if (p.do_propose) {
+        RCLK(cka = clock64();)
         __syncthreads();             // previous users of sm.u / sm.h are done
         if (tid < NP) {
           sm.h[tid] = field[l * NP + tid];
@@ -676,15 +896,26 @@ __global__ void __launch_bounds__(C::THREADS, (C::THREADS == 256) ? 2 : 4) sweep
           sm.u[tid] = u;
         }
         // propose_slice starts with its own barrier after the diagonal / buffer setup
+#if LQMC_REG_DELAYED
+        propose_slice_delayed<C, EXACT, PHYS>(g, sm, p, base, spin, t, ty, tx, n_accepted
+#ifdef LQMC_PHASE_CLOCKS
+                                              , ck
+#endif
+                                              );
+#else
         propose_slice<C, EXACT, PHYS>(g, sm, p, base, spin, t, ty, tx, n_accepted);
+#endif
         __syncthreads();
         if (tid < NP) field[l * NP + tid] = sm.h[tid];
+        RCLK(ck.slice += clock64() - cka;)
       }
       if (p.do_wrap && l > 0 && !(p.skip_last_wrap && step == p.step_hi - 1)) {
+        RCLK(cka = clock64();)
         __syncthreads();
         if (tid < NP) sm.hn[tid] = field[(l - 1) * NP + tid];
         // wrap_g's first barrier (after store_tile) also publishes sm.hn
         wrap_g<C, PHYS>(g, sm, p, spin, ty, tx);
+        RCLK(ck.wrap += clock64() - cka;)
       }
     }
     if (p.measure) {
@@ -720,6 +951,18 @@ __global__ void __launch_bounds__(C::THREADS, (C::THREADS == 256) ? 2 : 4) sweep
       *reinterpret_cast<double2*>(Gc + row * NP + 2 * tx + 2 * C::GX * q) = make_double2(g[a][2 * q], g[a][2 * q + 1]);
   }
   if (tid == 0 && n_accepted) p.n_acc[chain] += n_accepted;
+#ifdef LQMC_PHASE_CLOCKS
+  if (tid == 0 && N >= 8) {     // tools/reg_split.py reads these back through lqmc_get_measurements
+    double* ob = p.obs_sum + (size_t)chain * 3 * N;
+    ob[0] = (double)ck.rec; ob[1] = (double)ck.slice; ob[2] = (double)ck.wrap; ob[3] = (double)ck.scan;
+    ob[4] = (double)ck.build; ob[5] = (double)ck.flush; ob[6] = (double)ck.flips; ob[7] = (double)ck.scans;
+    ob[8] = (double)ck.b_load; ob[9] = (double)ck.b_chain; ob[10] = (double)ck.b_vec; ob[11] = (double)ck.b_bar;
+  }
+  if (tid == NP && N >= 16) {   // a column-role thread
+    double* ob = p.obs_sum + (size_t)chain * 3 * N;
+    ob[12] = (double)ck.b_load; ob[13] = (double)ck.b_chain; ob[14] = (double)ck.b_vec; ob[15] = (double)ck.b_bar;
+  }
+#endif
 }
 
 // ---- device self-test of the shared-reciprocal division ---------------------------------------------------

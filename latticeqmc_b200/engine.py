@@ -261,7 +261,7 @@ class SweepEngine:
         """`n_sweeps` x `LatticeQMC._update_step_det` (lqmc.py:236-259) as one of the reference's det-mode loops:
         `old_det` from `get_m(0, +-1)` at the start of the call (`old_det=None`), a caller-supplied value per chain, or
         `"carry"` = the value the previous call left on the device; `measure` adds `inv(get_m(0, +-1))` after every sweep
-        (lqmc.py:293-297).  `uniforms` as in `sweep`.  N <= 64."""
+        (lqmc.py:293-297).  `uniforms` as in `sweep`.  Any N (N > 64: matrices in global memory, slow)."""
         if isinstance(old_det, str):
             if old_det != "carry":
                 raise ValueError("old_det must be None, 'carry' or per-chain values")

@@ -14,7 +14,7 @@ same accept/reject sequence as the reference.  `rng="philox"` uses the device co
 instead (no host traffic).
 
 `det_mode=True` (the reference's validation sampler, lqmc.py:236-299: every proposal rebuilds `get_m(l, +-1)` and
-takes two determinants) runs on the device too (`SweepEngine.sweep_det`, `csrc/sweep_det.cuh`; N <= 64).  One
+takes two determinants) runs on the device too (`SweepEngine.sweep_det`, `csrc/sweep_det.cuh`).  One
 `warmup_loop_det` / `measure_loop_det` call is one engine call, so `old_det` is initialised from `get_m(0, +-1)` at the
 start of each loop and carried through it exactly as in the reference (loops longer than 256 MiB of uniforms are split,
 and `old_det` is re-initialised from the field at the split).

@@ -152,10 +152,33 @@ def test_old_det_is_carried_between_calls(golden):
             eng.sweep_det(1, uni[:, :1], old_det="carry")            # nothing to carry yet
 
 
-def test_det_mode_rejects_large_lattices():
-    from latticeqmc_b200 import EngineError
-    ham = so.ideal_ring_kinetic(100, t=1.0, mu=2.0)
-    dtau, lamb, exp_k = so.set_beta_constants(ham, 4.0, 1.0, 4)
-    with _engine(exp_k, lamb, 4) as eng:
-        with pytest.raises(EngineError):
-            eng.sweep_det(1)
+@pytest.mark.parametrize("n,lt,chains", [(100, 4, 2), (260, 2, 1)])
+def test_det_mode_large_lattice_against_oracle(n, lt, chains):
+    """The reference's det mode has no size limit (lqmc.py:236-259).  Above 64 sites the device kernel keeps its matrices
+    in a global-memory workspace: ring of 100 sites (one thread per row element) and of 260 sites (more rows than threads
+    per spin group), two chains, one sweep + one measured sweep against the oracle on the same uniforms."""
+    # determinants ~ 2^N per spin: mu = 0 and a small beta keep det(M_up) det(M_dn) inside the double range at N = 260
+    ham = so.ideal_ring_kinetic(n, t=1.0, mu=0.0 if n > 200 else 2.0)
+    dtau, lamb, exp_k = so.set_beta_constants(ham, 4.0, 0.2 if n > 200 else 0.4, lt)
+    fields = np.stack([so.initial_field(n, lt, 500 + c) for c in range(chains)])
+    uni = np.random.RandomState(9).rand(chains, 2, lt, n)
+    with _engine(exp_k, lamb, lt, n_chains=chains, trace=True) as eng:
+        eng.set_field(fields)
+        eng.sweep_det(1, uni[:, :1])
+        a1, r1 = eng.get_trace()
+        eng.sweep_det(1, uni[:, 1:], measure=True, old_det="carry")
+        a2, r2 = eng.get_trace()
+        out = eng.get_field()
+        m = eng.get_measurements()
+    for c in range(chains):
+        h = fields[c].copy()
+        old = so.det_product(h, exp_k, lamb)
+        for s, (a, r) in enumerate(((a1, r1), (a2, r2))):
+            old, rr, aa = so.det_update_step(h, exp_k, lamb, old, uni[c, s])
+            assert np.array_equal(aa, a[c, 0]), f"chain {c} sweep {s}"
+            assert _rel(r[c, 0], rr) <= RTOL_RATIO
+        assert np.array_equal(h, out[c])
+        gu = np.linalg.inv(so.get_m(h, exp_k, lamb, 0, +1))
+        gd = np.linalg.inv(so.get_m(h, exp_k, lamb, 0, -1))
+        assert np.max(np.abs(m["g_sum"][c, 0] - gu)) <= RTOL * np.max(np.abs(gu))
+        assert np.max(np.abs(m["g_sum"][c, 1] - gd)) <= RTOL * np.max(np.abs(gd))
