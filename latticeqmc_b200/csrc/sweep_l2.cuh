@@ -45,6 +45,12 @@ constexpr int L2_GY = 16, L2_GX = 16;                  // thread grid inside a b
 #ifndef LQMC_L2_STAGING_TMA
 #define LQMC_L2_STAGING_TMA 1                          // 1: cp.async.bulk.tensor (tensor maps, 128-byte swizzle) + full / empty mbarrier ring; 0: LDGSTS (cp.async) ring
 #endif
+#ifndef LQMC_FLUSHX_EPF
+#define LQMC_FLUSHX_EPF 1
+#endif
+#ifndef LQMC_L2_WIDE_TILE
+#define LQMC_L2_WIDE_TILE 1
+#endif
 constexpr int L2_STAGES = 3;                           // operand-panel ring depth of the LDGSTS variant
 constexpr int L2_TMA_STAGES = 4;                       // ... of the TMA variant: 4 x (8 KB + 16 KB) dense, swizzled panels
 constexpr int L2_TMA_SUB = 16 * 16 * 8;                // one TMA box: 16 k-rows x 16 doubles (128-byte rows, the swizzle span) = 2 KB
@@ -446,18 +452,23 @@ struct L2GemmTmaCtx { uint32_t stage0; uint32_t bars; uint32_t* pipe_iter; const
 // CL: the launch runs one chain per thread-block cluster.  A template flag, not a run-time test: with the cluster code compiled into
 // the one-CTA kernel its slice phase ran 20 % slower (1.77 -> 2.12 ms; cause not isolated - not the barrier instructions, not the
 // L2-only loads, not the run-time chunk ranges), so the one-CTA instantiation contains none of it.
-template <bool CL>
+// NT: 8-column fragments per warp in N.  4: block tile 64 x 128 (two CTAs per SM, 128 registers).  6: block tile 64 x 192, warp tile
+// 32 x 48 - the one-CTA-per-SM sizes (NP > 384, 255 registers): 10 fragment loads per 24 DMMAs instead of 8 per 16, and 576 = 3 x 192
+// has no half tile at the right edge (with 128-column tiles 9 of its 45 tiles were half empty but took a full tile's time).
+template <bool CL, int NT>
 __device__ __noinline__ void l2_gemm_tma_sub(const L2TmaOperand opA, const L2TmaOperand opB, double* __restrict__ Cout, int NP, int spin,
                                              const L2Epilogue ep, const L2GemmTmaCtx sm) {
   const int ccs = CL ? sm.cs : 1, ccrank = CL ? sm.crank : 0;
   constexpr int S = L2_TMA_STAGES;
-  constexpr uint32_t STAGE_BYTES = (L2_BM + L2_BN) * L2_BK * sizeof(double);       // 24 KB
+  constexpr int BN = 32 * NT;                                                      // 4 warps in N x NT fragments of 8 columns
+  static_assert(NT == 4 || NT == 6, "warp tile 32 x 32 or 32 x 48");
+  constexpr uint32_t STAGE_BYTES = (L2_BM + BN) * L2_BK * sizeof(double);          // 24 KB / 32 KB
   constexpr uint32_t A_BYTES = L2_BM * L2_BK * sizeof(double);                     // 8 KB: boxes 0..3 of a stage, then 8 B boxes
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp >> 2, wn = warp & 3;            // 2 x 4 warps, 32 x 32 warp tiles
   const int lr = lane >> 2, lk = lane & 3;
   const int nk = NP / L2_BK;
-  const int tiles_n = (NP + L2_BN - 1) / L2_BN, n_tiles_all = (NP / L2_BM) * tiles_n;
+  const int tiles_n = (NP + BN - 1) / BN, n_tiles_all = (NP / L2_BM) * tiles_n;
   // block tiles crank, crank + cs, ... of the GEMM are this CTA's (cs = 1: all of them)
   const int n_tiles = (n_tiles_all - ccrank + ccs - 1) / ccs;
   const int n_panels = n_tiles * nk;
@@ -480,8 +491,8 @@ __device__ __noinline__ void l2_gemm_tma_sub(const L2TmaOperand opA, const L2Tma
 #pragma unroll
     for (int b = 0; b < L2_BM / 16; ++b) tma_load_2d(dst + b * L2_TMA_SUB, opA.map, ti * L2_BM + 16 * b, opA.row0 + kp * L2_BK, bar);
 #pragma unroll
-    for (int b = 0; b < L2_BN / 16; ++b)
-      tma_load_2d(dst + A_BYTES + b * L2_TMA_SUB, opB.map, tj * L2_BN + 16 * b, opB.row0 + kp * L2_BK, bar);
+    for (int b = 0; b < BN / 16; ++b)
+      tma_load_2d(dst + A_BYTES + b * L2_TMA_SUB, opB.map, tj * BN + 16 * b, opB.row0 + kp * L2_BK, bar);
   };
   // the producer is ONE elected lane of warp 0 (elect.sync: the compiler then knows the TMA operands are uniform and emits the
   // UTMALDG straight from uniform registers instead of a per-lane loop)
@@ -497,34 +508,41 @@ __device__ __noinline__ void l2_gemm_tma_sub(const L2TmaOperand opA, const L2Tma
   }
   // per-lane fragment offsets inside a stage (bytes): box of the fragment's 16-column group, k-row 2 lk (+ step parity, + 8 for
   // the second half), 16-byte chunk XOR (row & 7), 8-byte half
-  uint32_t offA[4], offB[4];                       // [m] / [n] for step parity 0, k-half 0; the other three steps are derived
+  uint32_t offA[4], offB[NT];                      // [m] / [n] for step parity 0, k-half 0; the other three steps are derived
 #pragma unroll
   for (int m = 0; m < 4; ++m) {
     const int e = 8 * (m & 1) + lr;                // element inside the 16-wide box
     offA[m] = (uint32_t)((2 * wm + (m >> 1)) * L2_TMA_SUB + (2 * lk) * 128 + (((e >> 1) ^ (2 * lk)) << 4) + ((e & 1) << 3));
-    offB[m] = A_BYTES + (uint32_t)((2 * wn + (m >> 1)) * L2_TMA_SUB + (2 * lk) * 128 + (((e >> 1) ^ (2 * lk)) << 4) + ((e & 1) << 3));
+  }
+#pragma unroll
+  for (int n = 0; n < NT; ++n) {
+    const int e = 8 * (n & 1) + lr;
+    offB[n] = A_BYTES + (uint32_t)(((NT / 2) * wn + (n >> 1)) * L2_TMA_SUB + (2 * lk) * 128 + (((e >> 1) ^ (2 * lk)) << 4) + ((e & 1) << 3));
   }
   int q = 0;
   for (int tl = 0; tl < n_tiles; ++tl) {
     const int t = ccrank + tl * ccs;
     const int ti = t / tiles_n, tj = t - ti * tiles_n;
-    const int i0 = ti * L2_BM, j0 = tj * L2_BN;
-    const bool w_ok = j0 + 32 * wn < NP;                 // half tile at the right edge: this warp owns no columns (warp-uniform)
-    double acc[4][4][2];
+    const int i0 = ti * L2_BM, j0 = tj * BN, jw = j0 + 8 * NT * wn;     // jw: first column of this warp
+    const bool w_ok = jw < NP;                           // partial tile at the right edge: this warp owns no columns (warp-uniform)
+    double acc[4][NT][2];
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
-      for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+      for (int b = 0; b < NT; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
     // field bytes of this thread's rows / column pairs for the epilogue scales: in flight during the main loop
     int hr[4] = {1, 1, 1, 1};
-    unsigned hc[4] = {0x0101u, 0x0101u, 0x0101u, 0x0101u};
+    unsigned hc[NT];
+#pragma unroll
+    for (int n = 0; n < NT; ++n) hc[n] = 0x0101u;
     if (ep.hrow) {
 #pragma unroll
       for (int m = 0; m < 4; ++m) hr[m] = ep.hrow[i0 + 32 * wm + 8 * m + lr];
     }
     if (ep.hcol && w_ok) {
 #pragma unroll
-      for (int n = 0; n < 4; ++n) hc[n] = *reinterpret_cast<const unsigned short*>(ep.hcol + j0 + 32 * wn + 8 * n + 2 * lk);
+      for (int n = 0; n < NT; ++n)
+        if (NT == 4 || jw + 8 * n < NP) hc[n] = *reinterpret_cast<const unsigned short*>(ep.hcol + jw + 8 * n + 2 * lk);
     }
     for (int kp = 0; kp < nk; ++kp, ++q) {
       const uint32_t qg = q0 + (uint32_t)q;
@@ -538,15 +556,15 @@ __device__ __noinline__ void l2_gemm_tma_sub(const L2TmaOperand opA, const L2Tma
         for (int s4 = 0; s4 < 4; ++s4) {
           // step s4: k-rows 8 (s4 >> 1) + 2 lk + (s4 & 1); an odd row flips bit 0 of the chunk XOR, the second half adds 1 KB
           const uint32_t delta = (uint32_t)((s4 >> 1) * 1024 + (s4 & 1) * 128), flip = (uint32_t)((s4 & 1) << 4);
-          double a[4], b[4];
+          double a[4], b[NT];
 #pragma unroll
           for (int m = 0; m < 4; ++m) a[m] = *reinterpret_cast<const double*>(base + ((offA[m] + delta) ^ flip));
 #pragma unroll
-          for (int n = 0; n < 4; ++n) b[n] = *reinterpret_cast<const double*>(base + ((offB[n] + delta) ^ flip));
+          for (int n = 0; n < NT; ++n) b[n] = *reinterpret_cast<const double*>(base + ((offB[n] + delta) ^ flip));
 #pragma unroll
           for (int m = 0; m < 4; ++m)
 #pragma unroll
-            for (int n = 0; n < 4; ++n) dmma884(acc[m][n], a[m], b[n]);
+            for (int n = 0; n < NT; ++n) dmma884(acc[m][n], a[m], b[n]);
         }
       }
       __syncwarp();
@@ -564,9 +582,9 @@ __device__ __noinline__ void l2_gemm_tma_sub(const L2TmaOperand opA, const L2Tma
     }
     if (!w_ok) continue;
     // epilogue: element (row, col) = acc[m][n][s]
-    double cs[4][2];
+    double cs[NT][2];
 #pragma unroll
-    for (int n = 0; n < 4; ++n) {
+    for (int n = 0; n < NT; ++n) {
       cs[n][0] = ep.hcol ? hs_v2((int8_t)(hc[n] & 0xff), spin, ep.col_inv, sm.exp_pl, sm.exp_ml) : 1.0;
       cs[n][1] = ep.hcol ? hs_v2((int8_t)(hc[n] >> 8), spin, ep.col_inv, sm.exp_pl, sm.exp_ml) : 1.0;
     }
@@ -575,8 +593,9 @@ __device__ __noinline__ void l2_gemm_tma_sub(const L2TmaOperand opA, const L2Tma
       const int row = i0 + 32 * wm + 8 * m + lr;
       const double rs = hs_v2((int8_t)hr[m], spin, ep.row_inv, sm.exp_pl, sm.exp_ml);
 #pragma unroll
-      for (int n = 0; n < 4; ++n) {
-        const int col0 = j0 + 32 * wn + 8 * n + 2 * lk;
+      for (int n = 0; n < NT; ++n) {
+        const int col0 = jw + 8 * n + 2 * lk;
+        if (NT != 4 && jw + 8 * n >= NP) continue;       // fragment past the right edge (zero-filled operands): nothing to store
 #pragma unroll
         for (int s2 = 0; s2 < 2; ++s2) {
           double v = acc[m][n][s2];
@@ -610,7 +629,7 @@ __device__ __forceinline__ L2TmaOperand l2_tma_operand(const L2TmaMaps& m, const
 
 // One staging variant per binary: with both compiled in, every GEMM call site marshals two argument sets around two calls and the
 // one-launch sweep ran 2 % slower (274 vs 269 ms) whichever path was taken at run time.
-template <bool CL>
+template <bool CL, int NT = 4>
 __device__ __forceinline__ void l2_gemm(const double* __restrict__ At, const double* __restrict__ B, double* __restrict__ Cout, int NP, int spin,
                                         const L2Epilogue& ep, const SweepParams& p, L2Smem& sm) {
 #if LQMC_L2_STAGING_TMA
@@ -618,7 +637,7 @@ __device__ __forceinline__ void l2_gemm(const double* __restrict__ At, const dou
   c.stage0 = smem_u32(sm.U); c.bars = smem_u32(sm.full); c.pipe_iter = reinterpret_cast<uint32_t*>(sm.hist + 62);
   c.stage_ptr = reinterpret_cast<const unsigned char*>(sm.U);
   c.exp_pl = p.exp_pl; c.exp_ml = p.exp_ml; c.cs = sm.cs; c.crank = sm.crank;
-  l2_gemm_tma_sub<CL>(l2_tma_operand(*sm.maps, At, NP), l2_tma_operand(*sm.maps, B, NP), Cout, NP, spin, ep, c);
+  l2_gemm_tma_sub<CL, NT>(l2_tma_operand(*sm.maps, At, NP), l2_tma_operand(*sm.maps, B, NP), Cout, NP, spin, ep, c);
   if (CL && sm.cs > 1) l2_cluster_sync(sm.cs);    // every tile of the product is in memory before any CTA reads it as an operand
 #else
   L2GemmCtx c;
@@ -1763,75 +1782,113 @@ __device__ __forceinline__ void tmem_free_cta_x(uint32_t base) {
 template <bool EXACT, int CPT, int KDX>
 __device__ void l2_flush_tmemx(double* __restrict__ Gc, int NP, int nd, double* __restrict__ U3, uint32_t tm_my, double* __restrict__ Tc, int wlo) {
   const int tid = threadIdx.x;
-  bool jv[CPT], jw[CPT];
-#pragma unroll
-  for (int q = 0; q < CPT; ++q) {
-    jv[q] = tid + L2_THREADS * q < NP;       // warp-uniform: NP is a multiple of 64
-    jw[q] = jv[q] && (unsigned)(tid + L2_THREADS * q - wlo) < (unsigned)L2_COLWIN;
-  }
+  // NP is a multiple of 64, so whether a thread has a column in window q is warp-uniform; windows 0 .. CPT-2 are always full and
+  // only the last one is partial (N = 576: warps 0 and 1 own a third column, warps 2 - 7 do not).  The warps without it run the
+  // CPT - 1 instantiation of the pass instead of multiplying zeros (a third of their FP64 instructions at N = 576).
+  const bool last_col = tid + L2_THREADS * (CPT - 1) < NP;
   if (nd < KDX) {
     for (int spin = 0; spin < 2; ++spin)
       for (int m = nd; m < KDX; ++m)
         for (int r = tid; r < NP; r += L2_THREADS) U3[((size_t)spin * KDX + m) * NP + r] = 0.0;
     __syncthreads();
   }
-  for (int spin = 0; spin < 2; ++spin) {
-    double cj[CPT][KDX];
+  auto pass = [&](auto ca_tag) {
+    constexpr int CA = decltype(ca_tag)::value;      // columns of this thread
+    bool jw[CA];
 #pragma unroll
-    for (int q = 0; q < CPT; ++q)
+    for (int q = 0; q < CA; ++q) jw[q] = (unsigned)(tid + L2_THREADS * q - wlo) < (unsigned)L2_COLWIN;
+    for (int spin = 0; spin < 2; ++spin) {
+      double cj[CA][KDX];
 #pragma unroll
-      for (int m0 = 0; m0 < KDX; m0 += 8) {
-        double v[8];
-        tmem_ld_f64x8(tm_my + 2 * ((2 * q + spin) * KDX + m0), v);
+      for (int q = 0; q < CA; ++q)
 #pragma unroll
-        for (int t = 0; t < 8; ++t) cj[q][m0 + t] = (m0 + t < nd) ? v[t] : 0.0;
-      }
-    double* const col = Gc + (size_t)spin * NP * NP + tid;
-    double* const colT = Tc + (size_t)spin * NP * NP + (size_t)tid * NP;
-    const double* const Us = U3 + (size_t)spin * KDX * NP;
-    double nxt[CPT][8];
+        for (int m0 = 0; m0 < KDX; m0 += 8) {
+          double v[8];
+          tmem_ld_f64x8(tm_my + 2 * ((2 * q + spin) * KDX + m0), v);
 #pragma unroll
-    for (int q = 0; q < CPT; ++q)
+          for (int t = 0; t < 8; ++t) cj[q][m0 + t] = (m0 + t < nd) ? v[t] : 0.0;
+        }
+      double* const col = Gc + (size_t)spin * NP * NP + tid;
+      double* const colT = Tc + (size_t)spin * NP * NP + (size_t)tid * NP;
+      const double* const Us = U3 + (size_t)spin * KDX * NP;
+      double nxt[CA][8];
 #pragma unroll
-      for (int r = 0; r < 8; ++r) nxt[q][r] = jv[q] ? col[(size_t)r * NP + L2_THREADS * q] : 0.0;
-    for (int r0 = 0; r0 < NP; r0 += 8) {
-      double g[CPT][8];
+      for (int q = 0; q < CA; ++q)
 #pragma unroll
-      for (int q = 0; q < CPT; ++q)
+        for (int r = 0; r < 8; ++r) nxt[q][r] = col[(size_t)r * NP + L2_THREADS * q];
+      for (int r0 = 0; r0 < NP; r0 += 8) {
+        double g[CA][8];
 #pragma unroll
-        for (int r = 0; r < 8; ++r) g[q][r] = nxt[q][r];
-      if (r0 + 8 < NP) {
+        for (int q = 0; q < CA; ++q)
 #pragma unroll
-        for (int q = 0; q < CPT; ++q)
+          for (int r = 0; r < 8; ++r) g[q][r] = nxt[q][r];
+        if (r0 + 8 < NP) {
+          // the next chunk's G0 is requested before this chunk's arithmetic (volatile: pinned here)
 #pragma unroll
-          for (int r = 0; r < 8; ++r) nxt[q][r] = jv[q] ? col[(size_t)(r0 + 8 + r) * NP + L2_THREADS * q] : 0.0;
-      }
+          for (int q = 0; q < CA; ++q)
 #pragma unroll
-      for (int m = 0; m < KDX; ++m) {
-        const double* ur = Us + (size_t)m * NP + r0;
+            for (int r = 0; r < 8; ++r)
+              asm volatile("ld.global.f64 %0, [%1];" : "=d"(nxt[q][r]) : "l"(col + (size_t)(r0 + 8 + r) * NP + L2_THREADS * q) : "memory");
+        }
+#if LQMC_FLUSHX_EPF
+        // e values of update m + 1 requested (volatile: pinned in this order) before the arithmetic of update m: with 8 warps per SM a
+        // broadcast LDS.128 issued right before its use is not covered by the 12 FP64 instructions of the previous one
+        // (clock64 at N = 576: flush 57.2 K -> 50.3 K clocks per flip)
+        double2 ebuf[2][4];
+        {
+          const uint32_t ua = smem_u32(Us + r0);
 #pragma unroll
-        for (int r = 0; r < 8; r += 2) {
-          const double2 e = *reinterpret_cast<const double2*>(ur + r);
+          for (int r = 0; r < 4; ++r)
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(ebuf[0][r].x), "=d"(ebuf[0][r].y) : "r"(ua + 16 * r) : "memory");
+        }
 #pragma unroll
-          for (int q = 0; q < CPT; ++q) {
-            g[q][r] = rank1<EXACT>(g[q][r], e.x, cj[q][m]);
-            g[q][r + 1] = rank1<EXACT>(g[q][r + 1], e.y, cj[q][m]);
+        for (int m = 0; m < KDX; ++m) {
+          if (m + 1 < KDX) {
+            const uint32_t ua = smem_u32(Us + (size_t)(m + 1) * NP + r0);
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+              asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(ebuf[(m + 1) & 1][r].x), "=d"(ebuf[(m + 1) & 1][r].y) : "r"(ua + 16 * r) : "memory");
+          }
+#pragma unroll
+          for (int r = 0; r < 8; r += 2) {
+            const double2 e = ebuf[m & 1][r >> 1];
+#pragma unroll
+            for (int q = 0; q < CA; ++q) {
+              g[q][r] = rank1<EXACT>(g[q][r], e.x, cj[q][m]);
+              g[q][r + 1] = rank1<EXACT>(g[q][r + 1], e.y, cj[q][m]);
+            }
+          }
+        }
+#else
+#pragma unroll
+        for (int m = 0; m < KDX; ++m) {
+          const double* ur = Us + (size_t)m * NP + r0;
+#pragma unroll
+          for (int r = 0; r < 8; r += 2) {
+            const double2 e = *reinterpret_cast<const double2*>(ur + r);
+#pragma unroll
+            for (int q = 0; q < CA; ++q) {
+              g[q][r] = rank1<EXACT>(g[q][r], e.x, cj[q][m]);
+              g[q][r + 1] = rank1<EXACT>(g[q][r + 1], e.y, cj[q][m]);
+            }
+          }
+        }
+#endif
+#pragma unroll
+        for (int q = 0; q < CA; ++q) {
+#pragma unroll
+          for (int r = 0; r < 8; ++r) col[(size_t)(r0 + r) * NP + L2_THREADS * q] = g[q][r];
+          if (jw[q]) {
+            double* dst = colT + (size_t)(L2_THREADS * q) * NP + r0;
+#pragma unroll
+            for (int r = 0; r < 8; r += 2) *reinterpret_cast<double2*>(dst + r) = make_double2(g[q][r], g[q][r + 1]);
           }
         }
       }
-#pragma unroll
-      for (int q = 0; q < CPT; ++q) {
-#pragma unroll
-        for (int r = 0; r < 8; ++r)
-          if (jv[q]) col[(size_t)(r0 + r) * NP + L2_THREADS * q] = g[q][r];
-        if (jw[q]) {
-          double* dst = colT + (size_t)(L2_THREADS * q) * NP + r0;
-#pragma unroll
-          for (int r = 0; r < 8; r += 2) *reinterpret_cast<double2*>(dst + r) = make_double2(g[q][r], g[q][r + 1]);
-        }
-      }
     }
-  }
+  };
+  if (last_col) pass(std::integral_constant<int, CPT>{});
+  else pass(std::integral_constant<int, CPT - 1>{});
   __syncthreads();
 }
 
@@ -1867,6 +1924,11 @@ __device__ void l2_propose_slice_tmemx(double* __restrict__ Gc, double* __restri
   int wlo = 0;
   __syncthreads();
   int nd = 0, i0 = 0, cur = 0;
+#ifdef LQMC_PHASE_CLOCKS
+  long long tk_scan = 0, tk_build = 0, tk_flush = 0, tk0 = clock64();
+  const long long tk_begin = tk0;
+  unsigned long long gt0; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt0));
+#endif
   while (i0 < N) {
     const double* dcur = sm.d + cur * 2 * NP;
     double* dnxt = sm.d + (cur ^ 1) * 2 * NP;
@@ -1892,6 +1954,9 @@ __device__ void l2_propose_slice_tmemx(double* __restrict__ Gc, double* __restri
       p.tr_acc[trace_base + i] = (lane == first) ? 1 : 0;
     }
     if (!ballot) { i0 += 32; continue; }
+#ifdef LQMC_PHASE_CLOCKS
+    { const long long tk1 = clock64(); tk_scan += tk1 - tk0; tk0 = tk1; }
+#endif
     const int is = i0 + first;
     gu = __shfl_sync(0xffffffffu, gu, first);
     gd = __shfl_sync(0xffffffffu, gd, first);
@@ -1978,10 +2043,24 @@ __device__ void l2_propose_slice_tmemx(double* __restrict__ Gc, double* __restri
     cur ^= 1;
     __syncthreads();
     if (tid == 0) sm.h[is] = (int8_t)(-hs);     // after the barrier: no warp is still scanning site `is`
+#ifdef LQMC_PHASE_CLOCKS
+    { const long long tk1 = clock64(); tk_build += tk1 - tk0; tk0 = tk1; }
+#endif
     if (nd == KDX) { wlo = is + 1; l2_flush_tmemx<EXACT, CPT, KDX>(Gc, NP, nd, U3, tm_my, Tc, wlo); nd = 0; }
+#ifdef LQMC_PHASE_CLOCKS
+    { const long long tk1 = clock64(); tk_flush += tk1 - tk0; tk0 = tk1; }
+#endif
     i0 = is + 1;
   }
   if (nd > 0) l2_flush_tmemx<EXACT, CPT, KDX>(Gc, NP, nd, U3, tm_my, Tc, NP);
+#ifdef LQMC_PHASE_CLOCKS
+  { const long long tk1 = clock64(); tk_flush += tk1 - tk0;
+    if (tid == 0) { double* ob = p.obs_sum + (size_t)blockIdx.x * 3 * N; ob[0] = (double)tk_scan; ob[1] = (double)tk_build; ob[2] = (double)tk_flush; ob[3] = (double)n_accepted;
+      for (int q = 4; q < 15; ++q) ob[q] = 0.0;
+      unsigned smid; asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+      unsigned long long gt1; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt1));
+      ob[8] = (double)(gt0 & 0xffffffffffffull); ob[9] = (double)(gt1 & 0xffffffffffffull); ob[10] = (double)smid; ob[11] = (double)(tk1 - tk_begin); } }
+#endif
 }
 
 // ---- Gauss-Jordan inverse in memory (both spins in lockstep, in place), partial pivoting, delayed updates ----------
@@ -2120,7 +2199,7 @@ __device__ void l2_gj_inverse(double* __restrict__ Gc, int NP, int KD, L2Smem& s
 }
 
 // ---- sweep-start G = inv(I + prod B) in memory ----------------------------------------------------------------
-template <bool CL>
+template <bool CL, int NT = 4>
 __device__ void l2_recompute(double* __restrict__ Gc, double* __restrict__ Tc, int NP, int KD, const int8_t* field, int l0,
                              const SweepParams& p, L2Smem& sm, int* piv_global) {
   const int L = p.n_slices;
@@ -2151,7 +2230,7 @@ __device__ void l2_recompute(double* __restrict__ Gc, double* __restrict__ Tc, i
       ep.hcol = field + (size_t)l * NP;
       ep.transposed_out = (m != L - 1);
       ep.add_identity = (m == L - 1);
-      l2_gemm<CL>(cur, p.E, oth, NP, spin, ep, p, sm);
+      l2_gemm<CL, NT>(cur, p.E, oth, NP, spin, ep, p, sm);
       double* t = cur; cur = oth; oth = t;
     }
   }
@@ -2161,18 +2240,18 @@ __device__ void l2_recompute(double* __restrict__ Gc, double* __restrict__ Tc, i
 }
 
 // ---- wrap from slice l to l-1 ------------------------------------------------------------------------------
-template <bool PHYS, bool CL>
+template <bool PHYS, bool CL, int NT = 4>
 __device__ void l2_wrap(double* __restrict__ Gc, double* __restrict__ Tc, int NP, const int8_t* hprev, const SweepParams& p, L2Smem& sm) {
   for (int spin = 0; spin < 2; ++spin) {
     double* G = Gc + (size_t)spin * NP * NP;
     double* T = Tc + (size_t)spin * NP * NP;
     L2Epilogue e1;
     e1.transposed_out = true;
-    l2_gemm<CL>(PHYS ? p.Eit : p.Et, G, T, NP, spin, e1, p, sm);           // T^T = (E G)^T   (or E^-1 G)
+    l2_gemm<CL, NT>(PHYS ? p.Eit : p.Et, G, T, NP, spin, e1, p, sm);           // T^T = (E G)^T   (or E^-1 G)
     L2Epilogue e2;
     e2.hrow = hprev; e2.hcol = hprev;
     e2.row_inv = PHYS; e2.col_inv = !PHYS;
-    l2_gemm<CL>(T, PHYS ? p.E : p.Ei, G, NP, spin, e2, p, sm);              // G = D (E G E^-1) D^-1
+    l2_gemm<CL, NT>(T, PHYS ? p.E : p.Ei, G, NP, spin, e2, p, sm);              // G = D (E G E^-1) D^-1
   }
 }
 
@@ -2190,6 +2269,8 @@ struct L2Params {
 // (384 < NP <= 512: 2 x depth 24; 512 < NP <= 768: 3 x depth 16 where it fits; one CTA per SM at those sizes)
 template <bool EXACT, bool PHYS, int TMEM, bool CL = false>
 __global__ void __launch_bounds__(L2_THREADS, TMEM >= 2 ? 1 : 2) sweep_l2_kernel(const __grid_constant__ L2Params lp) {
+  // GEMM warp tile: 32 x 48 (block tile 64 x 192) in the one-CTA-per-SM instantiations, which may use 255 registers
+  constexpr int GNT = (TMEM >= 2 && LQMC_L2_WIDE_TILE) ? 6 : 4;
   extern __shared__ __align__(1024) unsigned char smem_raw[];       // 128-byte-swizzled TMA boxes need 1 KB-aligned stages
   const SweepParams& p = lp.p;
   const int NP = lp.NP, KD = lp.KD;
@@ -2223,14 +2304,14 @@ __global__ void __launch_bounds__(L2_THREADS, TMEM >= 2 ? 1 : 2) sweep_l2_kernel
 #else
 #define LQMC_KT(acc)
 #endif
-    if (p.do_recompute) l2_recompute<CL>(Gc, Tc, NP, KD, field, p.recompute_l0, p, sm, piv);
+    if (p.do_recompute) l2_recompute<CL, GNT>(Gc, Tc, NP, KD, field, p.recompute_l0, p, sm, piv);
     LQMC_KT(kt_rec)
     for (int step = p.step_lo; step < p.step_hi; ++step) {
       const int l = L - 1 - step;
       const long long base = (((long long)chain * p.buf_sweeps + p.buf_sweep0 + sweep) * p.buf_steps + (step - p.buf_step0)) * N;
       if (p.wrap_first && step == p.step_lo) {
         __syncthreads();
-        l2_wrap<PHYS, CL>(Gc, Tc, NP, field + (size_t)l * NP, p, sm);
+        l2_wrap<PHYS, CL, GNT>(Gc, Tc, NP, field + (size_t)l * NP, p, sm);
       }
       if (p.do_propose) {
         __syncthreads();
@@ -2254,7 +2335,7 @@ __global__ void __launch_bounds__(L2_THREADS, TMEM >= 2 ? 1 : 2) sweep_l2_kernel
       }
       if (p.do_wrap && l > 0 && !(p.skip_last_wrap && step == p.step_hi - 1)) {
         __syncthreads();
-        l2_wrap<PHYS, CL>(Gc, Tc, NP, field + (size_t)(l - 1) * NP, p, sm);
+        l2_wrap<PHYS, CL, GNT>(Gc, Tc, NP, field + (size_t)(l - 1) * NP, p, sm);
         LQMC_KT(kt_wrap)
       }
     }
@@ -2313,7 +2394,9 @@ inline int l2_alloc(L2Workspace& w, int n_sites, int np, int n_slices, int n_cha
     const size_t region = (size_t)4 * kd * np;
     const int mode = (np <= 2 * L2_THREADS) ? 2 : 3;
     const size_t need = (size_t)2 * (mode == 2 ? 24 : 16) * np;
-    w.tmem_mode = (need <= region) ? mode : 0;
+    // these instantiations stage 64 x 192 GEMM tiles: 4 stages x 32 KB alias the U / W region
+    const size_t wide_stages = (size_t)L2_TMA_STAGES * L2_BK * (L2_BM + 192);
+    w.tmem_mode = (need <= region && wide_stages <= region) ? mode : 0;
   }
   return 0;
 }
