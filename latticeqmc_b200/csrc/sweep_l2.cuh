@@ -45,6 +45,12 @@ constexpr int L2_GY = 16, L2_GX = 16;                  // thread grid inside a b
 #ifndef LQMC_L2_STAGING_TMA
 #define LQMC_L2_STAGING_TMA 1                          // 1: cp.async.bulk.tensor (tensor maps, 128-byte swizzle) + full / empty mbarrier ring; 0: LDGSTS (cp.async) ring
 #endif
+#ifndef LQMC_L2_ROTATE_PRODUCER
+#define LQMC_L2_ROTATE_PRODUCER 1
+#endif
+#ifndef LQMC_L2_COL_OUTER
+#define LQMC_L2_COL_OUTER false     // measured neutral to slightly negative (cfg4 271.5 vs 270.9 ms, cfg5 2076 vs 2064 ms): the operand re-reads hit L2 either way
+#endif
 #ifndef LQMC_FLUSHX_EPF
 #define LQMC_FLUSHX_EPF 1
 #endif
@@ -52,6 +58,7 @@ constexpr int L2_GY = 16, L2_GX = 16;                  // thread grid inside a b
 #define LQMC_L2_WIDE_TILE 1
 #endif
 constexpr int L2_STAGES = 3;                           // operand-panel ring depth of the LDGSTS variant
+constexpr int L2_TMA_STAGES_MAX = 8;                   // mbarrier slots per direction
 constexpr int L2_TMA_STAGES = 4;                       // ... of the TMA variant: 4 x (8 KB + 16 KB) dense, swizzled panels
 constexpr int L2_TMA_SUB = 16 * 16 * 8;                // one TMA box: 16 k-rows x 16 doubles (128-byte rows, the swizzle span) = 2 KB
 constexpr size_t L2_GEMM_DOUBLES_LDGSTS = (size_t)3 * 16 * (64 + 128 + 8);
@@ -88,6 +95,7 @@ struct L2Workspace {
   double* T = nullptr;      // [chain][2][NP][NP] second matrix buffer (two-GEMM wrap, running product)
   int kd = 0;               // delay depth the shared-memory budget allows
   int tmem_mode = 0;        // tensor-memory slice path that fits the shared-memory region: 0 none, 1 NP <= 256, 2 384 < NP <= 512, 3 512 < NP <= 768
+  int gemm_stages = 4;      // operand-ring depth of the 64 x 192 GEMMs (tmem_mode 2 / 3 kernels)
   size_t smem = 0;          // dynamic shared memory per CTA
   L2TmaMaps maps;           // tensor maps of the GEMM operands (built at the first launch)
   int last_cluster = 1;     // CTAs per chain of the most recent launch
@@ -172,7 +180,7 @@ struct L2Smem {
     hist = red_v + 16;
     ring = hist + 64;
     full = reinterpret_cast<uint64_t*>(ring + L2_RING * 2 * L2_KDT);     // [0..3] "panel landed", [4..7] "panel consumed"
-    red_i = reinterpret_cast<int*>(full + 8);
+    red_i = reinterpret_cast<int*>(full + 16);    // full[0..7] "panel landed", full[8..15] "panel consumed"
     h = reinterpret_cast<int8_t*>(red_i + 16);
     hn = h + NP;
   }
@@ -182,7 +190,7 @@ inline size_t l2_smem_bytes(int NP, int KD, int ns = 2, bool with_gemm = true) {
   size_t vec = (size_t)2 * ns * KD * NP;
   const size_t gemm = L2_GEMM_DOUBLES;
   if (with_gemm && vec < gemm) vec = gemm;
-  return (vec + 5 * (size_t)NP + 16 + 64 + L2_RING * 2 * L2_KDT + 8) * sizeof(double) + 16 * sizeof(int) + 2 * (size_t)NP + 16;
+  return (vec + 5 * (size_t)NP + 16 + 64 + L2_RING * 2 * L2_KDT + 16) * sizeof(double) + 16 * sizeof(int) + 2 * (size_t)NP + 16;
 }
 
 // ---- tiled GEMM:  C = A * B  with A given k-major (At[k*NP + i] = A[i][k]) and B row-major ------------------
@@ -194,6 +202,11 @@ struct L2Epilogue {
   bool col_inv = false;
   bool transposed_out = false;
   bool add_identity = false;
+  // Tile order.  Every tile re-fetches its operand panels (nothing is kept between tiles), so an operand is read NP / BM (B) or
+  // NP / BN (A) times per product.  The chains' own matrices do not fit L2 together (cfg4: 592 MB, cfg5: 785 MB against 126 MB);
+  // the exp(-+dtau K) matrices are shared and do.  Row tiles outer (default) re-reads an A row tile back to back - right when A is
+  // the chain's matrix; column tiles outer does the same for B (the first product of the wrap, B = G).
+  bool col_outer = false;
 };
 
 // (dmma884, the FP64 tensor-core MMA wrapper, lives in sweep_reg.cuh)
@@ -459,7 +472,9 @@ template <bool CL, int NT>
 __device__ __noinline__ void l2_gemm_tma_sub(const L2TmaOperand opA, const L2TmaOperand opB, double* __restrict__ Cout, int NP, int spin,
                                              const L2Epilogue ep, const L2GemmTmaCtx sm) {
   const int ccs = CL ? sm.cs : 1, ccrank = CL ? sm.crank : 0;
-  constexpr int S = L2_TMA_STAGES;
+  // ring depth: 4 stages of 24 KB with the 64 x 128 tile (two CTAs per SM); the one-CTA-per-SM kernels take as many 32 KB stages as
+  // the U / W region holds (up to L2_TMA_STAGES_MAX; the host writes the count next to the panel counter)
+  const int S = (NT == 4) ? L2_TMA_STAGES : (int)sm.pipe_iter[1];
   constexpr int BN = 32 * NT;                                                      // 4 warps in N x NT fragments of 8 columns
   static_assert(NT == 4 || NT == 6, "warp tile 32 x 32 or 32 x 48");
   constexpr uint32_t STAGE_BYTES = (L2_BM + BN) * L2_BK * sizeof(double);          // 24 KB / 32 KB
@@ -468,11 +483,11 @@ __device__ __noinline__ void l2_gemm_tma_sub(const L2TmaOperand opA, const L2Tma
   const int wm = warp >> 2, wn = warp & 3;            // 2 x 4 warps, 32 x 32 warp tiles
   const int lr = lane >> 2, lk = lane & 3;
   const int nk = NP / L2_BK;
-  const int tiles_n = (NP + BN - 1) / BN, n_tiles_all = (NP / L2_BM) * tiles_n;
+  const int tiles_n = (NP + BN - 1) / BN, tiles_m = NP / L2_BM, n_tiles_all = tiles_m * tiles_n;
   // block tiles crank, crank + cs, ... of the GEMM are this CTA's (cs = 1: all of them)
   const int n_tiles = (n_tiles_all - ccrank + ccs - 1) / ccs;
   const int n_panels = n_tiles * nk;
-  const uint32_t full0 = sm.bars, empty0 = sm.bars + 8u * S;
+  const uint32_t full0 = sm.bars, empty0 = sm.bars + 8u * L2_TMA_STAGES_MAX;
   const unsigned char* const stage_ptr = sm.stage_ptr;
   __builtin_assume(__isShared(stage_ptr));
   // generic-proxy writes of this CTA (previous epilogue, flush, the U / W region the stages alias) before async-proxy traffic
@@ -484,7 +499,7 @@ __device__ __noinline__ void l2_gemm_tma_sub(const L2TmaOperand opA, const L2Tma
   auto issue = [&](int q) {
     const int tl = q / nk, kp = q - tl * nk;
     const int t = ccrank + tl * ccs;
-    const int ti = t / tiles_n, tj = t - ti * tiles_n;
+    const int ti = ep.col_outer ? t % tiles_m : t / tiles_n, tj = ep.col_outer ? t / tiles_m : t - ti * tiles_n;
     const int st = (q0 + q) % S;
     const uint32_t dst = sm.stage0 + (uint32_t)st * STAGE_BYTES, bar = full0 + 8u * st;
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(STAGE_BYTES) : "memory");
@@ -522,7 +537,7 @@ __device__ __noinline__ void l2_gemm_tma_sub(const L2TmaOperand opA, const L2Tma
   int q = 0;
   for (int tl = 0; tl < n_tiles; ++tl) {
     const int t = ccrank + tl * ccs;
-    const int ti = t / tiles_n, tj = t - ti * tiles_n;
+    const int ti = ep.col_outer ? t % tiles_m : t / tiles_n, tj = ep.col_outer ? t / tiles_m : t - ti * tiles_n;
     const int i0 = ti * L2_BM, j0 = tj * BN, jw = j0 + 8 * NT * wn;     // jw: first column of this warp
     const bool w_ok = jw < NP;                           // partial tile at the right edge: this warp owns no columns (warp-uniform)
     double acc[4][NT][2];
@@ -572,7 +587,11 @@ __device__ __noinline__ void l2_gemm_tma_sub(const L2TmaOperand opA, const L2Tma
       // The producer refills the stage panel q-1 sat in.  It does so AFTER its own warp's work on panel q: by then the other
       // warps have long released panel q-1, so the wait does not hold warp 0 back (issued before the compute it made warp 0 the
       // last warp of every panel: 0.93 ms per wrap against 0.78 with the cp.async ring, one CTA per SM).
-      if (warp == 0 && q + S - 1 < n_panels) {
+      // (r2) The producer role rotates over the warps: with warp 0 issuing every panel (an empty-barrier wait, 12 - 16 TMA instructions
+      // and their coordinates: several hundred clocks of one warp's dependent instruction stream) warp 0's loop was the slowest
+      // stage of the pipeline and the other seven warps waited for it on the "full" barrier - 28 % of the stall samples at N = 576,
+      // whatever the ring depth and the number of chains.
+      if (warp == (LQMC_L2_ROTATE_PRODUCER ? (q & 7) : 0) && q + S - 1 < n_panels) {
         if (elected()) {
           if (q >= 1) mbar_wait_u32(empty0 + 8u * ((qg - 1) % S), ((qg - 1) / S) & 1u);
           issue(q + S - 1);
@@ -2247,6 +2266,7 @@ __device__ void l2_wrap(double* __restrict__ Gc, double* __restrict__ Tc, int NP
     double* T = Tc + (size_t)spin * NP * NP;
     L2Epilogue e1;
     e1.transposed_out = true;
+    e1.col_outer = LQMC_L2_COL_OUTER;
     l2_gemm<CL, NT>(PHYS ? p.Eit : p.Et, G, T, NP, spin, e1, p, sm);           // T^T = (E G)^T   (or E^-1 G)
     L2Epilogue e2;
     e2.hrow = hprev; e2.hcol = hprev;
@@ -2263,6 +2283,7 @@ struct L2Params {
   int* piv;       // [chain][2][NP] scratch
   int NP, KD;
   int cluster;    // CTAs per chain (thread-block cluster size; 1 = one CTA per chain)
+  int gemm_stages;   // ring depth of the 64 x 192 GEMMs (one-CTA-per-SM kernels)
 };
 
 // TMEM: 0 shared-memory slice path; 1 tensor-memory path, one column per thread (NP <= 256); 2 / 3 several columns per thread
@@ -2291,8 +2312,9 @@ __global__ void __launch_bounds__(L2_THREADS, TMEM >= 2 ? 1 : 2) sweep_l2_kernel
   if ((smem_u32(smem_raw) & 1023u) != 0) __trap();          // the swizzled TMA boxes assume 1 KB-aligned stages
 #endif
   if (tid == 0) {
-    for (int s0 = 0; s0 < L2_TMA_STAGES; ++s0) { mbar_init(sm.full + s0, 1); mbar_init(sm.full + L2_TMA_STAGES + s0, L2_THREADS / 32); }
-    *reinterpret_cast<uint32_t*>(sm.hist + 62) = 0;          // panels consumed so far (TMA staging: stage / phase parity)
+    for (int s0 = 0; s0 < L2_TMA_STAGES_MAX; ++s0) { mbar_init(sm.full + s0, 1); mbar_init(sm.full + L2_TMA_STAGES_MAX + s0, L2_THREADS / 32); }
+    reinterpret_cast<uint32_t*>(sm.hist + 62)[0] = 0;        // panels consumed so far (TMA staging: stage / phase parity)
+    reinterpret_cast<uint32_t*>(sm.hist + 62)[1] = (uint32_t)lp.gemm_stages;   // ring depth of the wide-tile GEMMs
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -2395,8 +2417,11 @@ inline int l2_alloc(L2Workspace& w, int n_sites, int np, int n_slices, int n_cha
     const int mode = (np <= 2 * L2_THREADS) ? 2 : 3;
     const size_t need = (size_t)2 * (mode == 2 ? 24 : 16) * np;
     // these instantiations stage 64 x 192 GEMM tiles: 4 stages x 32 KB alias the U / W region
-    const size_t wide_stages = (size_t)L2_TMA_STAGES * L2_BK * (L2_BM + 192);
-    w.tmem_mode = (need <= region && wide_stages <= region) ? mode : 0;
+    const size_t wide_stage = (size_t)L2_BK * (L2_BM + 192);        // doubles per 32 KB stage
+    w.tmem_mode = (need <= region && L2_TMA_STAGES * wide_stage <= region) ? mode : 0;
+    int st = (int)(region / wide_stage);
+    if (const char* env = getenv("LQMC_L2_GEMM_STAGES")) { const int v = atoi(env); if (v >= 2 && v <= st) st = v; }   // experiments
+    w.gemm_stages = st > L2_TMA_STAGES_MAX ? L2_TMA_STAGES_MAX : st;
   }
   return 0;
 }
@@ -2446,6 +2471,7 @@ inline int launch_l2(L2Workspace& w, const SweepParams& p, int np, uint32_t flag
   lp.maps = w.maps;
   lp.p = p; lp.T = w.T; lp.NP = np; lp.KD = w.kd;
   lp.cluster = 1;
+  lp.gemm_stages = w.gemm_stages;
   lp.use_tmem = p.do_propose ? w.tmem_mode : 0;
   if (const char* env = getenv("LQMC_L2_SLICE_PATH")) { if (strcmp(env, "smem") == 0) lp.use_tmem = 0; }     // experiments
   lp.piv = reinterpret_cast<int*>(w.T + (size_t)p.n_chains * 2 * np * np);
