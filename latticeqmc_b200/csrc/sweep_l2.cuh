@@ -45,6 +45,9 @@ constexpr int L2_GY = 16, L2_GX = 16;                  // thread grid inside a b
 #ifndef LQMC_L2_STAGING_TMA
 #define LQMC_L2_STAGING_TMA 1                          // 1: cp.async.bulk.tensor (tensor maps, 128-byte swizzle) + full / empty mbarrier ring; 0: LDGSTS (cp.async) ring
 #endif
+#ifndef LQMC_FLUSH2_EPF
+#define LQMC_FLUSH2_EPF 0
+#endif
 #ifndef LQMC_L2_ROTATE_PRODUCER
 #define LQMC_L2_ROTATE_PRODUCER 1
 #endif
@@ -1046,6 +1049,32 @@ __device__ __forceinline__ void tmem_ld_quad_wait(TmemQuad& q) {
 #endif
 template <bool EXACT, int R>
 __device__ __forceinline__ void l2_flush_apply4(double (&g)[R][2], const TmemQuad& c, const double* __restrict__ ur, int NP) {
+#if LQMC_FLUSH2_EPF
+  // all e values of the quad requested up front (volatile: pinned), then the arithmetic
+  double2 eb[4][R / 2];
+  {
+    const uint32_t ua = smem_u32(ur);
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int r = 0; r < R / 2; ++r)
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(eb[q][r].x), "=d"(eb[q][r].y) : "r"(ua + (uint32_t)(q * NP + 2 * r) * 8u) : "memory");
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const double c0 = __hiloint2double((int)c.r[2 * q + 1], (int)c.r[2 * q]);
+    const double c1 = __hiloint2double((int)c.r[8 + 2 * q + 1], (int)c.r[8 + 2 * q]);
+#pragma unroll
+    for (int r = 0; r < R; r += 2) {
+      const double2 e = eb[q][r >> 1];
+      g[r][0] = rank1<EXACT>(g[r][0], e.x, c0);
+      g[r][1] = rank1<EXACT>(g[r][1], e.x, c1);
+      g[r + 1][0] = rank1<EXACT>(g[r + 1][0], e.y, c0);
+      g[r + 1][1] = rank1<EXACT>(g[r + 1][1], e.y, c1);
+    }
+  }
+  return;
+#endif
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const double c0 = __hiloint2double((int)c.r[2 * q + 1], (int)c.r[2 * q]);
