@@ -97,6 +97,28 @@ def test_free_running_sweep_23x23():
     assert _close(gg[0], gu, 1e-9) and _close(gg[1], gd, 1e-9)
 
 
+@pytest.mark.parametrize("size,n_pad", [(25, 640), (26, 704)])
+def test_free_running_sweep_partial_wide_tiles(size, n_pad):
+    """The one-CTA-per-SM kernels multiply on 64 x 192 block tiles; 640 = 3 x 192 + 64 and 704 = 3 x 192 + 128 end in a partial column
+    tile (fragments past the edge are zero-filled by the TMA unit and not stored), and their third column window of the flush is
+    owned by 4 / 6 of the 8 warps.  N = 625 and 676, U=4, beta=0.2, L=2: one free-running sweep against the oracle."""
+    ham = so.ideal_square_kinetic(size, 1.0, 2.0)
+    n, lt = size * size, 2
+    dtau, lamb, exp_k = so.set_beta_constants(ham, 4.0, 0.2, lt)
+    field = so.initial_field(n, lt, seed=500 + size)
+    uni = np.random.RandomState(size).rand(1, 1, lt, n)
+    with _engine(exp_k, lamb, lt, n_chains=1, trace=True) as eng:
+        assert eng.info()["n_pad"] == n_pad
+        eng.set_field(field[None])
+        eng.sweep(1, uni, measure=True)
+        acc, ratio = eng.get_trace()
+        gg, ff = eng.get_g()[0], eng.get_field()[0]
+    h = field.copy()
+    gu, gd, r, a = so.update_step(h, exp_k, lamb, uni[0, 0])
+    assert np.array_equal(a, acc[0, 0]) and np.array_equal(h, ff)
+    assert _close(gg[0], gu, 1e-9) and _close(gg[1], gd, 1e-9)
+
+
 @pytest.mark.parametrize("arith", ["exact", "fma"])
 def test_free_running_sweep_10x10(arith):
     """N = 100 (padded to 128), U=4, beta=1, L=10: two full free-running sweeps of 3 chains, one kernel
