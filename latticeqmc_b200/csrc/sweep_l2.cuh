@@ -45,6 +45,12 @@ constexpr int L2_GY = 16, L2_GX = 16;                  // thread grid inside a b
 #ifndef LQMC_L2_STAGING_TMA
 #define LQMC_L2_STAGING_TMA 1                          // 1: cp.async.bulk.tensor (tensor maps, 128-byte swizzle) + full / empty mbarrier ring; 0: LDGSTS (cp.async) ring
 #endif
+#ifndef LQMC_L2_MERGE_RC
+#define LQMC_L2_MERGE_RC 1
+#endif
+#ifndef LQMC_L2_ZPAD
+#define LQMC_L2_ZPAD 1
+#endif
 #ifndef LQMC_FLUSH2_EPF
 #define LQMC_FLUSH2_EPF 0
 #endif
@@ -1643,6 +1649,16 @@ __device__ __noinline__ int l2_propose_slice_tmem_sub(const L2SliceArgs a) {
         for (int q = 0; q < 4; ++q)
 #pragma unroll
           for (int spin = 0; spin < 2; ++spin) ui[spin][q] = U3[((size_t)spin * L2_KDT + m0 + q) * NP + is];
+#if LQMC_L2_ZPAD && LQMC_L2_MERGE_RC
+        double uj[2][4], ws[2][4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+          for (int spin = 0; spin < 2; ++spin) {
+            uj[spin][q] = U3[((size_t)spin * L2_KDT + m0 + q) * NP + j];
+            ws[spin][q] = wsrc[spin * L2_KDT + m0 + q];
+          }
+#endif
         tmem_ld_quad_wait(wq);
         double wj[2][4];
 #pragma unroll
@@ -1656,12 +1672,23 @@ __device__ __noinline__ int l2_propose_slice_tmem_sub(const L2SliceArgs a) {
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
+#if LQMC_L2_ZPAD
+          // slots nd .. of the quad hold e = c = +0 (written with slot nd & ~3, below): applying them changes no bit
+#pragma unroll
+          for (int spin = 0; spin < 2; ++spin) {
+            row[spin] = rank1<EXACT>(row[spin], ui[spin][q], wj[spin][q]);
+#if LQMC_L2_MERGE_RC
+            col[spin] = rank1<EXACT>(col[spin], uj[spin][q], ws[spin][q]);     // four independent chains per thread
+#endif
+          }
+#else
           const bool valid = m0 + q < nd;
 #pragma unroll
           for (int spin = 0; spin < 2; ++spin) {
             const double r = rank1<EXACT>(row[spin], ui[spin][q], wj[spin][q]);
             row[spin] = valid ? r : row[spin];
           }
+#endif
         }
       }
       // c vectors need the row only: park them in tensor memory (and the ring) while the column is still being rebuilt
@@ -1677,9 +1704,18 @@ __device__ __noinline__ int l2_propose_slice_tmem_sub(const L2SliceArgs a) {
         }
         tmem_st_f64(tm_my + 2 * (spin * L2_KDT + nd), cv[spin]);
         if (pubme) myring[spin * L2_KDT + nd] = cv[spin];
+#if LQMC_L2_ZPAD
+        if ((nd & 3) == 0) {       // a new quad of history slots: its other three read as +0 until they are written
+#pragma unroll
+          for (int q = 1; q < 4; ++q) {
+            tmem_st_f64(tm_my + 2 * (spin * L2_KDT + nd + q), 0.0);
+            if (pubme) myring[spin * L2_KDT + nd + q] = 0.0;
+          }
+        }
+#endif
       }
       // Column rebuild: e_m[j] (own entry) times the flipped site's c history (ring / owner-published, broadcast)
-      for (int m0 = 0; m0 < nd; m0 += 4) {
+      for (int m0 = 0; m0 < ((LQMC_L2_ZPAD && LQMC_L2_MERGE_RC) ? 0 : nd); m0 += 4) {
         double uj[2][4], ws[2][4];
 #pragma unroll
         for (int q = 0; q < 4; ++q)
@@ -1690,12 +1726,17 @@ __device__ __noinline__ int l2_propose_slice_tmem_sub(const L2SliceArgs a) {
           }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
+#if LQMC_L2_ZPAD
+#pragma unroll
+          for (int spin = 0; spin < 2; ++spin) col[spin] = rank1<EXACT>(col[spin], uj[spin][q], ws[spin][q]);
+#else
           const bool valid = m0 + q < nd;
 #pragma unroll
           for (int spin = 0; spin < 2; ++spin) {
             const double r = rank1<EXACT>(col[spin], uj[spin][q], ws[spin][q]);
             col[spin] = valid ? r : col[spin];
           }
+#endif
         }
       }
 #ifdef LQMC_PHASE_CLOCKS
@@ -1718,6 +1759,12 @@ __device__ __noinline__ int l2_propose_slice_tmem_sub(const L2SliceArgs a) {
           e = ((j == is) ? (1.0 - col[spin]) : -col[spin]) * fac;
         }
         U3[((size_t)spin * L2_KDT + nd) * NP + j] = e;
+#if LQMC_L2_ZPAD
+        if ((nd & 3) == 0) {
+#pragma unroll
+          for (int q = 1; q < 4; ++q) U3[((size_t)spin * L2_KDT + nd + q) * NP + j] = 0.0;
+        }
+#endif
 #ifdef LQMC_PHASE_CLOCKS
         if (spin == 1) { if (e + cv[1] == 1.2345e300) tk_b3 -= 1; const long long tk1 = clock64(); tk_b3 += tk1 - tk0; }
 #endif
