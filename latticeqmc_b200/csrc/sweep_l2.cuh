@@ -45,6 +45,9 @@ constexpr int L2_GY = 16, L2_GX = 16;                  // thread grid inside a b
 #ifndef LQMC_L2_STAGING_TMA
 #define LQMC_L2_STAGING_TMA 1                          // 1: cp.async.bulk.tensor (tensor maps, 128-byte swizzle) + full / empty mbarrier ring; 0: LDGSTS (cp.async) ring
 #endif
+#ifndef LQMC_L2_EARLY_RCP
+#define LQMC_L2_EARLY_RCP 1
+#endif
 #ifndef LQMC_L2_MERGE_RC
 #define LQMC_L2_MERGE_RC 1
 #endif
@@ -1580,6 +1583,24 @@ __device__ __noinline__ int l2_propose_slice_tmem_sub(const L2SliceArgs a) {
     // G0 row / column of the flipped site, both spins: from the prefetch slots when the site is one of them.  The strided
     // column gather is issued first: it is the longest latency of the flip and is not needed before the column loop below.
     double row[2] = {0.0, 0.0}, col[2] = {0.0, 0.0};
+#if LQMC_L2_EARLY_RCP
+    // the flip's denominators and their reciprocals depend on the scan only: formed here, their latency (reciprocal + Newton steps,
+    // ~30 dependent instructions for both spins) runs under the G0 loads instead of after the history loops
+    double den_s[2], rcp_s[2];
+#pragma unroll
+    for (int spin = 0; spin < 2; ++spin) {
+      const double gs = spin ? gd : gu;
+      if (!PHYS) {
+        const double gamma = spin ? fu : fd;
+        den_s[spin] = __dadd_rn(1.0, __dadd_rn(__dmul_rn(-gamma, gs), gamma));
+        rcp_s[spin] = __drcp_rn(den_s[spin]);
+      } else {
+        const double delta = spin ? fd : fu;
+        den_s[spin] = __dadd_rn(1.0, __dmul_rn(__dsub_rn(1.0, gs), delta));
+        rcp_s[spin] = delta / den_s[spin];
+      }
+    }
+#endif
     const int dpf = is - pf_base;                  // CTA-uniform
     if (PF >= 1 && dpf >= 0 && dpf < PF) {
 #pragma unroll
@@ -1746,6 +1767,11 @@ __device__ __noinline__ int l2_propose_slice_tmem_sub(const L2SliceArgs a) {
       for (int spin = 0; spin < 2; ++spin) {
         const double gs = spin ? gd : gu;
         double e;
+#if LQMC_L2_EARLY_RCP
+        (void)gs;
+        if (!PHYS) e = EXACT ? div_shared_rcp(col[spin], den_s[spin], rcp_s[spin], div_safe(den_s[spin])) : col[spin] * rcp_s[spin];
+        else e = ((j == is) ? (1.0 - col[spin]) : -col[spin]) * rcp_s[spin];
+#else
         if (!PHYS) {
           const double gamma = spin ? fu : fd;
           const double ci = __dadd_rn(__dmul_rn(-gamma, gs), gamma);
@@ -1758,6 +1784,7 @@ __device__ __noinline__ int l2_propose_slice_tmem_sub(const L2SliceArgs a) {
           const double fac = delta / rr;
           e = ((j == is) ? (1.0 - col[spin]) : -col[spin]) * fac;
         }
+#endif
         U3[((size_t)spin * L2_KDT + nd) * NP + j] = e;
 #if LQMC_L2_ZPAD
         if ((nd & 3) == 0) {
