@@ -63,6 +63,12 @@ constexpr int L2_GY = 16, L2_GX = 16;                  // thread grid inside a b
 #ifndef LQMC_L2_COL_OUTER
 #define LQMC_L2_COL_OUTER false     // measured neutral to slightly negative (cfg4 271.5 vs 270.9 ms, cfg5 2076 vs 2064 ms): the operand re-reads hit L2 either way
 #endif
+#ifndef LQMC_FLUSH2_L2PF
+#define LQMC_FLUSH2_L2PF 0
+#endif
+#ifndef LQMC_FLUSHX_L2PF
+#define LQMC_FLUSHX_L2PF 1      // chunks ahead of the register prefetch that are pulled into L2 (0: off)
+#endif
 #ifndef LQMC_FLUSHX_EPF
 #define LQMC_FLUSHX_EPF 1
 #endif
@@ -1159,6 +1165,16 @@ __device__ __noinline__ void l2_flush_tmem2_single(double* __restrict__ Gc, int 
 #pragma unroll
       for (int r = 0; r < R; ++r) { nxt[r][0] = cn[(size_t)r * NP]; nxt[r][1] = cn[(size_t)r * NP + 128]; }
     }
+#if LQMC_FLUSH2_L2PF
+    if (ch + 1 + LQMC_FLUSH2_L2PF < 2 * CH && (tid & 15) == 0) {     // one lane per 128-byte line
+      const double* cp = chunk_ptr(ch + 1 + LQMC_FLUSH2_L2PF);
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(cp + (size_t)r * NP));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(cp + (size_t)r * NP + 128));
+      }
+    }
+#endif
     for (int m0 = 0; m0 < nd8; m0 += 8) {
       const bool last = m0 + 8 >= nd8;
       tmem_ld_quad_wait(ca);
@@ -1952,6 +1968,17 @@ __device__ void l2_flush_tmemx(double* __restrict__ Gc, int NP, int nd, double* 
             for (int r = 0; r < 8; ++r)
               asm volatile("ld.global.f64 %0, [%1];" : "=d"(nxt[q][r]) : "l"(col + (size_t)(r0 + 8 + r) * NP + L2_THREADS * q) : "memory");
         }
+#if LQMC_FLUSHX_L2PF
+        // ... and the chunk after that is pulled into L2 (no destination register: more HBM requests in flight than the 24
+        // register loads per thread allow); one lane per 128-byte line
+        if (r0 + 8 * (1 + LQMC_FLUSHX_L2PF) < NP && (tid & 15) == 0) {
+#pragma unroll
+          for (int q = 0; q < CA; ++q)
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(col + (size_t)(r0 + 8 * (1 + LQMC_FLUSHX_L2PF) + r) * NP + L2_THREADS * q));
+        }
+#endif
 #if LQMC_FLUSHX_EPF
         // e values of update m + 1 requested (volatile: pinned in this order) before the arithmetic of update m: with 8 warps per SM a
         // broadcast LDS.128 issued right before its use is not covered by the 12 FP64 instructions of the previous one
