@@ -2367,9 +2367,17 @@ __device__ void l2_recompute(double* __restrict__ Gc, double* __restrict__ Tc, i
           G[(size_t)r * NP + c] = p.E[(size_t)r * NP + c] * hs_v(hl[c], spin, p) + (r == c ? 1.0 : 0.0);
     } else {
       // first factor, stored k-major (transposed): cur[c][r] = E[r][c] * v_c   (columns split over the cluster)
-      for (int c = (CL ? sm.crank : 0); c < NP; c += (CL ? sm.cs : 1)) {
-        const double v = hs_v(hl[c], spin, p);
-        for (int r = tid; r < NP; r += L2_THREADS) cur[(size_t)c * NP + r] = p.Et[(size_t)c * NP + r] * v;
+      // eight independent loads per thread in flight (one column per iteration was a chain of NP dependent load -> store round
+      // trips: 3.7 % of the stall samples of the N = 576 launch, profiles/r02l_cfg5_ncu_lines.txt)
+      const int c_first = CL ? sm.crank : 0, c_step = CL ? sm.cs : 1;
+      for (int c0 = c_first; c0 < NP; c0 += 8 * c_step) {
+        for (int r = tid; r < NP; r += L2_THREADS) {
+          double x[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) { const int c = c0 + q * c_step; x[q] = (c < NP) ? p.Et[(size_t)c * NP + r] : 0.0; }
+#pragma unroll
+          for (int q = 0; q < 8; ++q) { const int c = c0 + q * c_step; if (c < NP) cur[(size_t)c * NP + r] = x[q] * hs_v(hl[c], spin, p); }
+        }
       }
     }
     if (CL) l2_cluster_sync(sm.cs); else __syncthreads();
